@@ -1,0 +1,8 @@
+#!/bin/bash
+# Builds libeig.so for sm_100a in-tree (the .so is git-ignored but travels to the GPU box).
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+$NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --fmad=false \
+      -Xcompiler -fPIC -shared ${EIG_NVCC_EXTRA:-} -o ../libeig.so eig_api.cu -lcudart_static -ldl -lrt -lpthread
+echo "built $(cd .. && pwd)/libeig.so"

@@ -1,0 +1,610 @@
+// libeig.so: context, weight repacking, stage orchestration and the C ABI (include/eig.h).
+// Host-side C++ only orchestrates; every number on the hot path is produced by the CUDA kernels in
+// render.cuh / conv_simt.cuh / conv_tc.cuh / flow.cuh / score.cuh.  There is no CPU fallback.
+#ifdef EIG_EMU
+#include "cuda_emu.h"
+#endif
+#include "common.cuh"
+#include "render.cuh"
+#include "conv_simt.cuh"
+#include "flow.cuh"
+#include "score.cuh"
+#ifndef EIG_EMU
+#include "conv_tc.cuh"
+#endif
+#include "../../include/eig.h"
+
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace eig;
+#define TO_STREAM(p) ((cudaStream_t)(intptr_t)(p))
+
+static std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(expr)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(EIG_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+#define CKL()                                                                                         \
+    do {                                                                                              \
+        cudaError_t e_ = cudaGetLastError();                                                          \
+        if (e_ != cudaSuccess) return fail(EIG_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct LayerW {            // repacked weights of one PredNet layer (device)
+    float* convA = nullptr; float* convA_b = nullptr;   // [9][2C_{n-1}][Npad]
+    float* convP = nullptr; float* convP_b = nullptr;   // [9][R_n][Npad]
+    float* lstm = nullptr;  float* lstm_b = nullptr;    // [9][Ctot][4R], bias [4R] gate-interleaved
+    float* peep = nullptr;                              // [H][W][R][4]
+#ifndef EIG_EMU
+    TcWeights tcA, tcP, tcL;                            // tensor-core layouts (conv_tc.cuh)
+#endif
+};
+
+struct eig_ctx {
+    int device = 0, w = 0, h = 0, c_dim = 0, ch[4] = {0, 0, 0, 0}, cap = 0;
+    int H[4], W[4], ctot[4];
+    int conv_mode = EIG_CONV_SIMT;
+    bool have_w = false, have_grid = false;
+    double *xmat = nullptr, *ymat = nullptr;
+    LayerW lw[4];
+    // activations
+    float* X[4][2] = {{nullptr}};    // concat buffers [B][H][W][ctot]  (hi plane)
+    float* Xlo[4][2] = {{nullptr}};  // lo planes (layers >= 1 only)
+    float* cst[4] = {nullptr};       // cell state [B][H][W][R]
+    float* P[4] = {nullptr};         // predictions [B][H][W][C]
+    float* x_in = nullptr;           // [B][h][w][c]
+    unsigned char* img = nullptr;    // rendered [B][h][w][c]
+    unsigned char* frames = nullptr; // [3][B][h][w][c]
+    // flow
+    int n_levels = 1, lh[FLOW_MAX_LEVELS], lwid[FLOW_MAX_LEVELS];
+    unsigned char* gray[FLOW_MAX_LEVELS] = {nullptr};  // [2B][lh][lw]  (frame 1 images first, then frame 2)
+    short* deriv[FLOW_MAX_LEVELS] = {nullptr};         // [B][lh][lw][2]
+    float* eigmap = nullptr; int* eigmax = nullptr; unsigned long long* cand = nullptr;
+    float* corners = nullptr; int* ncorners = nullptr; float* next_pts = nullptr; unsigned char* status = nullptr;
+    float* vectors = nullptr; int* nvec = nullptr;
+    double* fitness = nullptr;
+    // host staging for eig_eval_host
+    void* d_blob = nullptr; size_t d_blob_cap = 0; long long* d_off = nullptr;
+    void* h_pin = nullptr; size_t h_pin_cap = 0;
+    cudaStream_t stream = 0;
+    std::vector<void*> allocs;
+};
+
+template <class T>
+static cudaError_t dalloc(eig_ctx* c, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
+    if (e == cudaSuccess) { c->allocs.push_back(q); *p = (T*)q; }
+    return e;
+}
+
+extern "C" const char* eig_last_error(void) { return g_err.c_str(); }
+extern "C" int eig_version(void) { return 100; }
+extern "C" int64_t eig_launch_count(void) { return launch_counter().n; }
+
+extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, const int channels[4], int max_genomes) {
+    if (!out || !channels || max_genomes <= 0) return fail(EIG_E_INVALID, "eig_create: null/invalid argument");
+    if (w % 8 || h % 8 || w <= 0 || h <= 0) return fail(EIG_E_INVALID, "eig_create: w and h must be positive multiples of 8");
+    if (c_dim != channels[0] || (c_dim != 1 && c_dim != 3)) return fail(EIG_E_INVALID, "eig_create: c_dim must equal channels[0] and be 1 or 3");
+    if (w <= FLOW_WIN || h <= FLOW_WIN) return fail(EIG_E_INVALID, "eig_create: image must be larger than the 50-px LK window");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(EIG_E_NODEVICE, "eig_create: no CUDA device visible; this engine has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(EIG_E_INVALID, "eig_create: bad device index");
+    CK(cudaSetDevice(device));
+    eig_ctx* c = new eig_ctx();
+    c->device = device; c->w = w; c->h = h; c->c_dim = c_dim; c->cap = max_genomes;
+    for (int n = 0; n < 4; ++n) { c->ch[n] = channels[n]; c->H[n] = h >> n; c->W[n] = w >> n; }
+    for (int n = 0; n < 4; ++n) c->ctot[n] = 2 * c->ch[n] + (n < 3 ? c->ch[n + 1] : 0) + c->ch[n];
+    const size_t B = max_genomes;
+    for (int n = 0; n < 4; ++n) {
+        const size_t px = B * c->H[n] * c->W[n];
+        for (int k = 0; k < 2; ++k) {
+            CK(dalloc(c, &c->X[n][k], px * c->ctot[n]));
+            if (n >= 1) CK(dalloc(c, &c->Xlo[n][k], px * c->ctot[n]));
+        }
+        CK(dalloc(c, &c->cst[n], px * c->ch[n]));
+        CK(dalloc(c, &c->P[n], px * c->ch[n]));
+    }
+    const size_t npx = B * w * h;
+    CK(dalloc(c, &c->x_in, npx * c_dim));
+    CK(dalloc(c, &c->img, npx * c_dim));
+    CK(dalloc(c, &c->frames, 3 * npx * c_dim));
+    // pyramid geometry (buildOpticalFlowPyramid: stop when the next level is <= the window)
+    c->n_levels = 1; c->lh[0] = h; c->lwid[0] = w;
+    for (int l = 1; l < FLOW_MAX_LEVELS; ++l) {
+        const int nw2 = (c->lwid[l - 1] + 1) / 2, nh2 = (c->lh[l - 1] + 1) / 2;
+        if (nw2 <= FLOW_WIN || nh2 <= FLOW_WIN) break;
+        c->lwid[l] = nw2; c->lh[l] = nh2; c->n_levels = l + 1;
+    }
+    for (int l = 0; l < c->n_levels; ++l) {
+        CK(dalloc(c, &c->gray[l], 2 * B * c->lh[l] * c->lwid[l]));
+        CK(dalloc(c, &c->deriv[l], 2 * B * c->lh[l] * c->lwid[l]));
+    }
+    CK(dalloc(c, &c->eigmap, npx)); CK(dalloc(c, &c->eigmax, B)); CK(dalloc(c, &c->cand, npx));
+    CK(dalloc(c, &c->corners, B * FLOW_MAX_CORNERS * 2)); CK(dalloc(c, &c->ncorners, B));
+    CK(dalloc(c, &c->next_pts, B * FLOW_MAX_CORNERS * 2)); CK(dalloc(c, &c->status, B * FLOW_MAX_CORNERS));
+    CK(dalloc(c, &c->vectors, B * FLOW_MAX_CORNERS * 4)); CK(dalloc(c, &c->nvec, B));
+    CK(dalloc(c, &c->fitness, B)); CK(dalloc(c, &c->d_off, B + 1));
+    CK(dalloc(c, &c->xmat, (size_t)w * h)); CK(dalloc(c, &c->ymat, (size_t)w * h));
+    *out = c;
+    return EIG_OK;
+}
+
+extern "C" void eig_destroy(eig_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+#ifndef EIG_EMU
+    for (int n = 0; n < 4; ++n) { tc_free(c->lw[n].tcA); tc_free(c->lw[n].tcP); tc_free(c->lw[n].tcL); }
+#endif
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->d_blob) cudaFree(c->d_blob);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    delete c;
+}
+
+extern "C" int eig_set_conv_mode(eig_ctx* c, int mode) {
+    if (!c) return fail(EIG_E_INVALID, "null ctx");
+    if (mode != EIG_CONV_SIMT && mode != EIG_CONV_TC) return fail(EIG_E_INVALID, "unknown conv mode");
+#ifdef EIG_EMU
+    if (mode == EIG_CONV_TC) return fail(EIG_E_INVALID, "tensor-core path is not available in the emulator build");
+#else
+    if (mode == EIG_CONV_TC && !tc_available()) return fail(EIG_E_INVALID, "tensor-core path unavailable: " + tc_unavailable_reason());
+#endif
+    c->conv_mode = mode;
+    return EIG_OK;
+}
+
+extern "C" int eig_set_grid(eig_ctx* c, const double* hx, const double* hy) {
+    if (!c || !hx || !hy) return fail(EIG_E_INVALID, "eig_set_grid: null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy(c->xmat, hx, sizeof(double) * c->w * c->h, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->ymat, hy, sizeof(double) * c->w * c->h, cudaMemcpyHostToDevice));
+    c->have_grid = true;
+    return EIG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+namespace {
+struct HostT { const float* p; int64_t s[4]; };
+typedef std::map<std::string, HostT> WMap;
+
+int need(const WMap& m, const std::string& k, int64_t s0, int64_t s1, int64_t s2, int64_t s3, const HostT** out) {
+    auto it = m.find(k);
+    if (it == m.end()) return fail(EIG_E_INVALID, "eig_load_weights: missing tensor " + k);
+    const int64_t* s = it->second.s;
+    if (s[0] != s0 || s[1] != s1 || s[2] != s2 || s[3] != s3) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "eig_load_weights: %s has shape (%lld,%lld,%lld,%lld), expected (%lld,%lld,%lld,%lld)",
+                 k.c_str(), (long long)s[0], (long long)s[1], (long long)s[2], (long long)s[3], (long long)s0,
+                 (long long)s1, (long long)s2, (long long)s3);
+        return fail(EIG_E_INVALID, buf);
+    }
+    *out = &it->second;
+    return EIG_OK;
+}
+template <class T>
+cudaError_t upload(eig_ctx* c, T** dst, const std::vector<T>& v) {
+    cudaError_t e = dalloc(c, dst, v.size());
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+// Chainer conv weight (Cout, Cin, 3, 3) -> dst[tap][cin_off + cin][Npad] at column col(n)
+void scatter_conv(std::vector<float>& dst, int cin_total, int npad, int cin_off, const HostT* t, int cout, int cin,
+                  int col_mul, int col_add) {
+    for (int n = 0; n < cout; ++n)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int tap = 0; tap < 9; ++tap)
+                dst[((size_t)tap * cin_total + cin_off + ci) * npad + n * col_mul + col_add] =
+                    t->p[((size_t)n * cin + ci) * 9 + tap];
+}
+}  // namespace
+
+extern "C" int eig_load_weights(eig_ctx* c, int nt, const char* const* names, const float* const* ptrs, const int64_t* shapes) {
+    if (!c || !names || !ptrs || !shapes || nt <= 0) return fail(EIG_E_INVALID, "eig_load_weights: null argument");
+    CK(cudaSetDevice(c->device));
+    WMap m;
+    for (int i = 0; i < nt; ++i) {
+        std::string k = names[i];
+        const std::string pre = "predictor/";
+        if (k.compare(0, pre.size(), pre) == 0) k = k.substr(pre.size());
+        HostT t; t.p = ptrs[i];
+        for (int d = 0; d < 4; ++d) t.s[d] = shapes[i * 4 + d];
+        m[k] = t;
+    }
+    const char gates[4] = {'i', 'f', 'c', 'o'};
+    for (int n = 0; n < 4; ++n) {
+        LayerW& L = c->lw[n];
+        const int C = c->ch[n], R = C, Hn = c->H[n], Wn = c->W[n];
+        const HostT* t = nullptr;
+        int rc;
+        char nm[96];
+        if (n >= 1) {
+            const int cin = 2 * c->ch[n - 1], npad = (C + 3) & ~3;
+            std::vector<float> wv((size_t)9 * cin * npad, 0.f), bv(C);
+            snprintf(nm, sizeof nm, "ConvA%d/W", n);
+            if ((rc = need(m, nm, C, cin, 3, 3, &t))) return rc;
+            scatter_conv(wv, cin, npad, 0, t, C, cin, 1, 0);
+            snprintf(nm, sizeof nm, "ConvA%d/b", n);
+            if ((rc = need(m, nm, C, 1, 1, 1, &t))) return rc;
+            for (int i = 0; i < C; ++i) bv[i] = t->p[i];
+            CK(upload(c, &L.convA, wv)); CK(upload(c, &L.convA_b, bv));
+#ifndef EIG_EMU
+            if ((rc = tc_pack(L.tcA, wv.data(), cin, C, npad))) return fail(EIG_E_CUDA, "tc_pack ConvA failed");
+#endif
+        }
+        {
+            const int cin = R, npad = (C + 3) & ~3;
+            std::vector<float> wv((size_t)9 * cin * npad, 0.f), bv(C);
+            snprintf(nm, sizeof nm, "ConvP%d/W", n);
+            if ((rc = need(m, nm, C, cin, 3, 3, &t))) return rc;
+            scatter_conv(wv, cin, npad, 0, t, C, cin, 1, 0);
+            snprintf(nm, sizeof nm, "ConvP%d/b", n);
+            if ((rc = need(m, nm, C, 1, 1, 1, &t))) return rc;
+            for (int i = 0; i < C; ++i) bv[i] = t->p[i];
+            CK(upload(c, &L.convP, wv)); CK(upload(c, &L.convP_b, bv));
+#ifndef EIG_EMU
+            if (n >= 1 && (rc = tc_pack(L.tcP, wv.data(), cin, C, npad))) return fail(EIG_E_CUDA, "tc_pack ConvP failed");
+#endif
+        }
+        {
+            const int ctot = c->ctot[n], N = 4 * R;
+            const int rup = n < 3 ? c->ch[n + 1] : 0;
+            std::vector<float> wv((size_t)9 * ctot * N, 0.f), bv(N), pv((size_t)Hn * Wn * R * 4, 0.f);
+            for (int g = 0; g < 4; ++g) {
+                snprintf(nm, sizeof nm, "ConvLSTM%d/x_%c0/W", n, gates[g]);
+                if ((rc = need(m, nm, R, 2 * C, 3, 3, &t))) return rc;
+                scatter_conv(wv, ctot, N, 0, t, R, 2 * C, 4, g);
+                if (n < 3) {
+                    snprintf(nm, sizeof nm, "ConvLSTM%d/x_%c1/W", n, gates[g]);
+                    if ((rc = need(m, nm, R, rup, 3, 3, &t))) return rc;
+                    scatter_conv(wv, ctot, N, 2 * C, t, R, rup, 4, g);
+                }
+                snprintf(nm, sizeof nm, "ConvLSTM%d/h_%c/W", n, gates[g]);
+                if ((rc = need(m, nm, R, R, 3, 3, &t))) return rc;
+                scatter_conv(wv, ctot, N, 2 * C + rup, t, R, R, 4, g);
+                snprintf(nm, sizeof nm, "ConvLSTM%d/h_%c/b", n, gates[g]);
+                if ((rc = need(m, nm, R, 1, 1, 1, &t))) return rc;
+                for (int r = 0; r < R; ++r) bv[r * 4 + g] = t->p[r];
+            }
+            const char pg[3] = {'i', 'f', 'o'};
+            for (int g = 0; g < 3; ++g) {
+                snprintf(nm, sizeof nm, "ConvLSTM%d/c_%c/W", n, pg[g]);
+                if ((rc = need(m, nm, 1, R, Hn, Wn, &t))) return rc;
+                for (int r = 0; r < R; ++r)
+                    for (int y = 0; y < Hn; ++y)
+                        for (int x = 0; x < Wn; ++x)
+                            pv[(((size_t)y * Wn + x) * R + r) * 4 + g] = t->p[((size_t)r * Hn + y) * Wn + x];
+            }
+            CK(upload(c, &L.lstm, wv)); CK(upload(c, &L.lstm_b, bv)); CK(upload(c, &L.peep, pv));
+#ifndef EIG_EMU
+            if (n >= 1 && (rc = tc_pack(L.tcL, wv.data(), ctot, N, N))) return fail(EIG_E_CUDA, "tc_pack ConvLSTM failed");
+#endif
+        }
+    }
+    c->have_w = true;
+    return EIG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ launches
+static int launch_conv(eig_ctx* c, const ConvArgs& a, cudaStream_t s) {
+    const int tiles = ((a.W + 15) / 16) * ((a.H + 7) / 8);
+    if (a.N <= 16) {
+        const int nw = (a.N + 3) / 4;
+        const size_t smem = (8 * 10 * 20 + 9 * 8 * nw * 4) * sizeof(float);
+        auto k = conv3x3_simt_kernel<4>;
+        EIG_LAUNCH(k, dim3(tiles, a.B, 1), dim3(32 * nw), smem, s, a);
+    } else {
+        int nw = (a.N + 15) / 16;
+        if (nw > 4) nw = 4;
+        const int gz = (a.N + nw * 16 - 1) / (nw * 16);
+        const size_t smem = (8 * 10 * 20 + 9 * 8 * nw * 16) * sizeof(float);
+        auto k = conv3x3_simt_kernel<16>;
+        EIG_LAUNCH(k, dim3(tiles, a.B, gz), dim3(32 * nw), smem, s, a);
+    }
+    EIG_COUNT_LAUNCH();
+    (void)c;
+    CKL();
+    return EIG_OK;
+}
+
+static View mkview(float* hi, float* lo, int pitch, int coff, int C) { View v; v.hi = hi; v.lo = lo; v.pitch = pitch; v.coff = coff; v.C = C; return v; }
+
+// One PredNet time step (net.py:175-211) for B genomes.  x: [B][h][w][c] input frame, t: step index.
+static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s) {
+    const int cur = t & 1, nxt = cur ^ 1;
+    const bool tc = c->conv_mode == EIG_CONV_TC;
+    int rc;
+    {   // E0 -> X0[cur].E
+        const long long npix = (long long)B * c->h * c->w;
+        const long long tot = npix * c->c_dim;
+        EIG_LAUNCH(error0_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, x, (const float*)c->P[0],
+                   mkview(c->X[0][cur], nullptr, c->ctot[0], 0, 2 * c->ch[0]), npix, c->c_dim);
+        EIG_COUNT_LAUNCH();
+        CKL();
+    }
+    for (int n = 1; n < 4; ++n) {  // ConvA_n: E_{n-1} (res n-1) -> pool -> E_n
+        ConvArgs a;
+        memset(&a, 0, sizeof a);
+        a.in_hi = c->X[n - 1][cur]; a.in_lo = c->Xlo[n - 1][cur];
+        a.in_pitch = c->ctot[n - 1]; a.in_coff = 0; a.Cin = 2 * c->ch[n - 1];
+        a.B = B; a.H = c->H[n - 1]; a.W = c->W[n - 1];
+        a.wgt = c->lw[n].convA; a.bias = c->lw[n].convA_b; a.N = c->ch[n]; a.Npad = (c->ch[n] + 3) & ~3;
+        a.epi = EPI_CONVA; a.P = c->P[n];
+        a.dstE = mkview(c->X[n][cur], c->Xlo[n][cur], c->ctot[n], 0, 2 * c->ch[n]);
+#ifndef EIG_EMU
+        if (tc && n >= 2) { if ((rc = tc_conv(c->lw[n].tcA, a, s))) return fail(EIG_E_CUDA, "tc_conv ConvA: " + tc_last_error()); continue; }
+#endif
+        if ((rc = launch_conv(c, a, s))) return rc;
+    }
+    for (int n = 3; n >= 0; --n) {  // ConvLSTM_n
+        ConvArgs a;
+        memset(&a, 0, sizeof a);
+        a.in_hi = c->X[n][cur]; a.in_lo = c->Xlo[n][cur];
+        a.in_pitch = c->ctot[n]; a.in_coff = 0; a.Cin = c->ctot[n];
+        a.B = B; a.H = c->H[n]; a.W = c->W[n];
+        a.wgt = c->lw[n].lstm; a.bias = c->lw[n].lstm_b; a.N = 4 * c->ch[n]; a.Npad = a.N;
+        a.epi = EPI_LSTM; a.cstate = c->cst[n]; a.peep = c->lw[n].peep;
+        const int hoff = 2 * c->ch[n] + (n < 3 ? c->ch[n + 1] : 0);
+        a.dstH = mkview(c->X[n][nxt], c->Xlo[n][nxt], c->ctot[n], hoff, c->ch[n]);
+        if (n >= 1) a.dstUp = mkview(c->X[n - 1][cur], c->Xlo[n - 1][cur], c->ctot[n - 1], 2 * c->ch[n - 1], c->ch[n]);
+#ifndef EIG_EMU
+        if (tc && n >= 1) { if ((rc = tc_conv(c->lw[n].tcL, a, s))) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); continue; }
+#endif
+        if ((rc = launch_conv(c, a, s))) return rc;
+    }
+    for (int n = 0; n < 4; ++n) {  // ConvP_n: R_n -> P_n
+        ConvArgs a;
+        memset(&a, 0, sizeof a);
+        const int hoff = 2 * c->ch[n] + (n < 3 ? c->ch[n + 1] : 0);
+        a.in_hi = c->X[n][nxt]; a.in_lo = c->Xlo[n][nxt];
+        a.in_pitch = c->ctot[n]; a.in_coff = hoff; a.Cin = c->ch[n];
+        a.B = B; a.H = c->H[n]; a.W = c->W[n];
+        a.wgt = c->lw[n].convP; a.bias = c->lw[n].convP_b; a.N = c->ch[n]; a.Npad = (c->ch[n] + 3) & ~3;
+        a.epi = EPI_CONVP; a.outP = c->P[n]; a.clip = n == 0;
+#ifndef EIG_EMU
+        if (tc && n >= 1) { if ((rc = tc_conv(c->lw[n].tcP, a, s))) return fail(EIG_E_CUDA, "tc_conv ConvP: " + tc_last_error()); continue; }
+#endif
+        if ((rc = launch_conv(c, a, s))) return rc;
+    }
+    return EIG_OK;
+}
+
+static int prednet_reset(eig_ctx* c, int B, cudaStream_t s) {
+    for (int n = 0; n < 4; ++n) {
+        const size_t px = (size_t)B * c->H[n] * c->W[n];
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaMemsetAsync(c->X[n][k], 0, px * c->ctot[n] * sizeof(float), s));
+            if (c->Xlo[n][k]) CK(cudaMemsetAsync(c->Xlo[n][k], 0, px * c->ctot[n] * sizeof(float), s));
+        }
+        CK(cudaMemsetAsync(c->cst[n], 0, px * c->ch[n] * sizeof(float), s));
+        CK(cudaMemsetAsync(c->P[n], 0, px * c->ch[n] * sizeof(float), s));
+    }
+    return EIG_OK;
+}
+
+// runs the frame protocol; frame k (0 = prediction #n_in, 1.. = extensions) is quantised to frames_out
+// (nullable) and its gray version to gray_dst[k] (nullable entries)
+static int prednet_sequence(eig_ctx* c, const float* d_x, int B, int n_in, int n_ext, unsigned char* frames_out,
+                            unsigned char* const* gray_dst, cudaStream_t s) {
+    int rc;
+    if ((rc = prednet_reset(c, B, s))) return rc;
+    const long long npix = (long long)B * c->h * c->w;
+    for (int t = 0; t < n_in + n_ext; ++t) {
+        // extension steps are fed the previous, unquantised prediction (call_prednet.py:185,200)
+        const float* x = t < n_in ? d_x : c->P[0];
+        if ((rc = prednet_step(c, x, B, t, s))) return rc;
+        if (t >= n_in - 1) {
+            const int k = t - (n_in - 1);
+            unsigned char* fo = frames_out ? frames_out + (size_t)k * npix * c->c_dim : nullptr;
+            unsigned char* go = gray_dst ? gray_dst[k] : nullptr;
+            if (fo || go) {
+                EIG_LAUNCH(quantize_gray_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s,
+                           (const float*)c->P[0], fo, go, npix, c->c_dim);
+                EIG_COUNT_LAUNCH();
+                CKL();
+            }
+        }
+    }
+    return EIG_OK;
+}
+
+static int check_ready(eig_ctx* c, int n, bool need_w, bool need_grid) {
+    if (!c) return fail(EIG_E_INVALID, "null ctx");
+    if (n <= 0) return fail(EIG_E_INVALID, "n must be positive");
+    if (n > c->cap) return fail(EIG_E_CAPACITY, "population larger than max_genomes given to eig_create");
+    if (need_w && !c->have_w) return fail(EIG_E_STATE, "PredNet weights not loaded (eig_load_weights)");
+    if (need_grid && !c->have_grid) return fail(EIG_E_STATE, "grid planes not set (eig_set_grid)");
+    return EIG_OK;
+}
+
+extern "C" int eig_cppn_render(eig_ctx* c, const void* d_blob, const int64_t* d_offsets, int n, int max_slots,
+                               int max_blob_bytes, int mode, double bg, uint8_t* d_img, float* d_x, void* stream) {
+    int rc;
+    if ((rc = check_ready(c, n, false, true))) return rc;
+    if (!d_blob || !d_offsets || !d_img) return fail(EIG_E_INVALID, "eig_cppn_render: null pointer");
+    if (mode < 0 || mode > 2) return fail(EIG_E_INVALID, "eig_cppn_render: mode must be 0, 1 or 2");
+    CK(cudaSetDevice(c->device));
+    RenderArgs a;
+    a.blob = (const unsigned char*)d_blob; a.offsets = (const long long*)d_offsets;
+    a.xmat = c->xmat; a.ymat = c->ymat; a.npix = c->w * c->h; a.c_dim = c->c_dim; a.mode = mode; a.bg = bg;
+    a.img = d_img; a.x = d_x;
+    a.max_blob_bytes = (max_blob_bytes + 15) & ~15;
+    int nt = 128;
+    size_t smem = (size_t)a.max_blob_bytes + (size_t)max_slots * nt * sizeof(double);
+    while (smem > 200 * 1024 && nt > 32) { nt >>= 1; smem = (size_t)a.max_blob_bytes + (size_t)max_slots * nt * sizeof(double); }
+    if (smem > 200 * 1024) return fail(EIG_E_CAPACITY, "eig_cppn_render: genome program too large for shared memory");
+    auto k = cppn_render_kernel;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EIG_LAUNCH(k, dim3((a.npix + nt - 1) / nt, n), dim3(nt), smem, TO_STREAM(stream), a);
+    EIG_COUNT_LAUNCH();
+    CKL();
+    return EIG_OK;
+}
+
+extern "C" int eig_prednet_run(eig_ctx* c, const float* d_x, int n, int n_in, int n_ext, uint8_t* d_frames, void* stream) {
+    int rc;
+    if ((rc = check_ready(c, n, true, false))) return rc;
+    if (!d_x || !d_frames || n_in < 1 || n_ext < 0) return fail(EIG_E_INVALID, "eig_prednet_run: bad argument");
+    CK(cudaSetDevice(c->device));
+    return prednet_sequence(c, d_x, n, n_in, n_ext, d_frames, nullptr, TO_STREAM(stream));
+}
+
+// corners + LK + vector rows from the gray level-0 images already in c->gray[0] ([0,B) frame 1, [B,2B) frame 2)
+static int flow_from_gray(eig_ctx* c, int B, cudaStream_t s) {
+    const int H = c->h, W = c->w;
+    for (int l = 1; l < c->n_levels; ++l) {
+        // frame-2 images of every level sit right after the B frame-1 images actually in use
+        const long long tot = 2LL * B * c->lh[l] * c->lwid[l];
+        EIG_LAUNCH(pyr_down_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, (const unsigned char*)c->gray[l - 1],
+                   c->gray[l], c->lh[l - 1], c->lwid[l - 1], c->lh[l], c->lwid[l], 2 * B);
+        EIG_COUNT_LAUNCH();
+        CKL();
+    }
+    for (int l = 0; l < c->n_levels; ++l) {
+        const long long tot = (long long)B * c->lh[l] * c->lwid[l];
+        EIG_LAUNCH(scharr_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, (const unsigned char*)c->gray[l],
+                   c->deriv[l], c->lh[l], c->lwid[l], B);
+        EIG_COUNT_LAUNCH();
+        CKL();
+    }
+    CK(cudaMemsetAsync(c->eigmax, 0x80, sizeof(int) * B, s));  // 0x80808080: below every real key
+    EigArgs ea; ea.gray = c->gray[0]; ea.eig = c->eigmap; ea.eig_max_key = c->eigmax; ea.H = H; ea.W = W;
+    EIG_LAUNCH(min_eig_kernel, dim3(((W + 31) / 32) * ((H + 15) / 16), B), dim3(256), 0, s, ea);
+    EIG_COUNT_LAUNCH();
+    CKL();
+    CornerArgs ca; ca.eig = c->eigmap; ca.eig_max_key = c->eigmax; ca.cand = c->cand; ca.corners = c->corners;
+    ca.ncorners = c->ncorners; ca.H = H; ca.W = W;
+    EIG_LAUNCH(corner_select_kernel, dim3(B), dim3(256), 0, s, ca);
+    EIG_COUNT_LAUNCH();
+    CKL();
+    LkArgs la;
+    memset(&la, 0, sizeof la);
+    for (int l = 0; l < c->n_levels; ++l) {
+        la.img1[l] = c->gray[l];
+        la.img2[l] = c->gray[l] + (size_t)B * c->lh[l] * c->lwid[l];
+        la.deriv1[l] = c->deriv[l];
+        la.lh[l] = c->lh[l]; la.lw[l] = c->lwid[l];
+    }
+    la.n_levels = c->n_levels; la.corners = c->corners; la.ncorners = c->ncorners; la.next_pts = c->next_pts;
+    la.status = c->status; la.B = B;
+    EIG_LAUNCH(lk_track_kernel, dim3((B * FLOW_MAX_CORNERS + LK_WARPS_PER_BLOCK - 1) / LK_WARPS_PER_BLOCK),
+               dim3(32 * LK_WARPS_PER_BLOCK), 0, s, la);
+    EIG_COUNT_LAUNCH();
+    CKL();
+    EIG_LAUNCH(collect_vectors_kernel, dim3((B + 63) / 64), dim3(64), 0, s, (const float*)c->corners, (const int*)c->ncorners,
+               (const float*)c->next_pts, (const unsigned char*)c->status, c->vectors, c->nvec, B);
+    EIG_COUNT_LAUNCH();
+    CKL();
+    return EIG_OK;
+}
+
+extern "C" int eig_flow(eig_ctx* c, const uint8_t* d_img1, const uint8_t* d_img2, int n, float* d_corners, int* d_ncorners,
+                        float* d_vectors, int* d_nvec, void* stream) {
+    int rc;
+    if ((rc = check_ready(c, n, false, false))) return rc;
+    if (!d_img1 || !d_img2 || !d_vectors || !d_nvec) return fail(EIG_E_INVALID, "eig_flow: null pointer");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = TO_STREAM(stream);
+    const long long npix = (long long)n * c->h * c->w;
+    EIG_LAUNCH(gray_u8_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, d_img1, c->gray[0], npix, c->c_dim);
+    EIG_LAUNCH(gray_u8_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, d_img2, c->gray[0] + npix, npix, c->c_dim);
+    EIG_COUNT_LAUNCH(); EIG_COUNT_LAUNCH();
+    CKL();
+    if ((rc = flow_from_gray(c, n, s))) return rc;
+    CK(cudaMemcpyAsync(d_vectors, c->vectors, sizeof(float) * n * FLOW_MAX_CORNERS * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(d_nvec, c->nvec, sizeof(int) * n, cudaMemcpyDeviceToDevice, s));
+    if (d_corners) CK(cudaMemcpyAsync(d_corners, c->corners, sizeof(float) * n * FLOW_MAX_CORNERS * 2, cudaMemcpyDeviceToDevice, s));
+    if (d_ncorners) CK(cudaMemcpyAsync(d_ncorners, c->ncorners, sizeof(int) * n, cudaMemcpyDeviceToDevice, s));
+    return EIG_OK;
+}
+
+static int score_launch(eig_ctx* c, const float* vec, const int* nvec, int n, int structure, double* fit, cudaStream_t s) {
+    if (structure < 0 || structure > 3) return fail(EIG_E_INVALID, "unknown structure id");
+    ScoreArgs sa; sa.vectors = vec; sa.nvec = nvec; sa.fitness = fit; sa.B = n; sa.structure = structure; sa.w = c->w; sa.h = c->h;
+    EIG_LAUNCH(score_kernel, dim3(n), dim3(32), 0, s, sa);
+    EIG_COUNT_LAUNCH();
+    CKL();
+    return EIG_OK;
+}
+
+extern "C" int eig_score(eig_ctx* c, const float* d_vectors, const int* d_nvec, int n, int structure, double* d_fitness, void* stream) {
+    int rc;
+    if ((rc = check_ready(c, n, false, false))) return rc;
+    if (!d_vectors || !d_nvec || !d_fitness) return fail(EIG_E_INVALID, "eig_score: null pointer");
+    CK(cudaSetDevice(c->device));
+    return score_launch(c, d_vectors, d_nvec, n, structure, d_fitness, TO_STREAM(stream));
+}
+
+extern "C" int eig_eval(eig_ctx* c, const void* d_blob, const int64_t* d_offsets, int n, int max_slots, int max_blob_bytes,
+                        int structure, int render_mode, int pair_mode, double* d_fitness, void* stream) {
+    int rc;
+    if ((rc = check_ready(c, n, true, true))) return rc;
+    if (!d_fitness) return fail(EIG_E_INVALID, "eig_eval: null fitness pointer");
+    if (pair_mode != EIG_PAIR_POPULATION && pair_mode != EIG_PAIR_SINGLE_IMAGE) return fail(EIG_E_INVALID, "unknown pair mode");
+    cudaStream_t s = TO_STREAM(stream);
+    if ((rc = eig_cppn_render(c, d_blob, d_offsets, n, max_slots, max_blob_bytes, render_mode, 1.0, c->img, c->x_in, stream))) return rc;
+    const long long npix = (long long)n * c->h * c->w;
+    unsigned char* g1 = c->gray[0];
+    unsigned char* g2 = c->gray[0] + npix;
+    unsigned char* gd[3];
+    int n_ext;
+    if (pair_mode == EIG_PAIR_POPULATION) {
+        gd[0] = g1; gd[1] = g2; gd[2] = nullptr; n_ext = 1;   // the reference's 22nd forward is dead work
+    } else {
+        gd[0] = nullptr; gd[1] = nullptr; gd[2] = g2; n_ext = 2;
+        EIG_LAUNCH(gray_u8_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, (const unsigned char*)c->img, g1, npix, c->c_dim);
+        EIG_COUNT_LAUNCH();
+        CKL();
+    }
+    if ((rc = prednet_sequence(c, c->x_in, n, 20, n_ext, c->frames, gd, s))) return rc;
+    if ((rc = flow_from_gray(c, n, s))) return rc;
+    return score_launch(c, c->vectors, c->nvec, n, structure, d_fitness, s);
+}
+
+extern "C" int eig_eval_host(eig_ctx* c, const void* h_blob, const int64_t* h_offsets, int n, int max_slots, int structure,
+                             int render_mode, int pair_mode, double* h_fitness) {
+    int rc;
+    if ((rc = check_ready(c, n, true, true))) return rc;
+    if (!h_blob || !h_offsets || !h_fitness) return fail(EIG_E_INVALID, "eig_eval_host: null pointer");
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)h_offsets[n];
+    int max_blob = 0;
+    for (int i = 0; i < n; ++i) { const int b = (int)(h_offsets[i + 1] - h_offsets[i]); if (b > max_blob) max_blob = b; }
+    if (bytes > c->d_blob_cap) {
+        if (c->d_blob) CK(cudaFree(c->d_blob));
+        c->d_blob = nullptr;
+        c->d_blob_cap = bytes * 2 + 4096;
+        CK(cudaMalloc(&c->d_blob, c->d_blob_cap));
+    }
+    cudaStream_t s = c->stream;
+    CK(cudaMemcpyAsync(c->d_blob, h_blob, bytes, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->d_off, h_offsets, sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, s));
+    if ((rc = eig_eval(c, c->d_blob, (const int64_t*)c->d_off, n, max_slots, max_blob, structure, render_mode, pair_mode,
+                       c->fitness, (void*)(intptr_t)s)))
+        return rc;
+    CK(cudaMemcpyAsync(h_fitness, c->fitness, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return EIG_OK;
+}
+
+extern "C" int eig_debug_buffers(eig_ctx* c, uint8_t** d_img, uint8_t** d_frames, float** d_vectors, int** d_nvec,
+                                 float** d_corners, int** d_ncorners) {
+    if (!c) return fail(EIG_E_INVALID, "null ctx");
+    if (d_img) *d_img = c->img;
+    if (d_frames) *d_frames = c->frames;
+    if (d_vectors) *d_vectors = c->vectors;
+    if (d_nvec) *d_nvec = c->nvec;
+    if (d_corners) *d_corners = c->corners;
+    if (d_ncorners) *d_ncorners = c->ncorners;
+    return EIG_OK;
+}
