@@ -1,0 +1,128 @@
+"""Drop-in for the fitness path of /root/reference/generate_illusion.py, backed by libeig.so on a B200.
+
+Same names, argument meaning and side effects on `genome.fitness` as the reference:
+  StructureType                  generate_illusion.py:25-29
+  create_grid                    generate_illusion.py:196-317   (grid.py)
+  get_image_from_cppn            generate_illusion.py:372-460   -> PIL image, rendered by the CUDA kernel
+  get_fitnesses_neat             generate_illusion.py:478-673   -> sets genome.fitness for every genome
+  neat_illusion / CLI            generate_illusion.py:676-771   (needs neat-python, which is untouched)
+Differences, all listed in SURVEY.md "defects": no Colab import, no PNG hand-offs between stages (files are
+written only for the best genome), N=1 populations work, Bands planes are reshaped to (h,w), colour uses
+outputs 0..2 of 6-output configs, the dead 22nd PredNet forward is not computed.
+"""
+import argparse
+import os
+
+import numpy as np
+
+from . import engine as engine_mod, genome as G, runtime
+from ._lib import PAIR_POPULATION
+from .grid import StructureType, create_grid  # noqa: F401  (re-exported, reference names)
+
+REPEAT = 20  # generate_illusion.py:482
+
+
+def _used_outputs(c_dim):
+    return c_dim if c_dim > 1 else 1
+
+
+def get_image_from_cppn(inputs, genome, c_dim, w, h, config, bg=1, gradient=1, engine=None, model_name=None,
+                        channels=None):
+    """PIL image of one genome on the given grid planes (same signature as the reference + optional engine)."""
+    from PIL import Image
+    eng = engine
+    if eng is None:
+        if channels is None:
+            channels = (c_dim, 16 * c_dim, 32 * c_dim, 64 * c_dim)
+        eng = engine_mod.Engine(w, h, channels, 8)
+    eng.set_grid(grid=inputs)
+    prog = G.flatten_genome(genome, config, n_outputs=_used_outputs(c_dim))
+    mode = engine_mod.render_mode_for(c_dim, gradient)
+    img, _ = eng.render([prog], mode=mode, bg=float(bg))
+    arr = img[0].cpu().numpy()
+    if c_dim > 1:
+        return Image.fromarray(arr)
+    return Image.fromarray(arr[:, :, 0], "L")
+
+
+def get_fitnesses_neat(structure, population, model_name, config, w, h, channels,
+                       id=0, c_dim=3, best_dir=".", gradient=1, export_best=True):
+    """population: [(genome_id, genome)].  On return every genome.fitness is a python float."""
+    population = list(population)
+    print("Calculating fitnesses of populations: ", len(population))
+    eng = runtime.get_engine(w, h, channels, model_name, len(population))
+    eng.set_grid(structure)
+    programs = [G.flatten_genome(g, config, n_outputs=_used_outputs(c_dim)) for _, g in population]
+    mode = engine_mod.render_mode_for(c_dim, gradient)
+    fit = runtime.evaluate_population(eng, programs, int(structure), mode, PAIR_POPULATION)
+    best_score, best_i = 0, 0
+    for i, (_, genome) in enumerate(population):
+        genome.fitness = float(fit[i])
+        if genome.fitness >= best_score:  # generate_illusion.py:625 (NaN never wins, like the reference)
+            best_score, best_i = genome.fitness, i
+    print("scores", [[i, float(f)] for i, f in enumerate(fit)])
+    if export_best and population:
+        _export_best(eng, population[best_i][1], config, c_dim, gradient, best_dir)
+    print("best", best_score, best_i)
+    return None
+
+
+def _export_best(eng, genome, config, c_dim, gradient, best_dir):
+    """best.png / best_black_bg.png (generate_illusion.py:650-663).  The 800x800 `enhanced.png` mosaic
+    (664-671) is a per-generation cosmetic outside the hot path and is not produced."""
+    from PIL import Image
+    os.makedirs(best_dir, exist_ok=True)
+    prog = G.flatten_genome(genome, config, n_outputs=_used_outputs(c_dim))
+    mode = engine_mod.render_mode_for(c_dim, gradient)
+    for name, bg in (("best.png", 1.0), ("best_black_bg.png", 0.0)):
+        img, _ = eng.render([prog], mode=mode, bg=bg)
+        arr = img[0].cpu().numpy()
+        im = Image.fromarray(arr) if c_dim > 1 else Image.fromarray(arr[:, :, 0], "L")
+        im.save(os.path.join(best_dir, name), "PNG")
+
+
+def neat_illusion(output_dir, model_name, config_path, structure, w, h, channels, c_dim=3, checkpoint=None,
+                  gradient=1, generations=100):
+    """generate_illusion.py:676-711 with neat-python untouched; only `eval_genomes` changes hands."""
+    import neat  # third-party, not vendored (pytorch_neat/requirements.txt:1)
+    os.makedirs(output_dir, exist_ok=True)
+    config = neat.Config(neat.DefaultGenome, neat.DefaultReproduction, neat.DefaultSpeciesSet,
+                         neat.DefaultStagnation, config_path)
+
+    def eval_genomes(genomes, config):
+        get_fitnesses_neat(structure, genomes, model_name, config, w, h, channels, c_dim=c_dim,
+                           best_dir=output_dir, gradient=gradient)
+
+    checkpointer = neat.Checkpointer(100)
+    p = neat.Population(config) if not checkpoint else checkpointer.restore_checkpoint(checkpoint)
+    p.add_reporter(neat.StdOutReporter(True))
+    p.add_reporter(neat.StatisticsReporter())
+    p.add_reporter(checkpointer)
+    return p.run(eval_genomes, generations)
+
+
+def string_to_intarray(string_input):
+    return [int(v) for v in string_input.split(",")]
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(description="generate illusions (B200 engine)")
+    parser.add_argument("--model", "-m", default="", help=".model file (Chainer npz)")
+    parser.add_argument("--output_dir", "-o", default=".", help="path of output directory")
+    parser.add_argument("--structure", "-s", default=0, type=int, help="0: Bands; 1: Circles; 2: Free form")
+    parser.add_argument("--config", "-cfg", default="", help="path to the NEAT config file")
+    parser.add_argument("--checkpoint", "-cp", help="path of checkpoint to restore")
+    parser.add_argument("--size", "-wh", help="big or small", default="small")
+    parser.add_argument("--color_space", "-c", help="1 for greyscale, 3 for rgb", default=3, type=int)
+    parser.add_argument("--channels", "-ch", default="3,48,96,192", help="Number of channels on each layers")
+    parser.add_argument("--gradient", "-g", default=1, type=int, help="1 to use gradients, 0 for pure colors")
+    args = parser.parse_args(argv)
+    w, h = (640, 480) if args.size == "big" else (160, 120)
+    if not args.config:
+        raise SystemExit("--config: pass the NEAT config file (the reference ships them under neat_configs/)")
+    neat_illusion(args.output_dir, args.model, args.config, args.structure, w, h,
+                  string_to_intarray(args.channels), args.color_space, args.checkpoint, args.gradient)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,65 @@
+"""Process-wide engine cache and genome-sharded evaluation (one process per GPU).
+
+`evaluate_population` is what `get_fitnesses_neat` runs: flatten -> (shard) -> libeig -> (all-gather) -> floats.
+Sharding follows SURVEY.md §8(e): rank r owns the contiguous block [r*ceil(N/G), (r+1)*ceil(N/G)) of the
+population, in population order; PredNet weights and grid planes are replicated; one all-gather of the
+padded per-rank fitness slices (NCCL over NVLink for CUDA tensors, gloo for the CPU-tensor unit tests) is the
+only exchange.  Genomes are independent, so the result is bit-identical for every world size.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, engine as engine_mod, genome as G
+
+_engines = {}
+
+
+def get_engine(w, h, channels, model_name, max_genomes):
+    """One Engine per (w, h, channels, weight file); re-created only when the population outgrows it."""
+    key = (w, h, tuple(channels), model_name if isinstance(model_name, str) else id(model_name))
+    eng = _engines.get(key)
+    if eng is None or eng.max_genomes < max_genomes:
+        if eng is not None:
+            eng.close()
+        eng = engine_mod.Engine(w, h, channels, max(max_genomes, 8))
+        eng.load_weights(model_name)
+        _engines[key] = eng
+    return eng
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous block of ceil(n/world) genomes per rank (the last ranks may be short or empty)."""
+    per = int(math.ceil(n / world)) if world > 0 else n
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per), per
+
+
+def gather_fitness(local, n_total, per, group=None):
+    """All-gather the padded per-rank slices and cut the result back to population order.
+    `local`: 1-D float64 tensor with this rank's fitness values (may be shorter than `per`)."""
+    world = dist.get_world_size(group)
+    pad = torch.full((per,), float("nan"), dtype=torch.float64, device=local.device)
+    pad[:local.numel()] = local
+    out = torch.empty((world * per,), dtype=torch.float64, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return out[:n_total]
+
+
+def evaluate_population(eng, programs, structure, render_mode=engine_mod.RENDER_GRADIENT,
+                        pair_mode=_lib.PAIR_POPULATION, group=None):
+    """[FlatProgram] for the WHOLE population (same list on every rank) -> numpy float64 fitness vector."""
+    n = len(programs)
+    if n == 0:
+        return np.zeros((0,), dtype=np.float64)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return eng.evaluate(programs, structure, render_mode, pair_mode)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi, per = shard_bounds(n, rank, world)
+    if hi > lo:
+        local = torch.from_numpy(eng.evaluate(programs[lo:hi], structure, render_mode, pair_mode)).to(eng.tdev)
+    else:
+        local = torch.zeros((0,), dtype=torch.float64, device=eng.tdev)
+    return gather_fitness(local, n, per, group).cpu().numpy()

@@ -188,7 +188,8 @@ def pyr_lk(gray1, gray2, pts):
     status = np.ones(n, np.uint8)
     half = f32((WIN - 1) * 0.5)
     flt_scale = f32(1.0 / (1 << 20))
-    eps2 = min(max(EPS, 0.0), 10.0) ** 2
+    eps2 = min(max(EPS, 0.0), 10.0)
+    eps2 = eps2 * eps2  # criteria.epsilon *= criteria.epsilon, in double
     top = len(pyr1) - 1
     for level in range(top, -1, -1):
         I = np.pad(pyr1[level].astype(np.int32), WIN, mode="reflect")
@@ -245,7 +246,7 @@ def pyr_lk(gray1, gray2, pts):
                 nxt[k] = (f32(cx + half), f32(cy + half))
                 if float(ddx) * float(ddx) + float(ddy) * float(ddy) <= eps2:
                     break
-                if j > 0 and abs(f32(ddx + pdx)) < 0.01 and abs(f32(ddy + pdy)) < 0.01:
+                if j > 0 and abs(float(f32(ddx + pdx))) < 0.01 and abs(float(f32(ddy + pdy))) < 0.01:
                     nxt[k, 0] = f32(nxt[k, 0] - f32(ddx * f32(0.5)))
                     nxt[k, 1] = f32(nxt[k, 1] - f32(ddy * f32(0.5)))
                     break

@@ -1,0 +1,146 @@
+"""Generates the committed golden fixtures.  Run here (build container), where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+  render_ref.npz   : images produced by the REFERENCE's own `get_image_from_cppn` (imported unmodified under the
+                     stubs of ref_harness.py) for seeded synthetic genomes  -> pins oracle/cppn.py + flattener + K1
+  scoring_ref.npz  : scores of the REFERENCE's `calculate_fitness` on seeded random vector sets -> pins
+                     oracle/scoring.py + K9
+  cppn_cases.json  : the four known answers of the reference's pytorch_neat/tests/test_cppn.py:27-92
+  flow_cv2.npz     : frame pairs (produced by the oracle PredNet on oracle renders) with the output of the
+                     cv2 4.13 calls the reference makes (corners, vectors) -> pins oracle/flow.py + K5-K8
+  pipeline.npz     : oracle fitness for seeded populations/weights at 64x64 and 160x120 -> whole-path anchor
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_harness  # noqa: E402
+from evolutionary_illusion_generator_b200 import genome as G, weights as W  # noqa: E402
+from oracle import cppn as OC, flow as OF, grid as OG, pipeline as OPL, prednet as OP  # noqa: E402
+
+RENDER_CASES = [  # (preset, c_dim, w, h, structure, gradient, evolved, indices)
+    ("circles_bw", 1, 160, 120, 1, 1, False, list(range(0, 6))),
+    ("circles_bw", 1, 160, 120, 1, 0, True, list(range(6, 10))),
+    ("circles", 3, 160, 120, 1, 1, True, list(range(0, 6))),
+    ("circles", 3, 64, 64, 1, 0, False, list(range(6, 9))),
+    ("free", 3, 64, 64, 2, 1, True, list(range(0, 4))),
+    ("bands", 3, 160, 120, 0, 1, False, list(range(0, 3))),
+]
+
+
+def make_render(ns):
+    out = {}
+    meta = []
+    for ci, (preset, c_dim, w, h, structure, gradient, evolved, idx) in enumerate(RENDER_CASES):
+        n_out = G.NEAT_PRESETS[preset]["num_outputs"]
+        # the reference crashes on 6-output colour configs and on Bands (SURVEY.md "defects"): run it on the
+        # documented fix-ups (first 3 outputs, planes reshaped to (h,w))
+        cfg = G.make_config(2, min(n_out, 3) if c_dim == 3 else n_out)
+        grid = ns.gi.create_grid(ns.gi.StructureType(structure), w, h, 10)
+        grid = {k: np.asarray(v).reshape(h, w) for k, v in grid.items()}
+        for i in idx:
+            g = G.synthetic_genome(preset, i, evolved=evolved)
+            if c_dim == 3 and n_out > 3:
+                g.nodes = {k: v for k, v in g.nodes.items()}
+            img = np.asarray(ns.gi.get_image_from_cppn(grid, g, c_dim, w, h, cfg, bg=1, gradient=gradient))
+            out["img_%d_%d" % (ci, i)] = img
+        meta.append(dict(case=ci, preset=preset, c_dim=c_dim, w=w, h=h, structure=structure, gradient=gradient,
+                         evolved=evolved, indices=idx))
+    out["meta"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(HERE, "render_ref.npz"), **out)
+    print("render_ref.npz:", len(out) - 1, "images")
+
+
+def make_scoring(ns):
+    rng = np.random.RandomState(7)
+    w, h = 160, 120
+    sets, scores = [], []
+    for trial in range(60):
+        n = int(rng.randint(1, 100))
+        v = np.zeros((n, 4), np.float32)
+        v[:, 0] = rng.uniform(0, w, n)
+        v[:, 1] = rng.uniform(0, h, n)
+        v[:, 2:] = rng.normal(0, rng.choice([0.03, 0.1, 0.25]), (n, 2))
+        if trial % 5 == 0:
+            v[:, :2] = np.round(v[:, :2])
+        row = []
+        for st in (0, 1, 2, 3):
+            try:
+                s = ns.fc.calculate_fitness(ns.fc.StructureType(st), v, "x.png", w, h)
+            except UnboundLocalError:
+                s = 0.0
+            row.append(float(s))
+        pad = np.zeros((100, 4), np.float32)
+        pad[:n] = v
+        sets.append(pad)
+        scores.append([n] + row)
+    np.savez_compressed(os.path.join(HERE, "scoring_ref.npz"), vectors=np.stack(sets), scores=np.array(scores), w=w, h=h)
+    print("scoring_ref.npz:", len(sets), "vector sets")
+
+
+def make_cppn_cases():
+    # pytorch_neat/tests/test_cppn.py:27-92, restated as genomes: (nodes, connections, inputs, expected)
+    cases = [
+        dict(name="simple", nodes={"0": [0.0, 1.0, "identity", "sum"]}, conns=[[-1, 0, 1.0]], x=3.0, y=0.0, expect=3.0),
+        dict(name="unconnected", nodes={"0": [0.5, 1.0, "identity", "sum"]}, conns=[], x=3.0, y=0.0, expect=0.5),
+        dict(name="call_b", nodes={"0": [0.0, 1.0, "identity", "sum"]}, conns=[[-1, 0, 1.0], [-2, 0, 1.0]], x=1.5, y=2.0,
+             expect=3.5),
+        dict(name="deep_call_b", nodes={"0": [0.0, 1.0, "identity", "sum"], "1": [0.0, 1.0, "identity", "sum"]},
+             conns=[[-2, 1, 1.0], [-1, 0, 1.0], [1, 0, 1.0]], x=1.5, y=2.0, expect=3.5, n_outputs=1),
+    ]
+    json.dump(cases, open(os.path.join(HERE, "cppn_cases.json"), "w"), indent=1)
+    print("cppn_cases.json:", len(cases))
+
+
+def make_flow_and_pipeline():
+    import torch
+    torch.set_num_threads(8)
+    out_flow, out_pipe = {}, {}
+    cases = [("c2", "circles_bw", 1, (1, 16, 32, 64), 160, 120, 1, 0, 8),
+             ("c1", "circles_bw", 1, (1, 16, 32, 64), 64, 64, 1, 1, 3),
+             ("c3", "circles", 3, (3, 48, 96, 192), 160, 120, 1, 0, 3),
+             ("small_free", "free", 3, (3, 6, 8, 12), 64, 64, 2, 0, 4)]
+    meta = []
+    for name, preset, c_dim, ch, w, h, structure, pair, n in cases:
+        wts = W.synthetic_weights(w, h, ch, seed=0)
+        n_out = G.NEAT_PRESETS[preset]["num_outputs"]
+        cfg = G.make_config(2, n_out)
+        pop = [G.synthetic_genome(preset, i) for i in range(n)]
+        fit, ex = OPL.evaluate_population(pop, cfg.genome_config.input_keys, cfg.genome_config.output_keys, structure,
+                                          wts, w, h, ch, c_dim, pair_mode=pair, keep=True)
+        out_pipe["fitness_" + name] = fit
+        out_pipe["nvec_" + name] = np.array([len(e["vectors"]) for e in ex])
+        out_pipe["frames_" + name] = np.stack([np.stack(e["frames"]) for e in ex])
+        meta.append(dict(name=name, preset=preset, c_dim=c_dim, channels=ch, w=w, h=h, structure=structure, pair=pair, n=n))
+        if name in ("c2", "c3"):
+            for i, e in enumerate(ex[:4]):
+                a, b = e["frames"][0], e["frames"][1]
+                cvv = OF.lucas_kanade_cv2(a, b)
+                import cv2
+                gray = OF.to_gray(a)
+                cc = cv2.goodFeaturesToTrack(gray, 100, 0.3, 7, blockSize=7)
+                cc = np.zeros((0, 2), np.float32) if cc is None else cc.reshape(-1, 2)
+                key = "%s_%d" % (name, i)
+                out_flow["a_" + key], out_flow["b_" + key] = a, b
+                out_flow["corners_" + key], out_flow["vectors_" + key] = cc, cvv
+        print(name, "fitness", np.round(fit, 5))
+    out_pipe["meta"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(HERE, "pipeline.npz"), **out_pipe)
+    np.savez_compressed(os.path.join(HERE, "flow_cv2.npz"), **out_flow)
+    print("pipeline.npz, flow_cv2.npz written")
+
+
+if __name__ == "__main__":
+    ns = ref_harness.load()
+    make_render(ns)
+    make_scoring(ns)
+    make_cppn_cases()
+    make_flow_and_pipeline()

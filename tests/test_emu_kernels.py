@@ -1,0 +1,101 @@
+"""The real kernel sources (csrc/*.cuh) executed by the TEST-ONLY fiber emulator (tests/emu/cuda_emu.h) and
+compared with the oracle.  This is how indexing / barriers / shuffles are checked in the GPU-less build
+container; the B200 run of the same comparisons is tests/test_gpu_parity.py."""
+import numpy as np
+import torch
+
+from evolutionary_illusion_generator_b200 import engine as E, genome as G, weights as W
+from oracle import cppn as OC, flow as OF, grid as OG, pipeline as OPL, prednet as OP, scoring as OS
+
+
+def _squeeze(a, c):
+    return a[..., 0] if c == 1 else a
+
+
+def test_render_kernel_bytes(emu_lib):
+    w, h = 64, 56
+    for preset, ch, gradient in (("circles_bw", (1, 4, 8, 8), 1), ("circles_bw", (1, 4, 8, 8), 0),
+                                 ("circles", (3, 4, 8, 8), 1), ("circles", (3, 4, 8, 8), 0)):
+        c = ch[0]
+        eng = E.Engine(w, h, ch, 8, lib=emu_lib)
+        eng.set_grid(1)
+        cfg = G.make_config(2, G.NEAT_PRESETS[preset]["num_outputs"])
+        gc = cfg.genome_config
+        pop = [G.synthetic_genome(preset, i, evolved=bool(i % 2)) for i in range(6)]
+        const = G.Genome()
+        const.nodes = {k: G.NodeGene(k, 0.3 + 0.2 * k, 1.0, "sigmoid", "sum") for k in gc.output_keys}
+        pop.append(const)
+        progs = [G.flatten_genome(g, cfg, n_outputs=c) for g in pop]
+        img, x = eng.render(progs, mode=E.render_mode_for(c, gradient))
+        grid = OG.create_grid(1, w, h, 10)
+        for i, g in enumerate(pop):
+            want = OC.render(grid, g, c, w, h, gc.input_keys, gc.output_keys, gradient=gradient)
+            assert np.array_equal(_squeeze(img[i].numpy(), c), want), (preset, gradient, i)
+            assert np.array_equal(_squeeze(x[i].numpy(), c), (want / 255).astype(np.float32))
+        eng.close()
+
+
+def test_prednet_kernels_frames(emu_lib):
+    w, h = 64, 56   # layer sizes 56/28/14/7: partial tiles and an odd top layer
+    for preset, ch in (("circles_bw", (1, 4, 8, 12)), ("circles", (3, 6, 8, 20))):
+        c = ch[0]
+        eng = E.Engine(w, h, ch, 4, lib=emu_lib)
+        eng.set_grid(1)
+        wts = W.synthetic_weights(w, h, ch, seed=1, bias_std=0.1)
+        eng.load_weights(wts)
+        cfg = G.make_config(2, G.NEAT_PRESETS[preset]["num_outputs"])
+        pop = [G.synthetic_genome(preset, i) for i in range(2)]
+        img, x = eng.render([G.flatten_genome(g, cfg, n_outputs=c) for g in pop])
+        frames = eng.prednet(x, n_input_steps=3, n_ext=2)
+        net = OP.PredNetOracle(wts, ch, w, h)
+        for i in range(len(pop)):
+            want = OP.run_genome_frames(net, _squeeze(img[i].numpy(), c), repeat=3, extension=2)
+            for k in range(3):
+                d = _squeeze(frames[k, i].numpy(), c).astype(int) - want[k].astype(int)
+                assert np.abs(d).max() <= 1 and (d != 0).mean() < 2e-3, (preset, i, k)
+        eng.close()
+
+
+def test_flow_and_score_kernels(emu_lib):
+    rng = np.random.RandomState(3)
+    import cv2
+    w, h = 112, 104   # two pyramid levels
+    a = cv2.GaussianBlur(rng.randint(0, 256, (h, w, 3)).astype(np.uint8), (7, 7), 2)
+    b = cv2.warpAffine(a, np.float32([[1, 0.003, 0.2], [-0.003, 1, -0.1]]), (w, h), borderMode=cv2.BORDER_REFLECT)
+    flat = np.full((h, w, 3), 128, np.uint8)
+    eng = E.Engine(w, h, (3, 4, 8, 8), 4, lib=emu_lib)
+    A = torch.from_numpy(np.stack([a, flat, a]))
+    Bt = torch.from_numpy(np.stack([b, flat, a]))
+    corners, nc, vec, nv = eng.flow(A, Bt)
+    for i, (p, q) in enumerate(((a, b), (flat, flat), (a, a))):
+        want_c = OF.good_features(OF.to_gray(p))
+        want_v = OF.lucas_kanade_np(p, q)
+        assert np.array_equal(corners[i, :nc[i]].numpy(), want_c)
+        assert np.array_equal(vec[i, :nv[i]].numpy(), want_v)
+        for st in range(4):
+            got = float(eng.score(vec[i:i + 1], nv[i:i + 1], st)[0])
+            want = OS.fitness_from_vectors(st, want_v, w, h)
+            assert (np.isnan(got) and np.isnan(want)) or abs(got - want) <= 1e-6 * max(1.0, abs(want)), (i, st)
+    assert int(nc[1]) == 0 and int(nv[1]) == 0   # flat image: no corners, sentinel path, fitness 0
+    eng.close()
+
+
+def test_whole_path_matches_oracle(emu_lib):
+    for (w, h, preset, ch, structure, pair) in [(64, 64, "circles_bw", (1, 4, 8, 8), 1, 0),
+                                                (64, 64, "free", (3, 4, 6, 8), 2, 1)]:
+        c, n = ch[0], 3
+        eng = E.Engine(w, h, ch, n, lib=emu_lib)
+        eng.set_grid(structure)
+        wts = W.synthetic_weights(w, h, ch, seed=2)
+        eng.load_weights(wts)
+        cfg = G.make_config(2, G.NEAT_PRESETS[preset]["num_outputs"])
+        gc = cfg.genome_config
+        pop = [G.synthetic_genome(preset, i) for i in range(n)]
+        progs = [G.flatten_genome(g, cfg, n_outputs=c) for g in pop]
+        fit = eng.evaluate(progs, structure, pair_mode=pair)
+        ref, ex = OPL.evaluate_population(pop, gc.input_keys, gc.output_keys, structure, wts, w, h, ch, c,
+                                          pair_mode=pair, keep=True)
+        dbg = eng.debug_buffers(n)
+        assert list(dbg["nvec"]) == [len(e["vectors"]) for e in ex]
+        assert np.allclose(fit, ref, rtol=1e-3, atol=1e-9)
+        eng.close()

@@ -1,0 +1,118 @@
+"""Host-side logic and the C-ABI surface (no compute calls): CPU only."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from evolutionary_illusion_generator_b200 import _lib, genome as G, grid as PG, runtime, weights as W
+from flat_interp import render_flat
+from oracle import cppn as OC, grid as OG
+
+
+def test_grid_matches_oracle_all_structures():
+    for s in range(4):
+        for (w, h) in [(160, 120), (64, 64), (320, 240)]:
+            if s == 0 and w % 10:
+                continue
+            a, b = OG.create_grid(s, w, h, 10), PG.create_grid(s, w, h, 10)
+            assert np.array_equal(a["x_mat"], b["x_mat"]) and np.array_equal(a["y_mat"], b["y_mat"])
+
+
+def test_flattener_matches_oracle_on_evolved_genomes():
+    w, h = 48, 40
+    for preset, c_dim, structure in (("circles_bw", 1, 1), ("circles", 3, 1), ("free", 3, 2)):
+        grid = OG.create_grid(structure, w, h, 10)
+        n_out = G.NEAT_PRESETS[preset]["num_outputs"]
+        cfg = G.make_config(2, n_out)
+        gc = cfg.genome_config
+        n_const = 0
+        for i in range(200, 260):
+            g = G.synthetic_genome(preset, i, evolved=True)
+            prog = G.flatten_genome(g, cfg, n_outputs=c_dim if c_dim > 1 else 1)
+            n_const += any(s == G.SLOT_ONE for _, s in prog.terms)
+            want = OC.render(grid, g, c_dim, w, h, gc.input_keys, gc.output_keys)
+            assert np.array_equal(render_flat(prog, grid, c_dim, w, h), want), (preset, i)
+        assert n_const > 5  # the constant-folding rule is actually exercised
+
+
+def test_flattener_edge_cases():
+    cfg = G.make_config(2, 1)
+    g = G.Genome()
+    g.nodes[0] = G.NodeGene(0, 0.25, 1.0, "sigmoid", "sum")
+    prog = G.flatten_genome(g, cfg)           # output without inputs: constant bias, activation skipped
+    assert len(prog.nodes) == 1 and prog.out_slots[0] & G.OUT_F32_CONST
+    assert prog.terms[0][0] == float(np.float32(0.25))
+    g.connections[(-1, 0)] = G.ConnectionGene((-1, 0), 2.0, enabled=False)
+    assert G.flatten_genome(g, cfg).terms[0][1] == G.SLOT_ONE   # disabled connection is dropped
+    g.connections[(-1, 0)].enabled = True
+    g.nodes[0].aggregation = "prod"
+    p = G.flatten_genome(g, cfg)
+    assert p.nodes[0][1] == G.AGG_IDS["prod"] and p.terms[0] == (2.0, G.SLOT_X)
+    with pytest.raises(ValueError):
+        G.flatten_genome(g, G.make_config(4, 1))   # default.txt's 4 inputs (cppn.py:198 asserts too)
+    blob, off, slots = G.pack_population([p, p])
+    assert off[1] * 2 == off[2] == len(blob) and off[1] % 8 == 0 and slots == 4
+
+
+def test_weight_layout_and_checks():
+    ch = (3, 48, 96, 192)
+    shapes = W.expected_shapes(160, 120, ch)
+    assert shapes["predictor/ConvLSTM1/x_i1/W"] == (48, 96, 3, 3)
+    assert shapes["predictor/ConvLSTM3/c_o/W"] == (1, 192, 15, 20)
+    assert "predictor/ConvLSTM3/x_i1/W" not in shapes and "predictor/ConvA0/W" not in shapes
+    n_params = sum(int(np.prod(s)) for s in shapes.values())
+    assert abs(n_params - 8.30e6) < 0.05e6   # 8.30 M parameters
+    wts = W.synthetic_weights(64, 64, (1, 4, 8, 8), seed=0)
+    W.check_weights(wts, 64, 64, (1, 4, 8, 8))
+    with pytest.raises(ValueError):
+        W.check_weights(wts, 72, 64, (1, 4, 8, 8))   # peephole maps tie a file to one resolution
+
+
+def test_shard_bounds_cover_population_in_order():
+    for n in (1, 5, 32, 33, 128, 1024):
+        for world in (1, 2, 3, 4, 8):
+            got = []
+            for r in range(world):
+                lo, hi, per = runtime.shard_bounds(n, r, world)
+                assert hi - lo <= per
+                got += list(range(lo, hi))
+            assert got == list(range(n))
+
+
+def test_libeig_exports_every_symbol_of_the_header():
+    header = open(os.path.join(ROOT, "include", "eig.h")).read()
+    declared = set(re.findall(r"\b(eig_[a-z_]+)\s*\(", header))
+    assert declared == {name for name, _, _ in _lib.SYMBOLS}
+    if not os.path.isfile(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    dll = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(dll, name), name
+    lib = _lib.EigLibrary(_lib.LIB_PATH)
+    assert lib.eig_version() >= 100
+
+
+def test_product_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from evolutionary_illusion_generator_b200 import engine as E
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        E.Engine(64, 64, (1, 4, 8, 8), 2)
+    lib = _lib.EigLibrary(_lib.LIB_PATH)
+    ctx = ctypes.c_void_p()
+    rc = lib.eig_create(ctypes.byref(ctx), 0, 64, 64, 1, (ctypes.c_int * 4)(1, 4, 8, 8), 2)
+    assert rc == _lib.EIG_E_NODEVICE and b"no CPU fallback" in lib.eig_last_error()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "evolutionary_illusion_generator_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+            assert "tests.emu" not in src and "libeig_emu" not in src, f

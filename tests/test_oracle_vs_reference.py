@@ -1,0 +1,73 @@
+"""Pins the oracle against the REFERENCE's own code, imported unmodified under stubs (build container only;
+skipped on the GPU box where /root/reference does not exist)."""
+import numpy as np
+import pytest
+
+from conftest import ref_available
+from evolutionary_illusion_generator_b200 import genome as G, grid as PG
+from oracle import cppn as OC, grid as OG, scoring as OS
+
+pytestmark = [pytest.mark.needs_reference,
+              pytest.mark.skipif(not ref_available(), reason="reference tree not mounted")]
+
+
+@pytest.fixture(scope="module")
+def ns():
+    import ref_harness
+    return ref_harness.load()
+
+
+def test_grids_match_reference(ns):
+    for s in range(4):
+        for (w, h) in [(160, 120), (64, 64)]:
+            if s == 0 and w % 10:
+                continue
+            ref = ns.gi.create_grid(ns.gi.StructureType(s), w, h, 10)
+            for impl in (OG.create_grid(s, w, h, 10), PG.create_grid(s, w, h, 10)):
+                assert np.array_equal(np.asarray(ref["x_mat"]).reshape(h, w), impl["x_mat"])
+                assert np.array_equal(np.asarray(ref["y_mat"]).reshape(h, w), impl["y_mat"])
+
+
+def test_render_matches_reference_on_fresh_genomes(ns):
+    w, h = 64, 64
+    grid = ns.gi.create_grid(ns.gi.StructureType.Circles, w, h, 10)
+    for preset, c_dim in (("circles_bw", 1), ("circles", 3)):
+        cfg = G.make_config(2, G.NEAT_PRESETS[preset]["num_outputs"])
+        gc = cfg.genome_config
+        for i in range(100, 130):
+            g = G.synthetic_genome(preset, i, evolved=bool(i % 2))
+            ref = np.asarray(ns.gi.get_image_from_cppn(grid, g, c_dim, w, h, cfg))
+            got = OC.render(grid, g, c_dim, w, h, gc.input_keys, gc.output_keys)
+            assert np.array_equal(ref, got), (preset, i)
+
+
+def test_scoring_matches_reference_functions(ns):
+    rng = np.random.RandomState(11)
+    w, h = 160, 120
+    for _ in range(40):
+        n = rng.randint(2, 100)
+        v = np.zeros((n, 4), np.float32)
+        v[:, 0], v[:, 1] = rng.uniform(0, w, n), rng.uniform(0, h, n)
+        v[:, 2:] = rng.normal(0, 0.1, (n, 2))
+        assert OS.strength_number(v, 0.3) == ns.fc.strength_number(v, 0.3)
+        assert OS.swarm_score(v) == ns.fc.swarm_score(v)
+        assert OS.rotation_symmetry_score(v, w, h, [0, h / 2]) == ns.fc.rotation_symmetry_score(v, w, h, [0, h / 2])
+        assert OS.horizontal_symmetry_score(v, [0, 60.0]) == ns.fc.horizontal_symmetry_score(v, [0, 60.0])
+
+
+def test_reference_test_cppn_cases_pass_under_stub():
+    """The reference's own four known-answer tests (pytorch_neat/tests/test_cppn.py) run here unmodified
+    (in a subprocess: they import the inner package as top-level `pytorch_neat`)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, types\n"
+        "sys.path.insert(0, '/root/repo/tests/golden'); import ref_harness\n"
+        "neat = types.ModuleType('neat'); g = types.ModuleType('neat.graphs')\n"
+        "g.required_for_output = ref_harness.required_for_output; neat.graphs = g\n"
+        "sys.modules['neat'] = neat; sys.modules['neat.graphs'] = g\n"
+        "sys.path.insert(0, '/root/reference/pytorch_neat'); sys.path.insert(0, '/root/reference/pytorch_neat/tests')\n"
+        "import test_cppn as t\n"
+        "t.test_cppn_simple(); t.test_cppn_unconnected(); t.test_cppn_call(); t.test_cppn_deep_call(); print('OK4')\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "OK4" in out.stdout, out.stderr[-2000:]
