@@ -1,6 +1,9 @@
 // libeig.so: context, weight repacking, stage orchestration and the C ABI (include/eig.h).
 // Host-side C++ only orchestrates; every number on the hot path is produced by the CUDA kernels in
 // render.cuh / conv_simt.cuh / conv_tc.cuh / flow.cuh / score.cuh.  There is no CPU fallback.
+#include <map>
+#include <string>
+#include <vector>
 #ifdef EIG_EMU
 #include "cuda_emu.h"
 #endif
@@ -14,9 +17,6 @@
 #endif
 #include "../../include/eig.h"
 
-#include <map>
-#include <string>
-#include <vector>
 
 using namespace eig;
 #define TO_STREAM(p) ((cudaStream_t)(intptr_t)(p))
@@ -36,6 +36,34 @@ static int fail(int code, const std::string& msg) {
     do {                                                                                              \
         cudaError_t e_ = cudaGetLastError();                                                          \
         if (e_ != cudaSuccess) return fail(EIG_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+    } while (0)
+
+// Optional per-kernel-class device timing (bench.py's roofline pass): every launch is bracketed by a pair of
+// CUDA events on the launching stream; eig_profile_end sums them per class.
+enum { CLS_RENDER = 0, CLS_CONV_SIMT = 1, CLS_CONV_TC = 2, CLS_ELEMENTWISE = 3, CLS_FLOW = 4, CLS_SCORE = 5, CLS_COUNT = 8 };
+struct Profiler {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> cls;
+};
+static Profiler g_prof;
+static void prof_pre(int cls, cudaStream_t s) {
+    if (!g_prof.on) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, s);
+    g_prof.ev.push_back(a); g_prof.ev.push_back(b); g_prof.cls.push_back(cls);
+}
+static void prof_post(cudaStream_t s) {
+    if (!g_prof.on) return;
+    cudaEventRecord(g_prof.ev.back(), s);
+}
+#define LAUNCH_K(cls, kernel, grid, block, smem, s, ...)              \
+    do {                                                              \
+        prof_pre(cls, s);                                             \
+        EIG_LAUNCH(kernel, grid, block, smem, s, __VA_ARGS__);        \
+        prof_post(s);                                                 \
+        EIG_COUNT_LAUNCH();                                           \
     } while (0)
 
 struct LayerW {            // repacked weights of one PredNet layer (device)
@@ -302,16 +330,15 @@ static int launch_conv(eig_ctx* c, const ConvArgs& a, cudaStream_t s) {
         const int nw = (a.N + 3) / 4;
         const size_t smem = (8 * 10 * 20 + 9 * 8 * nw * 4) * sizeof(float);
         auto k = conv3x3_simt_kernel<4>;
-        EIG_LAUNCH(k, dim3(tiles, a.B, 1), dim3(32 * nw), smem, s, a);
+        LAUNCH_K(CLS_CONV_SIMT, k, dim3(tiles, a.B, 1), dim3(32 * nw), smem, s, a);
     } else {
         int nw = (a.N + 15) / 16;
         if (nw > 4) nw = 4;
         const int gz = (a.N + nw * 16 - 1) / (nw * 16);
         const size_t smem = (8 * 10 * 20 + 9 * 8 * nw * 16) * sizeof(float);
         auto k = conv3x3_simt_kernel<16>;
-        EIG_LAUNCH(k, dim3(tiles, a.B, gz), dim3(32 * nw), smem, s, a);
+        LAUNCH_K(CLS_CONV_SIMT, k, dim3(tiles, a.B, gz), dim3(32 * nw), smem, s, a);
     }
-    EIG_COUNT_LAUNCH();
     (void)c;
     CKL();
     return EIG_OK;
@@ -327,9 +354,8 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
     {   // E0 -> X0[cur].E
         const long long npix = (long long)B * c->h * c->w;
         const long long tot = npix * c->c_dim;
-        EIG_LAUNCH(error0_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, x, (const float*)c->P[0],
+        LAUNCH_K(CLS_ELEMENTWISE, error0_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, x, (const float*)c->P[0],
                    mkview(c->X[0][cur], nullptr, c->ctot[0], 0, 2 * c->ch[0]), npix, c->c_dim);
-        EIG_COUNT_LAUNCH();
         CKL();
     }
     for (int n = 1; n < 4; ++n) {  // ConvA_n: E_{n-1} (res n-1) -> pool -> E_n
@@ -342,7 +368,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         a.epi = EPI_CONVA; a.P = c->P[n];
         a.dstE = mkview(c->X[n][cur], c->Xlo[n][cur], c->ctot[n], 0, 2 * c->ch[n]);
 #ifndef EIG_EMU
-        if (tc && n >= 2) { if ((rc = tc_conv(c->lw[n].tcA, a, s))) return fail(EIG_E_CUDA, "tc_conv ConvA: " + tc_last_error()); continue; }
+        if (tc && n >= 2) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcA, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvA: " + tc_last_error()); continue; }
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }
@@ -358,7 +384,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         a.dstH = mkview(c->X[n][nxt], c->Xlo[n][nxt], c->ctot[n], hoff, c->ch[n]);
         if (n >= 1) a.dstUp = mkview(c->X[n - 1][cur], c->Xlo[n - 1][cur], c->ctot[n - 1], 2 * c->ch[n - 1], c->ch[n]);
 #ifndef EIG_EMU
-        if (tc && n >= 1) { if ((rc = tc_conv(c->lw[n].tcL, a, s))) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); continue; }
+        if (tc && n >= 1) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); continue; }
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }
@@ -372,7 +398,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         a.wgt = c->lw[n].convP; a.bias = c->lw[n].convP_b; a.N = c->ch[n]; a.Npad = (c->ch[n] + 3) & ~3;
         a.epi = EPI_CONVP; a.outP = c->P[n]; a.clip = n == 0;
 #ifndef EIG_EMU
-        if (tc && n >= 1) { if ((rc = tc_conv(c->lw[n].tcP, a, s))) return fail(EIG_E_CUDA, "tc_conv ConvP: " + tc_last_error()); continue; }
+        if (tc && n >= 1) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcP, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvP: " + tc_last_error()); continue; }
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }
@@ -408,9 +434,8 @@ static int prednet_sequence(eig_ctx* c, const float* d_x, int B, int n_in, int n
             unsigned char* fo = frames_out ? frames_out + (size_t)k * npix * c->c_dim : nullptr;
             unsigned char* go = gray_dst ? gray_dst[k] : nullptr;
             if (fo || go) {
-                EIG_LAUNCH(quantize_gray_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s,
+                LAUNCH_K(CLS_ELEMENTWISE, quantize_gray_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s,
                            (const float*)c->P[0], fo, go, npix, c->c_dim);
-                EIG_COUNT_LAUNCH();
                 CKL();
             }
         }
@@ -445,8 +470,7 @@ extern "C" int eig_cppn_render(eig_ctx* c, const void* d_blob, const int64_t* d_
     if (smem > 200 * 1024) return fail(EIG_E_CAPACITY, "eig_cppn_render: genome program too large for shared memory");
     auto k = cppn_render_kernel;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    EIG_LAUNCH(k, dim3((a.npix + nt - 1) / nt, n), dim3(nt), smem, TO_STREAM(stream), a);
-    EIG_COUNT_LAUNCH();
+    LAUNCH_K(CLS_RENDER, k, dim3((a.npix + nt - 1) / nt, n), dim3(nt), smem, TO_STREAM(stream), a);
     CKL();
     return EIG_OK;
 }
@@ -465,27 +489,23 @@ static int flow_from_gray(eig_ctx* c, int B, cudaStream_t s) {
     for (int l = 1; l < c->n_levels; ++l) {
         // frame-2 images of every level sit right after the B frame-1 images actually in use
         const long long tot = 2LL * B * c->lh[l] * c->lwid[l];
-        EIG_LAUNCH(pyr_down_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, (const unsigned char*)c->gray[l - 1],
+        LAUNCH_K(CLS_FLOW, pyr_down_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, (const unsigned char*)c->gray[l - 1],
                    c->gray[l], c->lh[l - 1], c->lwid[l - 1], c->lh[l], c->lwid[l], 2 * B);
-        EIG_COUNT_LAUNCH();
         CKL();
     }
     for (int l = 0; l < c->n_levels; ++l) {
         const long long tot = (long long)B * c->lh[l] * c->lwid[l];
-        EIG_LAUNCH(scharr_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, (const unsigned char*)c->gray[l],
+        LAUNCH_K(CLS_FLOW, scharr_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, (const unsigned char*)c->gray[l],
                    c->deriv[l], c->lh[l], c->lwid[l], B);
-        EIG_COUNT_LAUNCH();
         CKL();
     }
     CK(cudaMemsetAsync(c->eigmax, 0x80, sizeof(int) * B, s));  // 0x80808080: below every real key
     EigArgs ea; ea.gray = c->gray[0]; ea.eig = c->eigmap; ea.eig_max_key = c->eigmax; ea.H = H; ea.W = W;
-    EIG_LAUNCH(min_eig_kernel, dim3(((W + 31) / 32) * ((H + 15) / 16), B), dim3(256), 0, s, ea);
-    EIG_COUNT_LAUNCH();
+    LAUNCH_K(CLS_FLOW, min_eig_kernel, dim3(((W + 31) / 32) * ((H + 15) / 16), B), dim3(256), 0, s, ea);
     CKL();
     CornerArgs ca; ca.eig = c->eigmap; ca.eig_max_key = c->eigmax; ca.cand = c->cand; ca.corners = c->corners;
     ca.ncorners = c->ncorners; ca.H = H; ca.W = W;
-    EIG_LAUNCH(corner_select_kernel, dim3(B), dim3(256), 0, s, ca);
-    EIG_COUNT_LAUNCH();
+    LAUNCH_K(CLS_FLOW, corner_select_kernel, dim3(B), dim3(256), 0, s, ca);
     CKL();
     LkArgs la;
     memset(&la, 0, sizeof la);
@@ -497,13 +517,11 @@ static int flow_from_gray(eig_ctx* c, int B, cudaStream_t s) {
     }
     la.n_levels = c->n_levels; la.corners = c->corners; la.ncorners = c->ncorners; la.next_pts = c->next_pts;
     la.status = c->status; la.B = B;
-    EIG_LAUNCH(lk_track_kernel, dim3((B * FLOW_MAX_CORNERS + LK_WARPS_PER_BLOCK - 1) / LK_WARPS_PER_BLOCK),
+    LAUNCH_K(CLS_FLOW, lk_track_kernel, dim3((B * FLOW_MAX_CORNERS + LK_WARPS_PER_BLOCK - 1) / LK_WARPS_PER_BLOCK),
                dim3(32 * LK_WARPS_PER_BLOCK), 0, s, la);
-    EIG_COUNT_LAUNCH();
     CKL();
-    EIG_LAUNCH(collect_vectors_kernel, dim3((B + 63) / 64), dim3(64), 0, s, (const float*)c->corners, (const int*)c->ncorners,
+    LAUNCH_K(CLS_FLOW, collect_vectors_kernel, dim3((B + 63) / 64), dim3(64), 0, s, (const float*)c->corners, (const int*)c->ncorners,
                (const float*)c->next_pts, (const unsigned char*)c->status, c->vectors, c->nvec, B);
-    EIG_COUNT_LAUNCH();
     CKL();
     return EIG_OK;
 }
@@ -516,9 +534,8 @@ extern "C" int eig_flow(eig_ctx* c, const uint8_t* d_img1, const uint8_t* d_img2
     CK(cudaSetDevice(c->device));
     cudaStream_t s = TO_STREAM(stream);
     const long long npix = (long long)n * c->h * c->w;
-    EIG_LAUNCH(gray_u8_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, d_img1, c->gray[0], npix, c->c_dim);
-    EIG_LAUNCH(gray_u8_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, d_img2, c->gray[0] + npix, npix, c->c_dim);
-    EIG_COUNT_LAUNCH(); EIG_COUNT_LAUNCH();
+    LAUNCH_K(CLS_ELEMENTWISE, gray_u8_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, d_img1, c->gray[0], npix, c->c_dim);
+    LAUNCH_K(CLS_ELEMENTWISE, gray_u8_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, d_img2, c->gray[0] + npix, npix, c->c_dim);
     CKL();
     if ((rc = flow_from_gray(c, n, s))) return rc;
     CK(cudaMemcpyAsync(d_vectors, c->vectors, sizeof(float) * n * FLOW_MAX_CORNERS * 4, cudaMemcpyDeviceToDevice, s));
@@ -531,8 +548,7 @@ extern "C" int eig_flow(eig_ctx* c, const uint8_t* d_img1, const uint8_t* d_img2
 static int score_launch(eig_ctx* c, const float* vec, const int* nvec, int n, int structure, double* fit, cudaStream_t s) {
     if (structure < 0 || structure > 3) return fail(EIG_E_INVALID, "unknown structure id");
     ScoreArgs sa; sa.vectors = vec; sa.nvec = nvec; sa.fitness = fit; sa.B = n; sa.structure = structure; sa.w = c->w; sa.h = c->h;
-    EIG_LAUNCH(score_kernel, dim3(n), dim3(32), 0, s, sa);
-    EIG_COUNT_LAUNCH();
+    LAUNCH_K(CLS_SCORE, score_kernel, dim3(n), dim3(32), 0, s, sa);
     CKL();
     return EIG_OK;
 }
@@ -562,8 +578,7 @@ extern "C" int eig_eval(eig_ctx* c, const void* d_blob, const int64_t* d_offsets
         gd[0] = g1; gd[1] = g2; gd[2] = nullptr; n_ext = 1;   // the reference's 22nd forward is dead work
     } else {
         gd[0] = nullptr; gd[1] = nullptr; gd[2] = g2; n_ext = 2;
-        EIG_LAUNCH(gray_u8_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, (const unsigned char*)c->img, g1, npix, c->c_dim);
-        EIG_COUNT_LAUNCH();
+        LAUNCH_K(CLS_ELEMENTWISE, gray_u8_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, (const unsigned char*)c->img, g1, npix, c->c_dim);
         CKL();
     }
     if ((rc = prednet_sequence(c, c->x_in, n, 20, n_ext, c->frames, gd, s))) return rc;
@@ -606,5 +621,29 @@ extern "C" int eig_debug_buffers(eig_ctx* c, uint8_t** d_img, uint8_t** d_frames
     if (d_nvec) *d_nvec = c->nvec;
     if (d_corners) *d_corners = c->corners;
     if (d_ncorners) *d_ncorners = c->ncorners;
+    return EIG_OK;
+}
+
+extern "C" int eig_profile_begin(eig_ctx* c) {
+    if (!c) return fail(EIG_E_INVALID, "null ctx");
+    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+    g_prof.ev.clear(); g_prof.cls.clear();
+    g_prof.on = true;
+    return EIG_OK;
+}
+
+extern "C" int eig_profile_end(eig_ctx* c, double* ms_per_class, int64_t* launches_per_class) {
+    if (!c || !ms_per_class || !launches_per_class) return fail(EIG_E_INVALID, "eig_profile_end: null pointer");
+    g_prof.on = false;
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < CLS_COUNT; ++i) { ms_per_class[i] = 0.0; launches_per_class[i] = 0; }
+    for (size_t i = 0; i < g_prof.cls.size(); ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+        ms_per_class[g_prof.cls[i]] += ms;
+        launches_per_class[g_prof.cls[i]] += 1;
+    }
+    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+    g_prof.ev.clear(); g_prof.cls.clear();
     return EIG_OK;
 }

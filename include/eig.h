@@ -95,6 +95,12 @@ int eig_eval_host(eig_ctx* ctx, const void* h_blob, const int64_t* h_offsets, in
 int eig_debug_buffers(eig_ctx* ctx, uint8_t** d_img, uint8_t** d_frames, float** d_vectors, int** d_nvec,
                       float** d_corners, int** d_ncorners);
 
+/* Per-kernel-class device timing for bench.py's roofline pass: between begin and end every kernel launch is
+ * bracketed by CUDA events on its stream.  Classes: 0 render, 1 conv SIMT, 2 conv tcgen05, 3 element-wise,
+ * 4 flow, 5 score (arrays of 8).  eig_profile_end synchronises the device. */
+int eig_profile_begin(eig_ctx* ctx);
+int eig_profile_end(eig_ctx* ctx, double* ms_per_class, int64_t* launches_per_class);
+
 #ifdef __cplusplus
 }
 #endif
