@@ -32,6 +32,7 @@ SYMBOLS = [
     ("eig_eval", _I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     ("eig_eval_host", _I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     ("eig_debug_buffers", _I, [_P] + [C.POINTER(_P)] * 6),
+    ("eig_memcpy_d2h", _I, [_P, _P, C.c_int64]),
     ("eig_profile_begin", _I, [_P]),
     ("eig_profile_end", _I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 ]

@@ -5,4 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --fmad=false \
       -Xcompiler -fPIC -shared ${EIG_NVCC_EXTRA:-} -o ../libeig.so eig_api.cu -lcudart_static -ldl -lrt -lpthread
+# GPU self-check of the tcgen05 convolution (run by tests/test_gpu_parity.py on the B200)
+$NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --fmad=false ${EIG_NVCC_EXTRA:-} \
+      -o ../../tests/gpu/tc_check ../../tests/gpu/tc_check.cu -lcudart_static -ldl -lrt -lpthread
 echo "built $(cd .. && pwd)/libeig.so"

@@ -267,7 +267,7 @@ extern "C" int eig_load_weights(eig_ctx* c, int nt, const char* const* names, co
             for (int i = 0; i < C; ++i) bv[i] = t->p[i];
             CK(upload(c, &L.convA, wv)); CK(upload(c, &L.convA_b, bv));
 #ifndef EIG_EMU
-            if ((rc = tc_pack(L.tcA, wv.data(), cin, C, npad))) return fail(EIG_E_CUDA, "tc_pack ConvA failed");
+            if (n >= 2 && (rc = tc_pack(L.tcA, wv.data(), cin, C, npad))) return fail(EIG_E_CUDA, "tc_pack ConvA: " + tc_last_error());
 #endif
         }
         {
@@ -281,7 +281,7 @@ extern "C" int eig_load_weights(eig_ctx* c, int nt, const char* const* names, co
             for (int i = 0; i < C; ++i) bv[i] = t->p[i];
             CK(upload(c, &L.convP, wv)); CK(upload(c, &L.convP_b, bv));
 #ifndef EIG_EMU
-            if (n >= 1 && (rc = tc_pack(L.tcP, wv.data(), cin, C, npad))) return fail(EIG_E_CUDA, "tc_pack ConvP failed");
+            if (n >= 1 && (rc = tc_pack(L.tcP, wv.data(), cin, C, npad))) return fail(EIG_E_CUDA, "tc_pack ConvP: " + tc_last_error());
 #endif
         }
         {
@@ -315,7 +315,7 @@ extern "C" int eig_load_weights(eig_ctx* c, int nt, const char* const* names, co
             }
             CK(upload(c, &L.lstm, wv)); CK(upload(c, &L.lstm_b, bv)); CK(upload(c, &L.peep, pv));
 #ifndef EIG_EMU
-            if (n >= 1 && (rc = tc_pack(L.tcL, wv.data(), ctot, N, N))) return fail(EIG_E_CUDA, "tc_pack ConvLSTM failed");
+            if (n >= 1 && (rc = tc_pack(L.tcL, wv.data(), ctot, N, N))) return fail(EIG_E_CUDA, "tc_pack ConvLSTM: " + tc_last_error());
 #endif
         }
     }
@@ -368,7 +368,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         a.epi = EPI_CONVA; a.P = c->P[n];
         a.dstE = mkview(c->X[n][cur], c->Xlo[n][cur], c->ctot[n], 0, 2 * c->ch[n]);
 #ifndef EIG_EMU
-        if (tc && n >= 2) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcA, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvA: " + tc_last_error()); continue; }
+        if (tc && n >= 2 && c->lw[n].tcA.ok) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcA, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvA: " + tc_last_error()); continue; }
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }
@@ -384,7 +384,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         a.dstH = mkview(c->X[n][nxt], c->Xlo[n][nxt], c->ctot[n], hoff, c->ch[n]);
         if (n >= 1) a.dstUp = mkview(c->X[n - 1][cur], c->Xlo[n - 1][cur], c->ctot[n - 1], 2 * c->ch[n - 1], c->ch[n]);
 #ifndef EIG_EMU
-        if (tc && n >= 1) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); continue; }
+        if (tc && n >= 1 && c->lw[n].tcL.ok) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); continue; }
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }
@@ -398,7 +398,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         a.wgt = c->lw[n].convP; a.bias = c->lw[n].convP_b; a.N = c->ch[n]; a.Npad = (c->ch[n] + 3) & ~3;
         a.epi = EPI_CONVP; a.outP = c->P[n]; a.clip = n == 0;
 #ifndef EIG_EMU
-        if (tc && n >= 1) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcP, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvP: " + tc_last_error()); continue; }
+        if (tc && n >= 1 && c->lw[n].tcP.ok) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcP, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvP: " + tc_last_error()); continue; }
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }
@@ -621,6 +621,12 @@ extern "C" int eig_debug_buffers(eig_ctx* c, uint8_t** d_img, uint8_t** d_frames
     if (d_nvec) *d_nvec = c->nvec;
     if (d_corners) *d_corners = c->corners;
     if (d_ncorners) *d_ncorners = c->ncorners;
+    return EIG_OK;
+}
+
+extern "C" int eig_memcpy_d2h(void* h_dst, const void* d_src, int64_t bytes) {
+    if (!h_dst || !d_src || bytes < 0) return fail(EIG_E_INVALID, "eig_memcpy_d2h: bad argument");
+    CK(cudaMemcpy(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost));
     return EIG_OK;
 }
 

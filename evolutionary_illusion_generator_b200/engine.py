@@ -191,13 +191,7 @@ class Engine:
         def grab(ptr, shape, dtype):
             nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
             host = np.empty(shape, dtype=dtype)
-            if self.tdev.type == "cuda":
-                from torch.cuda import cudart
-                rc = cudart().cudaMemcpy(host.ctypes.data, ptr.value, nbytes, 2)
-                if int(rc[0] if isinstance(rc, tuple) else rc) != 0:
-                    raise RuntimeError("cudaMemcpy D2H failed: %r" % (rc,))
-            else:
-                C.memmove(host.ctypes.data, ptr.value, nbytes)
+            self.lib.check(self.lib.eig_memcpy_d2h(host.ctypes.data, ptr.value, nbytes))
             return host
 
         h, w, c = self.h, self.w, self.c_dim

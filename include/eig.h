@@ -95,6 +95,9 @@ int eig_eval_host(eig_ctx* ctx, const void* h_blob, const int64_t* h_offsets, in
 int eig_debug_buffers(eig_ctx* ctx, uint8_t** d_img, uint8_t** d_frames, float** d_vectors, int** d_nvec,
                       float** d_corners, int** d_ncorners);
 
+/* Synchronous device -> host copy of `bytes` bytes (tests read the debug taps with it; no torch type needed). */
+int eig_memcpy_d2h(void* h_dst, const void* d_src, int64_t bytes);
+
 /* Per-kernel-class device timing for bench.py's roofline pass: between begin and end every kernel launch is
  * bracketed by CUDA events on its stream.  Classes: 0 render, 1 conv SIMT, 2 conv tcgen05, 3 element-wise,
  * 4 flow, 5 score (arrays of 8).  eig_profile_end synchronises the device. */
