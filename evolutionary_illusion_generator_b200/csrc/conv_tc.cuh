@@ -45,7 +45,8 @@ struct TcParams {
     int KBn, Ncta, N;
     int a_plane_bytes, b_plane_bytes, a_box_bytes;
     int SA, SB;
-    int a_mode;  // 0: halo box + descriptor base offset, 1: halo box, base offset 0, 2: one box per tap
+    int a_mode;  // 1 (product): halo box, row-shifted descriptors with base offset 0; 2: one box per tap (9x the loads,
+                 // same numbers - kept as the cross-check); 0: base offset = row phase (WRONG on B200, kept for the probe)
     int tmem_cols;
     int stage_ld;  // floats per row of the ConvA staging tile
     ConvArgs ca;
@@ -137,6 +138,11 @@ __device__ __forceinline__ float lstm_cell_v(float gi, float gf, float gc, float
 
 __device__ __forceinline__ void view_store4(const View& v, long long pix, int c, const float* val) {
     const long long idx = pix * v.pitch + v.coff + c;
+    if ((v.pitch | v.coff) & 3) {  // layer-0 concat buffer (pitch 2*C0 + R1 + C0): not 16-byte aligned
+#pragma unroll
+        for (int i = 0; i < 4; ++i) view_store(v, pix, c + i, val[i]);
+        return;
+    }
     if (v.lo) {
         float4 h, l;
         h.x = tf32_round(val[0]); h.y = tf32_round(val[1]); h.z = tf32_round(val[2]); h.w = tf32_round(val[3]);
@@ -364,7 +370,7 @@ struct TcState {
     EigEncodeTiledFn encode = nullptr;
     bool probed = false, available = false;
     std::string reason, last_error;
-    int a_mode = 0;
+    int a_mode = 1;  // measured on B200: the 128B swizzle is a function of the absolute smem address, base offset stays 0
     int force_nt = 0;
     std::map<std::tuple<const void*, const void*, int, int, int, int, int, int, int>, std::pair<CUtensorMap, CUtensorMap>> amaps;
 };

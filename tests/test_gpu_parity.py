@@ -249,3 +249,14 @@ def test_full_size_properties_c2(gpu_engine_factory):
     print("C2 first 8 genomes rel err vs oracle:", np.array2string(rel, precision=2))
     assert (rel <= 1e-3).mean() >= 0.75
     assert (full > 0).mean() > 0.5
+
+
+def test_tcgen05_conv_self_check():
+    """tests/gpu/tc_check (built by csrc/build.sh): the tcgen05 conv against a float64 CPU convolution and, epilogue by
+    epilogue, against the exact-fp32 SIMT kernel on identical inputs."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpu", "tc_check")
+    assert os.path.isfile(exe), "tests/gpu/tc_check missing: run __graft_entry__.build()"
+    r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=300)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-500:]
