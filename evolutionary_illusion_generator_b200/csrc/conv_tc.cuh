@@ -3,22 +3,22 @@
 //
 // Reference semantics are those of conv_simt.cuh (Chainer `L.Convolution2D(cin, cout, 3, pad=1)` +
 // ConvLSTM / error-unit / pooling epilogues, /root/reference/chainer_prednet/PredNet/net.py:46-62,94-126,
-// 187-209); the SIMT kernel is the exact-fp32 twin this one is checked against on the GPU.
+// 187-209); the SIMT kernel is the exact-fp32 twin this one is checked against on the GPU (tests/gpu/tc_check.cu).
 //
 // GEMM view: D[m][n] = sum_{tap, c} A[m + shift(tap)][c] * Wt[tap][c][n]
 //   m   = "flat padded" pixel index inside a CTA region: m = h * P + w, P = TW + 2.  The CTA loads ONE halo box
-//         (32 channels x P columns x NT*TH+2 rows) per 32-channel block with a single 4-D TMA (negative / out of
+//         (KBT channels x P columns x NT*TH+2 rows) per channel block with a single 4-D TMA (negative / out of
 //         range coordinates are zero-filled by the TMA unit = the conv's zero padding) and the nine taps are nine
 //         row-shifted views of that box: tap (ky,kx) of MMA tile t starts (t*TH + ky) * P + kx rows into the box.
 //         Rows with w >= TW are computed and dropped (2/P waste); the halo is fetched once instead of 9 times.
-//   K   = 32 channels per block (one 128-byte swizzle row), UMMA_K = 8 -> 4 k-steps per (block, tap)
+//   K   = KBT channels per block (16 -> 64-byte swizzle rows, 32 -> 128-byte), UMMA_K = 8
 //   N   = output channels of this CTA (<= 256; the 4 gates of an LSTM cell are adjacent columns)
-// 3xTF32: activations and weights are stored as hi = tf32(v), lo = v - hi; every k-step issues
-//   lo*hi + hi*lo + hi*hi into the same fp32 TMEM accumulator (the lo*lo term, 2^-22 relative, is dropped).
-// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer, warp 5 MMA
-// issuer + TMEM allocator.  Two mbarrier rings: A (halo boxes, SA stages) and B (per-tap weight tiles, SB stages).
+// 3xTF32: activations live in HBM as plain fp32; the converter warps split each staged box into hi = tf32(v) and
+//   lo = v - hi in shared memory, weights are pre-split on the host; every k-step issues lo*hi + hi*lo + hi*hi into
+//   the same fp32 TMEM accumulator (the lo*lo term, 2^-22 relative, is dropped).
 #pragma once
 #include <cuda.h>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <tuple>
@@ -29,11 +29,11 @@
 namespace eig {
 
 enum { EPI_RAW = 3 };  // test only: out = acc + bias, no activation (conv3x3_tc_kernel only)
-enum { TC_KB = 32, TC_THREADS = 192, TC_SMEM_LIMIT = 227 * 1024 };
+enum { TC_THREADS = 512, TC_SMEM_LIMIT = 227 * 1024 };
 
 struct TcWeights {
-    float* d = nullptr;  // [2 planes][9 taps][KBn][N][32] fp32 (hi plane, then lo plane)
-    int cin = 0, N = 0, KBn = 0, Ncta = 0, gz = 1;
+    float* d = nullptr;  // [2 planes][9 taps][KBn][N][KBT] fp32 (hi plane, then lo plane)
+    int cin = 0, N = 0, KBT = 16, KBn = 0, Ncta = 0, gz = 1;
     CUtensorMap map;
     bool ok = false;
 };
@@ -41,14 +41,12 @@ struct TcWeights {
 struct TcParams {
     int B, H, W;
     int TW, TH, P, NT;
-    int tiles_x, tiles_y;
+    int tiles_x, tiles_y, regions;
     int KBn, Ncta, N;
     int a_plane_bytes, b_plane_bytes, a_box_bytes;
     int SA, SB;
-    int a_mode;  // 1 (product): halo box, row-shifted descriptors with base offset 0; 2: one box per tap (9x the loads,
-                 // same numbers - kept as the cross-check); 0: base offset = row phase (WRONG on B200, kept for the probe)
     int tmem_cols;
-    int stage_ld;  // floats per row of the ConvA staging tile
+    int staging_bytes, stage_ld;  // ConvA pooling tile: 128 rows x stage_ld floats
     ConvArgs ca;
 };
 
@@ -114,18 +112,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row atoms 1024 bytes apart
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t base_off) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;            // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset: next 8-row group
-    d |= (uint64_t)1 << 46;            // descriptor version (sm_100)
-    d |= (uint64_t)(base_off & 7u) << 49;
-    d |= (uint64_t)2 << 61;            // SWIZZLE_128B
-    return d;
-}
-
 __device__ __forceinline__ float lstm_cell_v(float gi, float gf, float gc, float go, const float4 b, const float4 pe,
                                              float c_old, float* c_new) {
     const float i = chainer_sigmoid(__fadd_rn(__fadd_rn(gi, b.x), __fmul_rn(c_old, pe.x)));
@@ -155,9 +141,55 @@ __device__ __forceinline__ void view_store4(const View& v, long long pix, int c,
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
+template <int KBT> struct TcSwz;
+template <> struct TcSwz<32> { static constexpr uint64_t layout = 2, sbo = 1024; };  // SWIZZLE_128B
+template <> struct TcSwz<16> { static constexpr uint64_t layout = 4, sbo = 512; };   // SWIZZLE_64B
+
+// K-major swizzled shared-memory matrix descriptor (rows of KBT*4 bytes, 8-row atoms `sbo` bytes apart).  Measured on
+// B200 (tests/gpu/tc_check): the swizzle XOR is a function of the absolute smem address, so a start address shifted by
+// whole rows is legal with base offset 0 - that is what makes the nine taps nine views of one halo box.
+template <int KBT>
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(TcSwz<KBT>::sbo >> 4) << 32;  // stride byte offset: next 8-row group
+    d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+    d |= TcSwz<KBT>::layout << 61;
+    return d;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+struct TcRegion { int x0, y0, b, n0; };
+__device__ __forceinline__ TcRegion tc_region(const TcParams& p, int reg) {
+    TcRegion r;
+    const int tiles = p.tiles_x * p.tiles_y;
+    const int tile = reg % tiles;
+    const int rest = reg / tiles;
+    r.b = rest % p.B;
+    r.n0 = (rest / p.B) * p.Ncta;
+    r.x0 = (tile % p.tiles_x) * p.TW;
+    r.y0 = (tile / p.tiles_x) * (p.NT * p.TH);
+    return r;
+}
+
+// Persistent, warp-specialised: grid = min(regions, #SM) CTAs of 512 threads, each looping over CTA regions
+// (NT stacked MMA tiles of one genome x Ncta output channels).
+//   warps 0-3   converter: raw fp32 halo box (TMA) -> hi = tf32(v) in place, lo = v - hi in the second plane
+//   warp  4     weight producer (one thread): per-tap weight tiles, hi and lo planes (pre-split on the host)
+//   warp  5     MMA issuer (one thread) + TMEM allocator; accumulators double-buffered in TMEM
+//   warp  6     activation producer (one thread): one halo box per channel block, runs SA stages ahead
+//   warp  7     idle
+//   warps 8-15  epilogue (TMEM lane quarter = warp & 3, column half = (warp - 8) >> 2): drains accumulator set i
+//               while set i^1 is being computed
+template <int KBT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
-                  const __grid_constant__ CUtensorMap mB, const TcParams p) {
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, const TcParams p) {
+    constexpr int RB = KBT * 4;       // bytes per operand row
+    constexpr int KSTEPS = KBT / 8;   // UMMA_K = 8 for tf32
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -168,20 +200,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_consta
     const int a_stage_bytes = 2 * p.a_plane_bytes, b_stage_bytes = 2 * p.b_plane_bytes;
     const uint32_t sA = sbase, sB = sbase + p.SA * a_stage_bytes;
     const uint32_t pipe_bytes = p.SA * a_stage_bytes + p.SB * b_stage_bytes;
-    const uint32_t sBar = sbase + pipe_bytes;  // fullA[SA], emptyA[SA], fullB[SB], emptyB[SB], accFull
-    const uint32_t fullA = sBar, emptyA = sBar + 8 * p.SA, fullB = sBar + 16 * p.SA, emptyB = fullB + 8 * p.SB;
-    const uint32_t accFull = emptyB + 8 * p.SB;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pipe_bytes + 8 * (2 * p.SA + 2 * p.SB + 1));
-
-    const int tile = blockIdx.x;
-    const int x0 = (tile % p.tiles_x) * p.TW, y0 = (tile / p.tiles_x) * (p.NT * p.TH);
-    const int b = blockIdx.y;
-    const int n0 = blockIdx.z * p.Ncta;
+    float* stage = reinterpret_cast<float*>(smem + pipe_bytes);
+    const uint32_t sBar = sbase + pipe_bytes + p.staging_bytes;
+    // barriers: fullA[SA] convA[SA] emptyA[SA] fullB[SB] emptyB[SB] accFull[2] accEmpty[2]
+    const uint32_t fullA = sBar, convA = fullA + 8 * p.SA, emptyA = convA + 8 * p.SA;
+    const uint32_t fullB = emptyA + 8 * p.SA, emptyB = fullB + 8 * p.SB;
+    const uint32_t accFull = emptyB + 8 * p.SB, accEmpty = accFull + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pipe_bytes + p.staging_bytes + 8 * (3 * p.SA + 2 * p.SB + 4));
 
     if (warp == 4 && lane == 0) {
-        for (int i = 0; i < p.SA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
+        for (int i = 0; i < p.SA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(convA + 8 * i, 4); mbar_init(emptyA + 8 * i, 1); }
         for (int i = 0; i < p.SB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
-        mbar_init(accFull, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, 1); mbar_init(accEmpty + 8 * i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
@@ -192,32 +222,61 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int acc_stride = p.NT * p.Ncta;
 
-    if (warp == 4) {
-        // ===== TMA producer =====
+    if (warp < 4) {
+        // ===== converter =====
+        const int chunks = p.a_box_bytes >> 4;
+        int ia = 0;
+        for (int reg = blockIdx.x; reg < p.regions; reg += gridDim.x) {
+            for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
+                const int s = ia % p.SA;
+                mbar_wait(fullA + 8 * s, (ia / p.SA) & 1);
+                float4* p0 = reinterpret_cast<float4*>(smem + s * a_stage_bytes);
+                float4* p1 = reinterpret_cast<float4*>(smem + s * a_stage_bytes + p.a_plane_bytes);
+#pragma unroll 2
+                for (int i = threadIdx.x; i < chunks; i += 128) {
+                    const float4 v = p0[i];
+                    float4 h, l;
+                    h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
+                    l.x = __fsub_rn(v.x, h.x); l.y = __fsub_rn(v.y, h.y); l.z = __fsub_rn(v.z, h.z); l.w = __fsub_rn(v.w, h.w);
+                    p0[i] = h;
+                    p1[i] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(convA + 8 * s);
+            }
+        }
+    } else if (warp == 6) {
+        // ===== activation (A) producer =====
         if (lane == 0) {
-            int ia = 0, ib = 0;
-            for (int kb = 0; kb < p.KBn; ++kb) {
-                for (int tap = 0; tap < 9; ++tap) {
-                    if (p.a_mode == 2 || tap == 0) {
-                        const int s = ia % p.SA;
-                        mbar_wait(emptyA + 8 * s, ((ia / p.SA) & 1) ^ 1);
-                        mbar_expect_tx(fullA + 8 * s, 2 * p.a_box_bytes);
-                        const int sx = p.a_mode == 2 ? tap % 3 : 0, sy = p.a_mode == 2 ? tap / 3 : 0;
-                        const uint32_t dst = sA + s * a_stage_bytes;
-                        tma_load_4d(dst, &mA_hi, fullA + 8 * s, kb * TC_KB, x0 - 1 + sx, y0 - 1 + sy, b);
-                        tma_load_4d(dst + p.a_plane_bytes, &mA_lo, fullA + 8 * s, kb * TC_KB, x0 - 1 + sx, y0 - 1 + sy, b);
-                        ++ia;
+            int ia = 0;
+            for (int reg = blockIdx.x; reg < p.regions; reg += gridDim.x) {
+                const TcRegion r = tc_region(p, reg);
+                for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
+                    const int s = ia % p.SA;
+                    mbar_wait(emptyA + 8 * s, ((ia / p.SA) & 1) ^ 1);
+                    mbar_expect_tx(fullA + 8 * s, p.a_box_bytes);
+                    tma_load_4d(sA + s * a_stage_bytes, &mA, fullA + 8 * s, kb * KBT, r.x0 - 1, r.y0 - 1, r.b);
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ===== weight (B) producer =====
+        if (lane == 0) {
+            int ib = 0;
+            for (int reg = blockIdx.x; reg < p.regions; reg += gridDim.x) {
+                const TcRegion r = tc_region(p, reg);
+                for (int kb = 0; kb < p.KBn; ++kb) {
+                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                        const int s = ib % p.SB;
+                        mbar_wait(emptyB + 8 * s, ((ib / p.SB) & 1) ^ 1);
+                        mbar_expect_tx(fullB + 8 * s, 2 * p.b_plane_bytes);
+                        const uint32_t dst = sB + s * b_stage_bytes;
+                        tma_load_2d(dst, &mB, fullB + 8 * s, 0, (tap * p.KBn + kb) * p.N + r.n0);
+                        tma_load_2d(dst + p.b_plane_bytes, &mB, fullB + 8 * s, 0, ((9 + tap) * p.KBn + kb) * p.N + r.n0);
                     }
-                    const int s = ib % p.SB;
-                    mbar_wait(emptyB + 8 * s, ((ib / p.SB) & 1) ^ 1);
-                    mbar_expect_tx(fullB + 8 * s, 2 * p.b_plane_bytes);
-                    const uint32_t dst = sB + s * b_stage_bytes;
-                    const int row_hi = (tap * p.KBn + kb) * p.N + n0;
-                    const int row_lo = ((9 + tap) * p.KBn + kb) * p.N + n0;
-                    tma_load_2d(dst, &mB, fullB + 8 * s, 0, row_hi);
-                    tma_load_2d(dst + p.b_plane_bytes, &mB, fullB + 8 * s, 0, row_lo);
-                    ++ib;
                 }
             }
         }
@@ -225,135 +284,180 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_consta
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Ncta >> 3) << 17) | ((128u >> 4) << 24);
-            int ia = 0, ib = 0, cur_sa = 0;
-            for (int kb = 0; kb < p.KBn; ++kb) {
-                for (int tap = 0; tap < 9; ++tap) {
-                    if (p.a_mode == 2 || tap == 0) {
-                        cur_sa = ia % p.SA;
-                        mbar_wait(fullA + 8 * cur_sa, (ia / p.SA) & 1);
-                        ++ia;
-                    }
-                    const int sb = ib % p.SB;
-                    mbar_wait(fullB + 8 * sb, (ib / p.SB) & 1);
-                    tc_fence_after();
-                    const int tap_rows = p.a_mode == 2 ? 0 : (tap / 3) * p.P + (tap % 3);
-                    const uint32_t b_hi = sB + sb * b_stage_bytes, b_lo = b_hi + p.b_plane_bytes;
-                    for (int t = 0; t < p.NT; ++t) {
-                        const uint32_t a_hi = sA + cur_sa * a_stage_bytes + (uint32_t)(t * p.TH * p.P + tap_rows) * 128u;
-                        const uint32_t a_lo = a_hi + p.a_plane_bytes;
-                        const uint32_t boff = p.a_mode == 0 ? ((a_hi >> 7) & 7u) : 0u;
-                        const uint32_t d = tmem_base + (uint32_t)(t * p.Ncta);
+            // descriptor = {hi word: constant, lo word: (address >> 4) | LBO}; offsets are plain adds on the lo word
+            const uint64_t desc_hi = tc_smem_desc<KBT>(0) & 0xffffffff00000000ull;
+            const uint32_t lo_flag = 1u << 16;
+            const uint32_t plane_a16 = (uint32_t)p.a_plane_bytes >> 4, plane_b16 = (uint32_t)p.b_plane_bytes >> 4;
+            int ia = 0, ib = 0, it = 0;
+            for (int reg = blockIdx.x; reg < p.regions; reg += gridDim.x, ++it) {
+                const int set = it & 1;
+                mbar_wait(accEmpty + 8 * set, ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)(set * acc_stride);
+                for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
+                    const int sa = ia % p.SA;
+                    mbar_wait(convA + 8 * sa, (ia / p.SA) & 1);
+                    const uint32_t a16 = (((sA + sa * a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
+                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                        const int sb = ib % p.SB;
+                        mbar_wait(fullB + 8 * sb, (ib / p.SB) & 1);
+                        tc_fence_after();
+                        const uint32_t tap16 = (uint32_t)(((tap / 3) * p.P + (tap % 3)) * RB) >> 4;
+                        const uint32_t b16 = (((sB + sb * b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
+                        const uint32_t acc0 = (kb | tap) ? 1u : 0u;
+                        for (int t = 0; t < p.NT; ++t) {
+                            const uint32_t at16 = a16 + tap16 + ((uint32_t)(t * p.TH * p.P * RB) >> 4);
+                            const uint32_t d = d0 + (uint32_t)(t * p.Ncta);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t dah = tc_smem_desc(a_hi + ks * 32, boff), dal = tc_smem_desc(a_lo + ks * 32, boff);
-                            const uint64_t dbh = tc_smem_desc(b_hi + ks * 32, 0), dbl = tc_smem_desc(b_lo + ks * 32, 0);
-                            const uint32_t first = (kb == 0 && tap == 0 && ks == 0) ? 0u : 1u;
-                            tc_mma_tf32(d, dal, dbh, idesc, first);
-                            tc_mma_tf32(d, dah, dbl, idesc, 1u);
-                            tc_mma_tf32(d, dah, dbh, idesc, 1u);
-                        }
-                    }
-                    tc_commit(emptyB + 8 * sb);
-                    ++ib;
-                    if (p.a_mode == 2 || tap == 8) tc_commit(emptyA + 8 * cur_sa);
-                }
-            }
-            tc_commit(accFull);
-        }
-    } else {
-        // ===== epilogue warps 0..3: TMEM lane quarter = warp =====
-        mbar_wait(accFull, 0);
-        tc_fence_after();
-        const ConvArgs& a = p.ca;
-        const int m = warp * 32 + lane;
-        const int hh = m / p.P, ww = m - hh * p.P;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        float* stage = reinterpret_cast<float*>(smem);
-        for (int t = 0; t < p.NT; ++t) {
-            const int y = y0 + t * p.TH + hh, x = x0 + ww;
-            const bool valid = hh < p.TH && ww < p.TW && y < p.H && x < p.W;
-            const long long pix = ((long long)b * p.H + y) * p.W + x;
-            const uint32_t tcol = lane_addr + (uint32_t)(t * p.Ncta);
-            if (a.epi == EPI_LSTM) {
-                const int R = a.N >> 2;
-                const long long ppix = (long long)y * p.W + x;
-                for (int c0 = 0; c0 < p.Ncta; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(tcol + c0, v);
-                    if (!valid) continue;
-                    const int r0 = (n0 + c0) >> 2;
-                    const float4 cold = *reinterpret_cast<const float4*>(a.cstate + pix * R + r0);
-                    const float co[4] = {cold.x, cold.y, cold.z, cold.w};
-                    float cn[4], hn[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 bq = *reinterpret_cast<const float4*>(a.bias + n0 + c0 + q * 4);
-                        const float4 pq = *reinterpret_cast<const float4*>(a.peep + (ppix * R + r0 + q) * 4);
-                        hn[q] = lstm_cell_v(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3], bq, pq, co[q], &cn[q]);
-                    }
-                    *reinterpret_cast<float4*>(a.cstate + pix * R + r0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                    view_store4(a.dstH, pix, r0, hn);
-                    if (a.dstUp.hi) {
-                        const int W2 = p.W * 2;
-                        const long long ub = ((long long)b * p.H * 2 + y * 2) * W2 + x * 2;
-                        view_store4(a.dstUp, ub, r0, hn);
-                        view_store4(a.dstUp, ub + 1, r0, hn);
-                        view_store4(a.dstUp, ub + W2, r0, hn);
-                        view_store4(a.dstUp, ub + W2 + 1, r0, hn);
-                    }
-                }
-            } else if (a.epi == EPI_CONVP || a.epi == EPI_RAW) {
-                for (int c0 = 0; c0 < p.Ncta; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(tcol + c0, v);
-                    if (!valid) continue;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 bq = *reinterpret_cast<const float4*>(a.bias + n0 + c0 + q * 4);
-                        float o[4] = {__fadd_rn(v[q * 4], bq.x), __fadd_rn(v[q * 4 + 1], bq.y), __fadd_rn(v[q * 4 + 2], bq.z),
-                                      __fadd_rn(v[q * 4 + 3], bq.w)};
-                        if (a.epi == EPI_CONVP) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                o[i] = o[i] > 0.f ? o[i] : 0.f;
-                                if (a.clip && o[i] > 1.f) o[i] = 1.f;
+                            for (int ks = 0; ks < KSTEPS; ++ks) {
+                                const uint64_t dah = desc_hi | (at16 + 2 * ks), dal = desc_hi | (at16 + plane_a16 + 2 * ks);
+                                const uint64_t dbh = desc_hi | (b16 + 2 * ks), dbl = desc_hi | (b16 + plane_b16 + 2 * ks);
+                                tc_mma_tf32(d, dal, dbh, idesc, ks ? 1u : acc0);
+                                tc_mma_tf32(d, dah, dbl, idesc, 1u);
+                                tc_mma_tf32(d, dah, dbh, idesc, 1u);
                             }
                         }
-                        *reinterpret_cast<float4*>(a.outP + pix * a.N + n0 + c0 + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                        tc_commit(emptyB + 8 * sb);
                     }
+                    tc_commit(emptyA + 8 * sa);
                 }
-            } else {  // EPI_CONVA: relu -> staging tile -> 2x2 max-pool -> error units at half resolution
-                for (int c0 = 0; c0 < p.Ncta; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(tcol + c0, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float o = __fadd_rn(v[i], a.bias[n0 + c0 + i]);
-                        stage[m * p.stage_ld + c0 + i] = o > 0.f ? o : 0.f;
-                    }
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int Hp = p.H >> 1, Wp = p.W >> 1, tw2 = p.TW >> 1, th2 = p.TH >> 1;
-                const int items = th2 * tw2 * p.Ncta;
-                for (int idx = m; idx < items; idx += 128) {
-                    const int n = idx % p.Ncta, pp = idx / p.Ncta;
-                    const int ph = pp / tw2, pw = pp - ph * tw2;
-                    const int py = ((y0 + t * p.TH) >> 1) + ph, px = (x0 >> 1) + pw;
-                    if (py >= Hp || px >= Wp) continue;
-                    const int m00 = (2 * ph) * p.P + 2 * pw;
-                    const float* s0 = stage + m00 * p.stage_ld + n;
-                    const float mx = fmaxf(fmaxf(s0[0], s0[p.stage_ld]), fmaxf(s0[p.P * p.stage_ld], s0[(p.P + 1) * p.stage_ld]));
-                    const long long ppos = ((long long)b * Hp + py) * Wp + px;
-                    const float pv = a.P[ppos * a.N + n0 + n];
-                    const float ep = __fsub_rn(mx, pv), en = __fsub_rn(pv, mx);
-                    view_store(a.dstE, ppos, n0 + n, ep > 0.f ? ep : 0.f);
-                    view_store(a.dstE, ppos, a.N + n0 + n, en > 0.f ? en : 0.f);
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                tc_commit(accFull + 8 * set);
             }
         }
-        tc_fence_before();
+    } else if (warp >= 8) {
+        // ===== epilogue warps 8..15 =====
+        const ConvArgs& a = p.ca;
+        const int q4 = warp & 3, half = (warp - 8) >> 2;
+        const int m = q4 * 32 + lane;
+        const int etid = (warp - 8) * 32 + lane;
+        const int hh = m / p.P, ww = m - hh * p.P;
+        int it = 0;
+        for (int reg = blockIdx.x; reg < p.regions; reg += gridDim.x, ++it) {
+            const TcRegion r = tc_region(p, reg);
+            const int set = it & 1, b = r.b, n0 = r.n0;
+            mbar_wait(accFull + 8 * set, (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(set * acc_stride);
+            for (int t = 0; t < p.NT; ++t) {
+                const int y = r.y0 + t * p.TH + hh, x = r.x0 + ww;
+                const bool valid = hh < p.TH && ww < p.TW && y < p.H && x < p.W;
+                const long long pix = valid ? ((long long)b * p.H + y) * p.W + x : 0;
+                const uint32_t tcol = lane_addr + (uint32_t)(t * p.Ncta);
+                if (a.epi == EPI_LSTM) {
+                    const int R = a.N >> 2;
+                    const long long ppix = valid ? (long long)y * p.W + x : 0;
+                    // software pipeline: the state / peephole loads of chunk c+32 are in flight while chunk c is computed
+                    float4 cold, pq[4];
+                    int c0 = half * 16;
+                    if (c0 < p.Ncta) {
+                        const int r0 = (n0 + c0) >> 2;
+                        cold = *reinterpret_cast<const float4*>(a.cstate + pix * R + r0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) pq[q] = *reinterpret_cast<const float4*>(a.peep + (ppix * R + r0 + q) * 4);
+                    }
+                    for (; c0 < p.Ncta; c0 += 32) {
+                        float v[16];
+                        tmem_ld16(tcol + c0, v);
+                        const int r0 = (n0 + c0) >> 2;
+                        const float4 ccur = cold;
+                        float4 pcur[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) pcur[q] = pq[q];
+                        if (c0 + 32 < p.Ncta) {
+                            const int r1 = (n0 + c0 + 32) >> 2;
+                            cold = *reinterpret_cast<const float4*>(a.cstate + pix * R + r1);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) pq[q] = *reinterpret_cast<const float4*>(a.peep + (ppix * R + r1 + q) * 4);
+                        }
+                        if (!valid) continue;
+                        const float co[4] = {ccur.x, ccur.y, ccur.z, ccur.w};
+                        float cn[4], hn[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 bq = *reinterpret_cast<const float4*>(a.bias + n0 + c0 + q * 4);
+                            hn[q] = lstm_cell_v(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3], bq, pcur[q], co[q], &cn[q]);
+                        }
+                        *reinterpret_cast<float4*>(a.cstate + pix * R + r0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                        view_store4(a.dstH, pix, r0, hn);
+                        if (a.dstUp.hi) {
+                            const int W2 = p.W * 2;
+                            const long long ub = ((long long)b * p.H * 2 + y * 2) * W2 + x * 2;
+                            view_store4(a.dstUp, ub, r0, hn);
+                            view_store4(a.dstUp, ub + 1, r0, hn);
+                            view_store4(a.dstUp, ub + W2, r0, hn);
+                            view_store4(a.dstUp, ub + W2 + 1, r0, hn);
+                        }
+                    }
+                } else if (a.epi == EPI_CONVP || a.epi == EPI_RAW) {
+                    for (int c0 = half * 16; c0 < p.Ncta; c0 += 32) {
+                        float v[16];
+                        tmem_ld16(tcol + c0, v);
+                        if (!valid) continue;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 bq = *reinterpret_cast<const float4*>(a.bias + n0 + c0 + q * 4);
+                            float o[4] = {__fadd_rn(v[q * 4], bq.x), __fadd_rn(v[q * 4 + 1], bq.y), __fadd_rn(v[q * 4 + 2], bq.z),
+                                          __fadd_rn(v[q * 4 + 3], bq.w)};
+                            if (a.epi == EPI_CONVP) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    o[i] = o[i] > 0.f ? o[i] : 0.f;
+                                    if (a.clip && o[i] > 1.f) o[i] = 1.f;
+                                }
+                            }
+                            *reinterpret_cast<float4*>(a.outP + pix * a.N + n0 + c0 + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                } else {  // EPI_CONVA: relu -> staging tile -> 2x2 max-pool -> error units at half resolution
+                    for (int c0 = half * 16; c0 < p.Ncta; c0 += 32) {
+                        float v[16];
+                        tmem_ld16(tcol + c0, v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float o = __fadd_rn(v[i], a.bias[n0 + c0 + i]);
+                            stage[m * p.stage_ld + c0 + i] = o > 0.f ? o : 0.f;
+                        }
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    const int Hp = p.H >> 1, Wp = p.W >> 1, tw2 = p.TW >> 1, th2 = p.TH >> 1;
+                    const int items = th2 * tw2 * p.Ncta;
+                    for (int base = 0; base < items; base += 4 * 256) {
+                        float mx[4], pv[4];
+                        long long ppos[4];
+                        int nn[4];
+                        bool okk[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {   // loads first: four independent global reads in flight
+                            const int idx = base + u * 256 + etid;
+                            okk[u] = idx < items;
+                            const int n = idx % p.Ncta, pp = idx / p.Ncta;
+                            const int ph = pp / tw2, pw = pp - ph * tw2;
+                            const int py = ((r.y0 + t * p.TH) >> 1) + ph, px = (r.x0 >> 1) + pw;
+                            okk[u] = okk[u] && py < Hp && px < Wp;
+                            nn[u] = n0 + n;
+                            ppos[u] = okk[u] ? ((long long)b * Hp + py) * Wp + px : 0;
+                            pv[u] = okk[u] ? a.P[ppos[u] * a.N + nn[u]] : 0.f;
+                            const int m00 = okk[u] ? (2 * ph) * p.P + 2 * pw : 0;
+                            const float* s0 = stage + m00 * p.stage_ld + n;
+                            mx[u] = fmaxf(fmaxf(s0[0], s0[p.stage_ld]), fmaxf(s0[p.P * p.stage_ld], s0[(p.P + 1) * p.stage_ld]));
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (!okk[u]) continue;
+                            const float ep = __fsub_rn(mx[u], pv[u]), en = __fsub_rn(pv[u], mx[u]);
+                            view_store(a.dstE, ppos[u], nn[u], ep > 0.f ? ep : 0.f);
+                            view_store(a.dstE, ppos[u], a.N + nn[u], en > 0.f ? en : 0.f);
+                        }
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accEmpty + 8 * set);
+        }
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
@@ -370,9 +474,10 @@ struct TcState {
     EigEncodeTiledFn encode = nullptr;
     bool probed = false, available = false;
     std::string reason, last_error;
-    int a_mode = 1;  // measured on B200: the 128B swizzle is a function of the absolute smem address, base offset stays 0
-    int force_nt = 0;
-    std::map<std::tuple<const void*, const void*, int, int, int, int, int, int, int>, std::pair<CUtensorMap, CUtensorMap>> amaps;
+    int kbt = 16;      // channels per K block (EIG_TC_KB = 16 | 32)
+    int force_nt = 0;  // EIG_TC_NT: cap on MMA tiles per CTA region
+    int n_sm = 148;
+    std::map<std::tuple<const void*, int, int, int, int, int, int, int, int>, CUtensorMap> amaps;
 };
 inline TcState& tc_state() { static TcState s; return s; }
 
@@ -384,6 +489,7 @@ inline bool tc_available() {
     cudaDeviceProp prop;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { s.reason = "no CUDA device"; return false; }
     if (prop.major != 10) { s.reason = "tcgen05 needs an sm_100-class GPU (found sm_" + std::to_string(prop.major * 10 + prop.minor) + ")"; return false; }
+    s.n_sm = prop.multiProcessorCount;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
@@ -391,19 +497,21 @@ inline bool tc_available() {
         return false;
     }
     s.encode = (EigEncodeTiledFn)fn;
-    if (cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv3x3_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess ||
+        cudaFuncSetAttribute(conv3x3_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
         s.reason = "cannot raise the dynamic shared memory limit";
         cudaGetLastError();
         return false;
     }
-    if (const char* e = getenv("EIG_TC_AMODE")) s.a_mode = atoi(e);
+    if (const char* e = getenv("EIG_TC_KB")) s.kbt = atoi(e) == 32 ? 32 : 16;
     if (const char* e = getenv("EIG_TC_NT")) s.force_nt = atoi(e);
     s.available = true;
     return true;
 }
 inline std::string tc_unavailable_reason() { return tc_state().reason; }
 inline std::string tc_last_error() { return tc_state().last_error; }
-inline void tc_set_a_mode(int m) { tc_state().a_mode = m; }
+inline void tc_set_kb(int kbt) { tc_state().kbt = kbt == 32 ? 32 : 16; }
+inline void tc_set_max_nt(int nt) { tc_state().force_nt = nt; }
 
 inline float tc_host_tf32(float v) {
     uint32_t u;
@@ -421,46 +529,49 @@ inline void tc_free(TcWeights& w) {
     w.ok = false;
 }
 
-// wv: [9][cin][npad] fp32 (the SIMT layout), N valid columns
-inline int tc_pack(TcWeights& w, const float* wv, int cin, int N, int npad) {
+// wv: [9][cin][npad] fp32 (the SIMT layout), N valid columns; max_ncta caps the output channels of one CTA
+inline int tc_pack(TcWeights& w, const float* wv, int cin, int N, int npad, int max_ncta = 256) {
     if (!tc_available()) return 0;  // no tensor-core path on this device: nothing to pack
     TcState& s = tc_state();
     tc_free(w);
     if (N % 16 || cin % 4) return 0;  // not a tensor-core shape: w.ok stays false, the caller keeps the SIMT kernel
-    w.cin = cin; w.N = N; w.KBn = (cin + TC_KB - 1) / TC_KB;
-    w.gz = (N + 255) / 256;
+    const int KBT = s.kbt;
+    w.cin = cin; w.N = N; w.KBT = KBT; w.KBn = (cin + KBT - 1) / KBT;
+    w.gz = (N + max_ncta - 1) / max_ncta;
     while (N % w.gz || (N / w.gz) % 16) ++w.gz;
     w.Ncta = N / w.gz;
-    const size_t plane = (size_t)9 * w.KBn * N * TC_KB;
+    const size_t plane = (size_t)9 * w.KBn * N * KBT;
     std::vector<float> pk(2 * plane, 0.f);
     for (int tap = 0; tap < 9; ++tap)
         for (int c = 0; c < cin; ++c)
             for (int n = 0; n < N; ++n) {
                 const float v = wv[((size_t)tap * cin + c) * npad + n];
                 const float hi = tc_host_tf32(v);
-                const size_t o = (((size_t)tap * w.KBn + c / TC_KB) * N + n) * TC_KB + c % TC_KB;
+                const size_t o = (((size_t)tap * w.KBn + c / KBT) * N + n) * KBT + c % KBT;
                 pk[o] = hi;
                 pk[plane + o] = v - hi;
             }
     if (cudaMalloc((void**)&w.d, pk.size() * sizeof(float)) != cudaSuccess) { s.last_error = "tc_pack: cudaMalloc failed"; return -1; }
     if (cudaMemcpy(w.d, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { s.last_error = "tc_pack: upload failed"; return -1; }
-    const cuuint64_t gdim[2] = {TC_KB, (cuuint64_t)2 * 9 * w.KBn * N};
-    const cuuint64_t gstr[1] = {TC_KB * sizeof(float)};
-    const cuuint32_t box[2] = {TC_KB, (cuuint32_t)w.Ncta};
+    const cuuint64_t gdim[2] = {(cuuint64_t)KBT, (cuuint64_t)2 * 9 * w.KBn * N};
+    const cuuint64_t gstr[1] = {(cuuint64_t)KBT * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)KBT, (cuuint32_t)w.Ncta};
     const cuuint32_t est[2] = {1, 1};
     const CUresult r = s.encode(&w.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w.d, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                KBT == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { s.last_error = "tc_pack: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return -1; }
     w.ok = true;
     return 0;
 }
 
-struct TcGeom { int TW, TH, P, NT, SA, SB, a_plane, b_plane, tmem_cols, tiles_x, tiles_y; size_t smem; };
+struct TcGeom { int TW, TH, P, NT, SA, SB, a_plane, b_plane, tmem_cols, tiles_x, tiles_y, regions, staging, stage_ld; size_t smem; };
 
 inline int tc_round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-// picks the flat-padded tile (TW x TH, P = TW + 2, (TH-1)*P + TW <= 128) with the best MMA-row efficiency
-inline bool tc_geometry(int B, int H, int W, int Ncta, int gz, bool pooled, int force_nt, TcGeom& g) {
+// Picks the flat-padded tile (TW x TH, P = TW + 2, (TH-1)*P + TW <= 128) with the best MMA-row efficiency, then the
+// number of stacked tiles per CTA region (weight-tile reuse) that still load-balances over the SMs and fits shared memory.
+inline bool tc_geometry(int B, int H, int W, int KBT, int Ncta, int gz, bool pooled, int force_nt, int n_sm, TcGeom& g) {
     double best = -1.0;
     int bTW = 0, bTH = 0;
     const int step = pooled ? 2 : 1;
@@ -478,81 +589,89 @@ inline bool tc_geometry(int B, int H, int W, int Ncta, int gz, bool pooled, int 
     g.TW = bTW; g.TH = bTH; g.P = bTW + 2;
     g.tiles_x = (W + g.TW - 1) / g.TW;
     const int row_tiles = (H + g.TH - 1) / g.TH;
-    g.b_plane = Ncta * 128;
-    int nt_max = 512 / Ncta;
-    if (nt_max > row_tiles) nt_max = row_tiles;
-    for (int NT = nt_max; NT >= 1; --NT) {
+    const int RB = KBT * 4;
+    g.b_plane = Ncta * RB;
+    g.stage_ld = Ncta + 1;
+    g.staging = pooled ? tc_round_up(128 * g.stage_ld * 4, 1024) : 0;
+    int nt_cap = 256 / Ncta;  // two accumulator sets of NT * Ncta columns in the 512 TMEM columns
+    if (nt_cap > row_tiles) nt_cap = row_tiles;
+    if (nt_cap < 1) nt_cap = 1;
+    if (force_nt > 0 && nt_cap > force_nt) nt_cap = force_nt;
+    int pick = 0;
+    double pick_eff = -1.0;
+    TcGeom cand[9];
+    for (int NT = nt_cap; NT >= 1; --NT) {
         const int rows = std::max((NT * g.TH + 2) * g.P, (NT - 1) * g.TH * g.P + 2 * g.P + 2 + 128);
-        const int a_plane = tc_round_up(rows * 128, 1024);
-        const int SA = 2;
-        const long long left = (long long)TC_SMEM_LIMIT - 2048 - (long long)SA * 2 * a_plane;
-        int SB = (int)(left / (2 * g.b_plane));
-        if (SB > 8) SB = 8;
-        const long long ctas = (long long)g.tiles_x * ((row_tiles + NT - 1) / NT) * B * gz;
-        const bool fits = SB >= 2;
-        const bool enough = ctas >= 2 * 148 || NT == 1;
-        if (force_nt > 0 ? (NT <= force_nt && fits) : (fits && enough)) {
-            g.NT = NT; g.SA = SA; g.SB = SB; g.a_plane = a_plane;
-            g.tiles_y = (row_tiles + NT - 1) / NT;
-            int cols = 32;
-            while (cols < NT * Ncta) cols <<= 1;
-            g.tmem_cols = cols;
-            g.smem = (size_t)SA * 2 * a_plane + (size_t)SB * 2 * g.b_plane + 8 * (2 * SA + 2 * SB + 1) + 16 + 1024;
-            return true;
+        const int a_plane = tc_round_up(rows * RB, 1024);
+        int SA = 3, SB = 0;
+        for (; SA >= 2; --SA) {   // three activation stages when the weight ring still gets >= 4
+            const long long left = (long long)TC_SMEM_LIMIT - 4096 - g.staging - (long long)SA * 2 * a_plane;
+            SB = left > 0 ? (int)(left / (2 * g.b_plane)) : 0;
+            if (SB > 8) SB = 8;
+            if (SB >= (SA == 3 ? 4 : 2)) break;
         }
+        if (SA < 2) continue;
+        TcGeom c = g;
+        c.NT = NT; c.SA = SA; c.SB = SB; c.a_plane = a_plane;
+        c.tiles_y = (row_tiles + NT - 1) / NT;
+        c.regions = c.tiles_x * c.tiles_y * B * gz;
+        int cols = 32;
+        while (cols < 2 * NT * Ncta) cols <<= 1;
+        c.tmem_cols = cols;
+        c.smem = (size_t)SA * 2 * a_plane + (size_t)SB * 2 * g.b_plane + g.staging + 8 * (3 * SA + 2 * SB + 4) + 16 + 1024;
+        const int rounds = (c.regions + n_sm - 1) / n_sm;
+        const double eff = (double)c.regions / ((double)rounds * n_sm);
+        cand[NT] = c;
+        if (eff >= 0.85) { pick = NT; break; }       // largest NT that still fills the machine evenly
+        if (eff > pick_eff) { pick_eff = eff; pick = NT; }
     }
-    return false;
+    if (!pick) return false;
+    g = cand[pick];
+    return true;
 }
 
 inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     TcState& s = tc_state();
     if (!tc_available()) { s.last_error = s.reason; return -1; }
     if (!w.ok) { s.last_error = "tc_conv: weights not packed"; return -1; }
-    if (!a.in_lo) { s.last_error = "tc_conv: input view has no lo plane"; return -1; }
+    if (a.in_lo) { s.last_error = "tc_conv: split activation planes are not used any more (pass in_lo = nullptr)"; return -1; }
     if (a.Cin != w.cin || a.N != w.N) { s.last_error = "tc_conv: shape mismatch with packed weights"; return -1; }
     if ((a.in_coff & 3) || (a.in_pitch & 3)) { s.last_error = "tc_conv: view not 16-byte aligned"; return -1; }
     const bool pooled = a.epi == EPI_CONVA;
     if (pooled && ((a.H | a.W) & 1)) { s.last_error = "tc_conv: pooled conv needs even H, W"; return -1; }
+    if (pooled && w.Ncta > 128) { s.last_error = "tc_conv: pooled conv needs <= 128 channels per CTA"; return -1; }
     TcGeom g;
-    if (!tc_geometry(a.B, a.H, a.W, w.Ncta, w.gz, pooled, s.force_nt, g)) { s.last_error = "tc_conv: no tile geometry fits"; return -1; }
+    if (!tc_geometry(a.B, a.H, a.W, w.KBT, w.Ncta, w.gz, pooled, s.force_nt, s.n_sm, g)) { s.last_error = "tc_conv: no tile geometry fits"; return -1; }
     const int box_rows = g.NT * g.TH + 2;
-    auto key = std::make_tuple((const void*)(a.in_hi + a.in_coff), (const void*)(a.in_lo + a.in_coff), a.Cin, a.W, a.H, a.B, a.in_pitch, g.P, box_rows);
+    auto key = std::make_tuple((const void*)(a.in_hi + a.in_coff), a.Cin, a.W, a.H, a.B, a.in_pitch, g.P, box_rows, w.KBT);
     auto it = s.amaps.find(key);
     if (it == s.amaps.end()) {
-        std::pair<CUtensorMap, CUtensorMap> maps;
+        CUtensorMap map;
         const cuuint64_t gdim[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
         const cuuint64_t gstr[3] = {(cuuint64_t)a.in_pitch * 4, (cuuint64_t)a.W * a.in_pitch * 4, (cuuint64_t)a.H * a.W * a.in_pitch * 4};
-        const cuuint32_t box[4] = {TC_KB, (cuuint32_t)g.P, (cuuint32_t)box_rows, 1};
+        const cuuint32_t box[4] = {(cuuint32_t)w.KBT, (cuuint32_t)g.P, (cuuint32_t)box_rows, 1};
         const cuuint32_t est[4] = {1, 1, 1, 1};
-        for (int k = 0; k < 2; ++k) {
-            const float* base = (k == 0 ? a.in_hi : a.in_lo) + a.in_coff;
-            const CUresult r = s.encode(k == 0 ? &maps.first : &maps.second, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, gdim, gstr, box,
-                                        est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) { s.last_error = "tc_conv: cuTensorMapEncodeTiled(A) failed (" + std::to_string((int)r) + ")"; return -1; }
-        }
-        it = s.amaps.emplace(key, maps).first;
+        const CUresult r = s.encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(a.in_hi + a.in_coff), gdim, gstr, box, est,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, w.KBT == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { s.last_error = "tc_conv: cuTensorMapEncodeTiled(A) failed (" + std::to_string((int)r) + ")"; return -1; }
+        it = s.amaps.emplace(key, map).first;
     }
     TcParams p;
     memset(&p, 0, sizeof p);
     p.B = a.B; p.H = a.H; p.W = a.W;
-    p.TW = g.TW; p.TH = g.TH; p.P = g.P; p.NT = g.NT; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y;
+    p.TW = g.TW; p.TH = g.TH; p.P = g.P; p.NT = g.NT; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y; p.regions = g.regions;
     p.KBn = w.KBn; p.Ncta = w.Ncta; p.N = w.N;
-    p.a_plane_bytes = g.a_plane; p.b_plane_bytes = g.b_plane; p.a_box_bytes = TC_KB * 4 * g.P * box_rows;
-    p.SA = g.SA; p.SB = g.SB; p.a_mode = s.a_mode; p.tmem_cols = g.tmem_cols;
-    p.stage_ld = w.Ncta + 1;
+    p.a_plane_bytes = g.a_plane; p.b_plane_bytes = g.b_plane; p.a_box_bytes = w.KBT * 4 * g.P * box_rows;
+    p.SA = g.SA; p.SB = g.SB; p.tmem_cols = g.tmem_cols;
+    p.staging_bytes = g.staging; p.stage_ld = g.stage_ld;
     p.ca = a;
-    size_t smem = g.smem;
-    if (pooled) {
-        const size_t need = (size_t)128 * p.stage_ld * 4 + 2048;
-        if (need > smem) smem = need;
-        if ((size_t)128 * p.stage_ld * 4 > (size_t)g.SA * 2 * g.a_plane + (size_t)g.SB * 2 * g.b_plane) {
-            s.last_error = "tc_conv: staging tile would overlap the barriers";
-            return -1;
-        }
-    }
-    if (smem > TC_SMEM_LIMIT) { s.last_error = "tc_conv: shared memory budget exceeded"; return -1; }
-    conv3x3_tc_kernel<<<dim3(g.tiles_x * g.tiles_y, a.B, w.gz), dim3(TC_THREADS), smem, stream>>>(it->second.first, it->second.second, w.map, p);
+    if (g.smem > TC_SMEM_LIMIT) { s.last_error = "tc_conv: shared memory budget exceeded"; return -1; }
+    const int grid = g.regions < s.n_sm ? g.regions : s.n_sm;
+    if (w.KBT == 32)
+        conv3x3_tc_kernel<32><<<dim3(grid), dim3(TC_THREADS), g.smem, stream>>>(it->second, w.map, p);
+    else
+        conv3x3_tc_kernel<16><<<dim3(grid), dim3(TC_THREADS), g.smem, stream>>>(it->second, w.map, p);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { s.last_error = std::string("tc_conv launch: ") + cudaGetErrorString(e); return -1; }
     return 0;

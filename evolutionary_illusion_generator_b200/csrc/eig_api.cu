@@ -84,8 +84,7 @@ struct eig_ctx {
     double *xmat = nullptr, *ymat = nullptr;
     LayerW lw[4];
     // activations
-    float* X[4][2] = {{nullptr}};    // concat buffers [B][H][W][ctot]  (hi plane)
-    float* Xlo[4][2] = {{nullptr}};  // lo planes (layers >= 1 only)
+    float* X[4][2] = {{nullptr}};    // concat buffers [B][H][W][ctot] = [E_n | up(R_{n+1}) | h_n], double-buffered over time steps
     float* cst[4] = {nullptr};       // cell state [B][H][W][R]
     float* P[4] = {nullptr};         // predictions [B][H][W][C]
     float* x_in = nullptr;           // [B][h][w][c]
@@ -137,7 +136,6 @@ extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, co
         const size_t px = B * c->H[n] * c->W[n];
         for (int k = 0; k < 2; ++k) {
             CK(dalloc(c, &c->X[n][k], px * c->ctot[n]));
-            if (n >= 1) CK(dalloc(c, &c->Xlo[n][k], px * c->ctot[n]));
         }
         CK(dalloc(c, &c->cst[n], px * c->ch[n]));
         CK(dalloc(c, &c->P[n], px * c->ch[n]));
@@ -267,7 +265,7 @@ extern "C" int eig_load_weights(eig_ctx* c, int nt, const char* const* names, co
             for (int i = 0; i < C; ++i) bv[i] = t->p[i];
             CK(upload(c, &L.convA, wv)); CK(upload(c, &L.convA_b, bv));
 #ifndef EIG_EMU
-            if (n >= 2 && (rc = tc_pack(L.tcA, wv.data(), cin, C, npad))) return fail(EIG_E_CUDA, "tc_pack ConvA: " + tc_last_error());
+            if (n >= 2 && (rc = tc_pack(L.tcA, wv.data(), cin, C, npad, 128))) return fail(EIG_E_CUDA, "tc_pack ConvA: " + tc_last_error());
 #endif
         }
         {
@@ -361,12 +359,12 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
     for (int n = 1; n < 4; ++n) {  // ConvA_n: E_{n-1} (res n-1) -> pool -> E_n
         ConvArgs a;
         memset(&a, 0, sizeof a);
-        a.in_hi = c->X[n - 1][cur]; a.in_lo = c->Xlo[n - 1][cur];
+        a.in_hi = c->X[n - 1][cur]; a.in_lo = nullptr;
         a.in_pitch = c->ctot[n - 1]; a.in_coff = 0; a.Cin = 2 * c->ch[n - 1];
         a.B = B; a.H = c->H[n - 1]; a.W = c->W[n - 1];
         a.wgt = c->lw[n].convA; a.bias = c->lw[n].convA_b; a.N = c->ch[n]; a.Npad = (c->ch[n] + 3) & ~3;
         a.epi = EPI_CONVA; a.P = c->P[n];
-        a.dstE = mkview(c->X[n][cur], c->Xlo[n][cur], c->ctot[n], 0, 2 * c->ch[n]);
+        a.dstE = mkview(c->X[n][cur], nullptr, c->ctot[n], 0, 2 * c->ch[n]);
 #ifndef EIG_EMU
         if (tc && n >= 2 && c->lw[n].tcA.ok) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcA, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvA: " + tc_last_error()); continue; }
 #endif
@@ -375,14 +373,14 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
     for (int n = 3; n >= 0; --n) {  // ConvLSTM_n
         ConvArgs a;
         memset(&a, 0, sizeof a);
-        a.in_hi = c->X[n][cur]; a.in_lo = c->Xlo[n][cur];
+        a.in_hi = c->X[n][cur]; a.in_lo = nullptr;
         a.in_pitch = c->ctot[n]; a.in_coff = 0; a.Cin = c->ctot[n];
         a.B = B; a.H = c->H[n]; a.W = c->W[n];
         a.wgt = c->lw[n].lstm; a.bias = c->lw[n].lstm_b; a.N = 4 * c->ch[n]; a.Npad = a.N;
         a.epi = EPI_LSTM; a.cstate = c->cst[n]; a.peep = c->lw[n].peep;
         const int hoff = 2 * c->ch[n] + (n < 3 ? c->ch[n + 1] : 0);
-        a.dstH = mkview(c->X[n][nxt], c->Xlo[n][nxt], c->ctot[n], hoff, c->ch[n]);
-        if (n >= 1) a.dstUp = mkview(c->X[n - 1][cur], c->Xlo[n - 1][cur], c->ctot[n - 1], 2 * c->ch[n - 1], c->ch[n]);
+        a.dstH = mkview(c->X[n][nxt], nullptr, c->ctot[n], hoff, c->ch[n]);
+        if (n >= 1) a.dstUp = mkview(c->X[n - 1][cur], nullptr, c->ctot[n - 1], 2 * c->ch[n - 1], c->ch[n]);
 #ifndef EIG_EMU
         if (tc && n >= 1 && c->lw[n].tcL.ok) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); continue; }
 #endif
@@ -392,7 +390,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         ConvArgs a;
         memset(&a, 0, sizeof a);
         const int hoff = 2 * c->ch[n] + (n < 3 ? c->ch[n + 1] : 0);
-        a.in_hi = c->X[n][nxt]; a.in_lo = c->Xlo[n][nxt];
+        a.in_hi = c->X[n][nxt]; a.in_lo = nullptr;
         a.in_pitch = c->ctot[n]; a.in_coff = hoff; a.Cin = c->ch[n];
         a.B = B; a.H = c->H[n]; a.W = c->W[n];
         a.wgt = c->lw[n].convP; a.bias = c->lw[n].convP_b; a.N = c->ch[n]; a.Npad = (c->ch[n] + 3) & ~3;
@@ -410,7 +408,6 @@ static int prednet_reset(eig_ctx* c, int B, cudaStream_t s) {
         const size_t px = (size_t)B * c->H[n] * c->W[n];
         for (int k = 0; k < 2; ++k) {
             CK(cudaMemsetAsync(c->X[n][k], 0, px * c->ctot[n] * sizeof(float), s));
-            if (c->Xlo[n][k]) CK(cudaMemsetAsync(c->Xlo[n][k], 0, px * c->ctot[n] * sizeof(float), s));
         }
         CK(cudaMemsetAsync(c->cst[n], 0, px * c->ch[n] * sizeof(float), s));
         CK(cudaMemsetAsync(c->P[n], 0, px * c->ch[n] * sizeof(float), s));

@@ -257,6 +257,6 @@ def test_tcgen05_conv_self_check():
     import subprocess
     exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpu", "tc_check")
     assert os.path.isfile(exe), "tests/gpu/tc_check missing: run __graft_entry__.build()"
-    r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe, "16"], capture_output=True, text=True, timeout=300)
     print(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-500:]
