@@ -34,19 +34,22 @@ enum { TC_THREADS = 512, TC_SMEM_LIMIT = 227 * 1024 };
 struct TcWeights {
     float* d = nullptr;  // [2 planes][9 taps][KBn][N][KBT] fp32 (hi plane, then lo plane)
     int cin = 0, N = 0, KBT = 16, KBn = 0, Ncta = 0, gz = 1;
-    CUtensorMap map;
+    CUtensorMap map[3];  // weight-tile boxes of Ncta, Ncta/2, Ncta/4 rows (cluster size 1, 2, 4)
+    int max_csize = 1;
     bool ok = false;
 };
 
 struct TcParams {
     int B, H, W;
     int TW, TH, P, NT;
-    int tiles_x, tiles_y, regions;
+    int tiles_x, tiles_y, regions;  // regions = spatial CTA regions (tiles_x * tiles_y * B)
+    int csize, groups_per_nz, groups;  // cluster size, groups (= csize regions sharing one weight slice) per N slice, total
     int KBn, Ncta, N;
     int a_plane_bytes, b_plane_bytes, a_box_bytes;
     int SA, SB;
     int tmem_cols;
     int staging_bytes, stage_ld;  // ConvA pooling tile: 128 rows x stage_ld floats
+    long long* dbg;               // optional [grid][16] cycle counters per role (tests/gpu/tc_check timing mode), else null
     ConvArgs ca;
 };
 
@@ -87,6 +90,31 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+// one elected lane of a converged warp; the surrounding code stays warp-uniform so that descriptors, barrier
+// addresses and loop counters live in uniform registers (an `if (lane == 0)` around the issue loop makes ptxas wrap
+// every tcgen05.mma in an R2UR "waterfall" of ~85 cycles - measured, see profiles/)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -163,14 +191,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-struct TcRegion { int x0, y0, b, n0; };
-__device__ __forceinline__ TcRegion tc_region(const TcParams& p, int reg) {
+// Work decomposition: a *group* is `csize` spatially consecutive CTA regions that use the same weight slice n0; the
+// CTAs of one cluster walk the groups in lockstep (cluster k takes groups k, k + #clusters, ...), CTA rank r of the
+// cluster computes region r of the group, and every weight tile is fetched once per cluster (each CTA loads 1/csize
+// of it and multicasts).  A rank without a region (tail group) still loads its slice and releases the stages.
+struct TcRegion { int x0, y0, b, n0; bool active; };
+__device__ __forceinline__ TcRegion tc_region(const TcParams& p, int group, int rank) {
     TcRegion r;
+    const int nz = group / p.groups_per_nz;
+    const int sp = (group - nz * p.groups_per_nz) * p.csize + rank;
+    r.active = sp < p.regions;
     const int tiles = p.tiles_x * p.tiles_y;
-    const int tile = reg % tiles;
-    const int rest = reg / tiles;
-    r.b = rest % p.B;
-    r.n0 = (rest / p.B) * p.Ncta;
+    const int tile = sp % tiles;
+    r.b = r.active ? sp / tiles : 0;
+    r.n0 = nz * p.Ncta;
     r.x0 = (tile % p.tiles_x) * p.TW;
     r.y0 = (tile / p.tiles_x) * (p.NT * p.TH);
     return r;
@@ -196,7 +230,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     unsigned char* smem = smem_raw + pad;
     const uint32_t sbase = raw_addr + pad;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int crank = p.csize > 1 ? (int)cluster_rank() : 0;
+    const int cluster_id = blockIdx.x / p.csize, n_clusters = gridDim.x / p.csize;
+    const uint16_t cmask = (uint16_t)((1u << p.csize) - 1u);
     const int a_stage_bytes = 2 * p.a_plane_bytes, b_stage_bytes = 2 * p.b_plane_bytes;
     const uint32_t sA = sbase, sB = sbase + p.SA * a_stage_bytes;
     const uint32_t pipe_bytes = p.SA * a_stage_bytes + p.SB * b_stage_bytes;
@@ -210,7 +247,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
 
     if (warp == 4 && lane == 0) {
         for (int i = 0; i < p.SA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(convA + 8 * i, 4); mbar_init(emptyA + 8 * i, 1); }
-        for (int i = 0; i < p.SB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
+        for (int i = 0; i < p.SB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, p.csize); }
         for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, 1); mbar_init(accEmpty + 8 * i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -220,18 +257,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (p.csize > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int acc_stride = p.NT * p.Ncta;
 
     if (warp < 4) {
         // ===== converter =====
         const int chunks = p.a_box_bytes >> 4;
         int ia = 0;
-        for (int reg = blockIdx.x; reg < p.regions; reg += gridDim.x) {
+        long long c_wait = 0, c0 = clock64(), cq;
+        for (int grp = cluster_id; grp < p.groups; grp += n_clusters) {
+            if (!tc_region(p, grp, crank).active) continue;
             for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
                 const int s = ia % p.SA;
+                cq = clock64();
                 mbar_wait(fullA + 8 * s, (ia / p.SA) & 1);
+                c_wait += clock64() - cq;
                 float4* p0 = reinterpret_cast<float4*>(smem + s * a_stage_bytes);
                 float4* p1 = reinterpret_cast<float4*>(smem + s * a_stage_bytes + p.a_plane_bytes);
 #pragma unroll 2
@@ -248,12 +290,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                 if (lane == 0) mbar_arrive(convA + 8 * s);
             }
         }
+        if (p.dbg && threadIdx.x == 0) {
+            long long* d = p.dbg + (long long)blockIdx.x * 16;
+            d[7] = clock64() - c0; d[8] = c_wait;
+        }
     } else if (warp == 6) {
         // ===== activation (A) producer =====
         if (lane == 0) {
             int ia = 0;
-            for (int reg = blockIdx.x; reg < p.regions; reg += gridDim.x) {
-                const TcRegion r = tc_region(p, reg);
+            for (int grp = cluster_id; grp < p.groups; grp += n_clusters) {
+                const TcRegion r = tc_region(p, grp, crank);
+                if (!r.active) continue;
                 for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
                     const int s = ia % p.SA;
                     mbar_wait(emptyA + 8 * s, ((ia / p.SA) & 1) ^ 1);
@@ -263,50 +310,83 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
             }
         }
     } else if (warp == 4) {
-        // ===== weight (B) producer =====
+        // ===== weight (B) producer: this CTA's 1/csize slice of every tile, multicast to the whole cluster =====
         if (lane == 0) {
             int ib = 0;
-            for (int reg = blockIdx.x; reg < p.regions; reg += gridDim.x) {
-                const TcRegion r = tc_region(p, reg);
+            long long b_wait = 0, b0 = clock64(), bq;
+            const int slice_rows = p.Ncta / p.csize;
+            const uint32_t slice_off = (uint32_t)(crank * slice_rows * RB);
+            for (int grp = cluster_id; grp < p.groups; grp += n_clusters) {
+                const int n0 = (grp / p.groups_per_nz) * p.Ncta + crank * slice_rows;
                 for (int kb = 0; kb < p.KBn; ++kb) {
                     for (int tap = 0; tap < 9; ++tap, ++ib) {
                         const int s = ib % p.SB;
+                        bq = clock64();
                         mbar_wait(emptyB + 8 * s, ((ib / p.SB) & 1) ^ 1);
+                        b_wait += clock64() - bq;
                         mbar_expect_tx(fullB + 8 * s, 2 * p.b_plane_bytes);
-                        const uint32_t dst = sB + s * b_stage_bytes;
-                        tma_load_2d(dst, &mB, fullB + 8 * s, 0, (tap * p.KBn + kb) * p.N + r.n0);
-                        tma_load_2d(dst + p.b_plane_bytes, &mB, fullB + 8 * s, 0, ((9 + tap) * p.KBn + kb) * p.N + r.n0);
+                        const uint32_t dst = sB + s * b_stage_bytes + slice_off;
+                        const int row_hi = (tap * p.KBn + kb) * p.N + n0, row_lo = ((9 + tap) * p.KBn + kb) * p.N + n0;
+                        if (p.csize > 1) {
+                            tma_load_2d_mc(dst, &mB, fullB + 8 * s, 0, row_hi, cmask);
+                            tma_load_2d_mc(dst + p.b_plane_bytes, &mB, fullB + 8 * s, 0, row_lo, cmask);
+                        } else {
+                            tma_load_2d(dst, &mB, fullB + 8 * s, 0, row_hi);
+                            tma_load_2d(dst + p.b_plane_bytes, &mB, fullB + 8 * s, 0, row_lo);
+                        }
                     }
                 }
             }
+            if (p.dbg) {
+                long long* d = p.dbg + (long long)blockIdx.x * 16;
+                d[9] = clock64() - b0; d[10] = b_wait;
+            }
         }
     } else if (warp == 5) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Ncta >> 3) << 17) | ((128u >> 4) << 24);
-            // descriptor = {hi word: constant, lo word: (address >> 4) | LBO}; offsets are plain adds on the lo word
-            const uint64_t desc_hi = tc_smem_desc<KBT>(0) & 0xffffffff00000000ull;
-            const uint32_t lo_flag = 1u << 16;
-            const uint32_t plane_a16 = (uint32_t)p.a_plane_bytes >> 4, plane_b16 = (uint32_t)p.b_plane_bytes >> 4;
-            int ia = 0, ib = 0, it = 0;
-            for (int reg = blockIdx.x; reg < p.regions; reg += gridDim.x, ++it) {
-                const int set = it & 1;
-                mbar_wait(accEmpty + 8 * set, ((it >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d0 = tmem_base + (uint32_t)(set * acc_stride);
-                for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
-                    const int sa = ia % p.SA;
-                    mbar_wait(convA + 8 * sa, (ia / p.SA) & 1);
-                    const uint32_t a16 = (((sA + sa * a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
-                    for (int tap = 0; tap < 9; ++tap, ++ib) {
-                        const int sb = ib % p.SB;
-                        mbar_wait(fullB + 8 * sb, (ib / p.SB) & 1);
-                        tc_fence_after();
-                        const uint32_t tap16 = (uint32_t)(((tap / 3) * p.P + (tap % 3)) * RB) >> 4;
-                        const uint32_t b16 = (((sB + sb * b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
-                        const uint32_t acc0 = (kb | tap) ? 1u : 0u;
+        // ===== MMA issuer: the warp walks the loops together, one elected lane issues =====
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Ncta >> 3) << 17) | ((128u >> 4) << 24);
+        // descriptor = {hi word: constant, lo word: (address >> 4) | LBO}; offsets are plain adds on the lo word
+        const uint64_t desc_hi = tc_smem_desc<KBT>(0) & 0xffffffff00000000ull;
+        const uint32_t lo_flag = 1u << 16;
+        const uint32_t plane_a16 = (uint32_t)p.a_plane_bytes >> 4, plane_b16 = (uint32_t)p.b_plane_bytes >> 4;
+        const uint32_t tile16 = (uint32_t)(p.TH * p.P * RB) >> 4;
+        int ia = 0, ib = 0, it = 0;
+        long long t_acc = 0, t_a = 0, t_b = 0, t0 = clock64(), tq;
+        for (int grp = cluster_id; grp < p.groups; grp += n_clusters) {
+            if (!tc_region(p, grp, crank).active) {
+                // no region for this rank in the tail group: keep the weight ring moving for the cluster
+                for (int k = 0; k < 9 * p.KBn; ++k, ++ib) {
+                    const int sb = ib % p.SB;
+                    mbar_wait(fullB + 8 * sb, (ib / p.SB) & 1);
+                    if (elect_one()) tc_commit_mc(emptyB + 8 * sb, cmask);
+                    __syncwarp();
+                }
+                continue;
+            }
+            const int set = it & 1;
+            tq = clock64();
+            mbar_wait(accEmpty + 8 * set, ((it >> 1) & 1) ^ 1);
+            t_acc += clock64() - tq;
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + (uint32_t)(set * acc_stride);
+            for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
+                const int sa = ia % p.SA;
+                tq = clock64();
+                mbar_wait(convA + 8 * sa, (ia / p.SA) & 1);
+                t_a += clock64() - tq;
+                const uint32_t a16 = (((sA + sa * a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
+                for (int tap = 0; tap < 9; ++tap, ++ib) {
+                    const int sb = ib % p.SB;
+                    tq = clock64();
+                    mbar_wait(fullB + 8 * sb, (ib / p.SB) & 1);
+                    t_b += clock64() - tq;
+                    tc_fence_after();
+                    const uint32_t tap16 = (uint32_t)(((tap / 3) * p.P + (tap % 3)) * RB) >> 4;
+                    const uint32_t b16 = (((sB + sb * b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
+                    const uint32_t acc0 = (kb | tap) ? 1u : 0u;
+                    if (elect_one()) {
                         for (int t = 0; t < p.NT; ++t) {
-                            const uint32_t at16 = a16 + tap16 + ((uint32_t)(t * p.TH * p.P * RB) >> 4);
+                            const uint32_t at16 = a16 + tap16 + (uint32_t)t * tile16;
                             const uint32_t d = d0 + (uint32_t)(t * p.Ncta);
 #pragma unroll
                             for (int ks = 0; ks < KSTEPS; ++ks) {
@@ -317,12 +397,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                                 tc_mma_tf32(d, dah, dbh, idesc, 1u);
                             }
                         }
-                        tc_commit(emptyB + 8 * sb);
+                        if (p.csize > 1) tc_commit_mc(emptyB + 8 * sb, cmask);
+                        else tc_commit(emptyB + 8 * sb);
+                        if (tap == 8) tc_commit(emptyA + 8 * sa);
+                        if (tap == 8 && kb == p.KBn - 1) tc_commit(accFull + 8 * set);
                     }
-                    tc_commit(emptyA + 8 * sa);
+                    __syncwarp();
                 }
-                tc_commit(accFull + 8 * set);
             }
+            ++it;
+        }
+        if (p.dbg && lane == 0) {
+            long long* d = p.dbg + (long long)blockIdx.x * 16;
+            d[0] = clock64() - t0; d[1] = t_acc; d[2] = t_a; d[3] = t_b; d[4] = it;
         }
     } else if (warp >= 8) {
         // ===== epilogue warps 8..15 =====
@@ -332,10 +419,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
         const int etid = (warp - 8) * 32 + lane;
         const int hh = m / p.P, ww = m - hh * p.P;
         int it = 0;
-        for (int reg = blockIdx.x; reg < p.regions; reg += gridDim.x, ++it) {
-            const TcRegion r = tc_region(p, reg);
+        long long e_wait = 0, e0 = clock64(), eq;
+        for (int grp = cluster_id; grp < p.groups; grp += n_clusters) {
+            const TcRegion r = tc_region(p, grp, crank);
+            if (!r.active) continue;
             const int set = it & 1, b = r.b, n0 = r.n0;
+            eq = clock64();
             mbar_wait(accFull + 8 * set, (it >> 1) & 1);
+            e_wait += clock64() - eq;
             tc_fence_after();
             const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(set * acc_stride);
             for (int t = 0; t < p.NT; ++t) {
@@ -455,10 +546,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(accEmpty + 8 * set);
+            ++it;
+        }
+        if (p.dbg && warp == 8 && lane == 0) {
+            long long* d = p.dbg + (long long)blockIdx.x * 16;
+            d[5] = clock64() - e0; d[6] = e_wait;
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (p.csize > 1) cluster_sync_all();   // nobody exits while a peer may still multicast into / arrive on this CTA
     if (warp == 5) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
@@ -476,6 +573,10 @@ struct TcState {
     std::string reason, last_error;
     int kbt = 16;      // channels per K block (EIG_TC_KB = 16 | 32)
     int force_nt = 0;  // EIG_TC_NT: cap on MMA tiles per CTA region
+    long long* dbg = nullptr;  // device buffer for the per-role cycle counters (tests only)
+    int last_grid = 0, last_csize = 0, last_nt = 0, last_sa = 0, last_sb = 0;
+    int max_cluster = 4;  // EIG_TC_CLUSTER: cap on the multicast cluster size (1, 2 or 4)
+    std::map<std::tuple<int, int, size_t>, int> max_clusters;  // (KBT, csize, smem) -> co-resident clusters
     int n_sm = 148;
     std::map<std::tuple<const void*, int, int, int, int, int, int, int, int>, CUtensorMap> amaps;
 };
@@ -505,6 +606,7 @@ inline bool tc_available() {
     }
     if (const char* e = getenv("EIG_TC_KB")) s.kbt = atoi(e) == 32 ? 32 : 16;
     if (const char* e = getenv("EIG_TC_NT")) s.force_nt = atoi(e);
+    if (const char* e = getenv("EIG_TC_CLUSTER")) s.max_cluster = atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1);
     s.available = true;
     return true;
 }
@@ -512,6 +614,7 @@ inline std::string tc_unavailable_reason() { return tc_state().reason; }
 inline std::string tc_last_error() { return tc_state().last_error; }
 inline void tc_set_kb(int kbt) { tc_state().kbt = kbt == 32 ? 32 : 16; }
 inline void tc_set_max_nt(int nt) { tc_state().force_nt = nt; }
+inline void tc_set_max_cluster(int c) { tc_state().max_cluster = c >= 4 ? 4 : (c >= 2 ? 2 : 1); }
 
 inline float tc_host_tf32(float v) {
     uint32_t u;
@@ -555,12 +658,18 @@ inline int tc_pack(TcWeights& w, const float* wv, int cin, int N, int npad, int 
     if (cudaMemcpy(w.d, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { s.last_error = "tc_pack: upload failed"; return -1; }
     const cuuint64_t gdim[2] = {(cuuint64_t)KBT, (cuuint64_t)2 * 9 * w.KBn * N};
     const cuuint64_t gstr[1] = {(cuuint64_t)KBT * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)KBT, (cuuint32_t)w.Ncta};
     const cuuint32_t est[2] = {1, 1};
-    const CUresult r = s.encode(&w.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w.d, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                KBT == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { s.last_error = "tc_pack: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return -1; }
+    w.max_csize = 1;
+    for (int ci = 0; ci < 3; ++ci) {
+        const int cs = 1 << ci;
+        if (w.Ncta % (8 * cs)) break;   // every CTA's slice must be whole 8-row swizzle atoms
+        const cuuint32_t box[2] = {(cuuint32_t)KBT, (cuuint32_t)(w.Ncta / cs)};
+        const CUresult r = s.encode(&w.map[ci], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w.d, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    KBT == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { s.last_error = "tc_pack: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return -1; }
+        w.max_csize = cs;
+    }
     w.ok = true;
     return 0;
 }
@@ -571,7 +680,7 @@ inline int tc_round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // Picks the flat-padded tile (TW x TH, P = TW + 2, (TH-1)*P + TW <= 128) with the best MMA-row efficiency, then the
 // number of stacked tiles per CTA region (weight-tile reuse) that still load-balances over the SMs and fits shared memory.
-inline bool tc_geometry(int B, int H, int W, int KBT, int Ncta, int gz, bool pooled, int force_nt, int n_sm, TcGeom& g) {
+inline bool tc_geometry(int B, int H, int W, int KBT, int Ncta, int gz, bool pooled, int force_nt, int n_sm, int csize, TcGeom& g) {
     double best = -1.0;
     int bTW = 0, bTH = 0;
     const int step = pooled ? 2 : 1;
@@ -614,13 +723,15 @@ inline bool tc_geometry(int B, int H, int W, int KBT, int Ncta, int gz, bool poo
         TcGeom c = g;
         c.NT = NT; c.SA = SA; c.SB = SB; c.a_plane = a_plane;
         c.tiles_y = (row_tiles + NT - 1) / NT;
-        c.regions = c.tiles_x * c.tiles_y * B * gz;
+        c.regions = c.tiles_x * c.tiles_y * B;
         int cols = 32;
         while (cols < 2 * NT * Ncta) cols <<= 1;
         c.tmem_cols = cols;
         c.smem = (size_t)SA * 2 * a_plane + (size_t)SB * 2 * g.b_plane + g.staging + 8 * (3 * SA + 2 * SB + 4) + 16 + 1024;
-        const int rounds = (c.regions + n_sm - 1) / n_sm;
-        const double eff = (double)c.regions / ((double)rounds * n_sm);
+        const int slots = n_sm / csize;                                    // clusters that run side by side
+        const int groups = ((c.regions + csize - 1) / csize) * gz;
+        const int rounds = (groups + slots - 1) / slots;
+        const double eff = (double)c.regions * gz / ((double)rounds * slots * csize);
         cand[NT] = c;
         if (eff >= 0.85) { pick = NT; break; }       // largest NT that still fills the machine evenly
         if (eff > pick_eff) { pick_eff = eff; pick = NT; }
@@ -640,8 +751,10 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     const bool pooled = a.epi == EPI_CONVA;
     if (pooled && ((a.H | a.W) & 1)) { s.last_error = "tc_conv: pooled conv needs even H, W"; return -1; }
     if (pooled && w.Ncta > 128) { s.last_error = "tc_conv: pooled conv needs <= 128 channels per CTA"; return -1; }
+    int csize = std::min(w.max_csize, s.max_cluster);
     TcGeom g;
-    if (!tc_geometry(a.B, a.H, a.W, w.KBT, w.Ncta, w.gz, pooled, s.force_nt, s.n_sm, g)) { s.last_error = "tc_conv: no tile geometry fits"; return -1; }
+    if (!tc_geometry(a.B, a.H, a.W, w.KBT, w.Ncta, w.gz, pooled, s.force_nt, s.n_sm, csize, g)) { s.last_error = "tc_conv: no tile geometry fits"; return -1; }
+    while (csize > 1 && g.regions < csize) csize >>= 1;
     const int box_rows = g.NT * g.TH + 2;
     auto key = std::make_tuple((const void*)(a.in_hi + a.in_coff), a.Cin, a.W, a.H, a.B, a.in_pitch, g.P, box_rows, w.KBT);
     auto it = s.amaps.find(key);
@@ -667,11 +780,35 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     p.staging_bytes = g.staging; p.stage_ld = g.stage_ld;
     p.ca = a;
     if (g.smem > TC_SMEM_LIMIT) { s.last_error = "tc_conv: shared memory budget exceeded"; return -1; }
-    const int grid = g.regions < s.n_sm ? g.regions : s.n_sm;
-    if (w.KBT == 32)
-        conv3x3_tc_kernel<32><<<dim3(grid), dim3(TC_THREADS), g.smem, stream>>>(it->second, w.map, p);
-    else
-        conv3x3_tc_kernel<16><<<dim3(grid), dim3(TC_THREADS), g.smem, stream>>>(it->second, w.map, p);
+    p.csize = csize;
+    p.dbg = s.dbg;
+    p.groups_per_nz = (g.regions + csize - 1) / csize;
+    p.groups = p.groups_per_nz * w.gz;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = g.smem; cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    void (*kern)(const CUtensorMap, const CUtensorMap, const TcParams) = w.KBT == 32 ? conv3x3_tc_kernel<32> : conv3x3_tc_kernel<16>;
+    int slots = s.n_sm / csize;
+    if (csize > 1) {   // how many clusters can be resident at once (GPC boundaries cost a few SMs)
+        auto ck = std::make_tuple(w.KBT, csize, g.smem);
+        auto ci = s.max_clusters.find(ck);
+        if (ci == s.max_clusters.end()) {
+            int n = 0;
+            cfg.gridDim = dim3(s.n_sm / csize * csize);
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = s.n_sm / csize / 2; }
+            ci = s.max_clusters.emplace(ck, n).first;
+        }
+        slots = std::min(slots, ci->second);
+    }
+    const int n_clusters = std::min(p.groups, slots);
+    cfg.gridDim = dim3(n_clusters * csize);
+    s.last_grid = n_clusters * csize; s.last_csize = csize; s.last_nt = g.NT; s.last_sa = g.SA; s.last_sb = g.SB;
+    const int ci_map = csize == 4 ? 2 : (csize == 2 ? 1 : 0);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, it->second, w.map[ci_map], p);
+    if (le != cudaSuccess) { s.last_error = std::string("tc_conv launch: ") + cudaGetErrorString(le); cudaGetLastError(); return -1; }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { s.last_error = std::string("tc_conv launch: ") + cudaGetErrorString(e); return -1; }
     return 0;

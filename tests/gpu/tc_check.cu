@@ -2,7 +2,7 @@
 //   part 1: raw accumulators (EPI_RAW) against a float64 CPU convolution
 //   part 2: the three fused epilogues against the exact-fp32 SIMT kernel on identical inputs
 // both for 16-channel (64-byte swizzle) and 32-channel (128-byte swizzle) K blocks, and with the tiles-per-region cap
-// at 1 (no weight-tile reuse) and unlimited.
+// at 1 (no weight-tile reuse) and unlimited, and with the weight-tile multicast cluster at 4, 2 and 1 CTAs.
 // usage: tc_check [kb]      exit code 0 = the selected K block (default 16, the product setting) passes everything.
 // Tolerances: the tensor core's fp32 accumulator truncates, so over K = 9*192 the result sits ~1e-5 (relative to the
 // output scale) from float64 and from the SIMT kernel's round-to-nearest fp32 sums; the bar is 4e-5 + 1e-5 * K/1000.
@@ -178,9 +178,73 @@ static bool check_epilogues(Problem& p, int mode) {
     return ok;
 }
 
+// timing mode: `tc_check time` runs the PredNet layer shapes at population 32 with the per-role cycle counters on
+static void time_shape(const char* name, int B, int H, int W, int pitch, int coff, int Cin, int N, int epi, int cluster, int max_nt) {
+    tc_set_max_cluster(cluster); tc_set_max_nt(max_nt);
+    Problem p; make_problem(p, B, H, W, pitch, coff, Cin, N, 5, 16);
+    const size_t px = (size_t)B * H * W;
+    ConvArgs a = base_args(p);
+    a.epi = epi;
+    float *out = nullptr, *cst = nullptr, *peep = nullptr, *dh = nullptr, *Pp = nullptr, *dE = nullptr;
+    if (epi == EPI_CONVP) { CHECK(cudaMalloc(&out, px * N * 4)); a.outP = out; }
+    if (epi == EPI_LSTM) {
+        const int R = N / 4;
+        CHECK(cudaMalloc(&cst, px * R * 4)); CHECK(cudaMemset(cst, 0, px * R * 4));
+        CHECK(cudaMalloc(&peep, (size_t)H * W * R * 16)); CHECK(cudaMemset(peep, 0, (size_t)H * W * R * 16));
+        CHECK(cudaMalloc(&dh, px * R * 4));
+        a.cstate = cst; a.peep = peep; a.dstH = mkview(dh, nullptr, R, 0, R);
+    }
+    if (epi == EPI_CONVA) {
+        CHECK(cudaMalloc(&Pp, px / 4 * N * 4)); CHECK(cudaMemset(Pp, 0, px / 4 * N * 4));
+        CHECK(cudaMalloc(&dE, px / 4 * 2 * N * 4));
+        a.P = Pp; a.dstE = mkview(dE, nullptr, 2 * N, 0, 2 * N);
+    }
+    long long* dbg; CHECK(cudaMalloc(&dbg, 160 * 16 * 8)); CHECK(cudaMemset(dbg, 0, 160 * 16 * 8));
+    tc_state().dbg = dbg;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) tc_conv(p.tw, a, 0);
+    CHECK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    const int reps = 10;
+    for (int i = 0; i < reps; ++i) if (tc_conv(p.tw, a, 0)) { printf("tc_conv: %s\n", tc_last_error().c_str()); exit(2); }
+    cudaEventRecord(e1);
+    CHECK(cudaDeviceSynchronize());
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    std::vector<long long> d = host(dbg, 160 * 16);
+    const int grid = tc_state().last_grid;
+    double s[11] = {0};
+    for (int c = 0; c < grid; ++c) for (int k = 0; k < 11; ++k) s[k] += (double)d[c * 16 + k] / grid;
+    const double flop = 2.0 * px * 9.0 * Cin * N;
+    printf("%-8s B%d %dx%d Cin%d N%d cluster %d NT %d SA %d SB %d grid %d: %7.1f us  %6.1f TFLOP/s(fp32-equiv) | MMA thr: total %6.0f waitAcc %5.0f waitA %5.0f waitB %5.0f regions %.1f | epi: total %6.0f wait %6.0f | conv: total %6.0f wait %6.0f | Bprod: wait %6.0f (cycles, avg per CTA)\n",
+           name, B, W, H, Cin, N, tc_state().last_csize, tc_state().last_nt, tc_state().last_sa, tc_state().last_sb, grid, 1e3 * ms / reps,
+           flop / (1e-3 * ms / reps) / 1e12, s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], s[10]);
+    tc_state().dbg = nullptr;
+    cudaFree(dbg); cudaFree(out); cudaFree(cst); cudaFree(peep); cudaFree(dh); cudaFree(Pp); cudaFree(dE);
+    cudaFree(p.d_hi); cudaFree(p.d_w); cudaFree(p.d_b); tc_free(p.tw);
+}
+
+static int timing_main() {
+    for (int cluster = 1; cluster <= 4; cluster *= 2) {
+        for (int max_nt = 0; max_nt <= 1; ++max_nt) {
+            printf("--- cluster <= %d, tiles per region %s\n", cluster, max_nt ? "1" : "auto");
+            time_shape("LSTM1", 32, 60, 80, 80, 0, 80, 64, EPI_LSTM, cluster, max_nt);
+            time_shape("LSTM2", 32, 30, 40, 160, 0, 160, 128, EPI_LSTM, cluster, max_nt);
+            time_shape("LSTM3", 32, 15, 20, 192, 0, 192, 256, EPI_LSTM, cluster, max_nt);
+            time_shape("ConvA2", 32, 60, 80, 80, 0, 32, 32, EPI_CONVA, cluster, max_nt);
+            time_shape("ConvA3", 32, 30, 40, 160, 0, 64, 64, EPI_CONVA, cluster, max_nt);
+            time_shape("ConvP1", 32, 60, 80, 80, 64, 16, 16, EPI_CONVP, cluster, max_nt);
+            time_shape("ConvP2", 32, 30, 40, 160, 128, 32, 32, EPI_CONVP, cluster, max_nt);
+            time_shape("ConvP3", 32, 15, 20, 192, 128, 64, 64, EPI_CONVP, cluster, max_nt);
+            time_shape("LSTM1x4", 128, 60, 80, 80, 0, 80, 64, EPI_LSTM, cluster, max_nt);
+        }
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
-    const int want_kb = argc > 1 ? atoi(argv[1]) : 16;
     if (!tc_available()) { printf("tensor-core path unavailable: %s\n", tc_unavailable_reason().c_str()); return 4; }
+    if (argc > 1 && !strcmp(argv[1], "time")) return timing_main();
+    const int want_kb = argc > 1 ? atoi(argv[1]) : 16;
     struct Shape { int B, H, W, pitch, coff, Cin, N; };
     const Shape shapes[] = {
         {2, 15, 20, 192, 0, 192, 256},   // gray ConvLSTM3
@@ -193,22 +257,24 @@ int main(int argc, char** argv) {
         {3, 30, 40, 480, 0, 480, 384},   // colour ConvLSTM2: N split over two CTA columns
     };
     bool kb_ok[2] = {true, true};
-    const int kbs[2] = {16, 32};
-    for (int ki = 0; ki < 2; ++ki) {
-        for (int max_nt = 0; max_nt < 2; ++max_nt) {
-            printf("== K block %d, tiles per region %s ==\n", kbs[ki], max_nt ? "capped at 1" : "auto");
-            tc_set_max_nt(max_nt);
-            unsigned seed = 1;
-            for (const Shape& s : shapes) {
-                Problem p; make_problem(p, s.B, s.H, s.W, s.pitch, s.coff, s.Cin, s.N, seed++, kbs[ki]);
-                g_tol = 4e-5 + 1e-5 * (9.0 * s.Cin / 1000.0);
-                bool ok = check_raw(p, max_nt);
-                if (ok) ok &= check_epilogues(p, max_nt);
-                kb_ok[ki] &= ok;
-                cudaFree(p.d_hi); cudaFree(p.d_w); cudaFree(p.d_b); tc_free(p.tw);
-            }
+    struct Cfg { int kb, max_nt, cluster; };
+    const Cfg cfgs[] = {{16, 0, 4}, {16, 0, 2}, {16, 1, 1}, {16, 0, 1}, {32, 0, 4}, {32, 1, 1}};
+    for (const Cfg& c : cfgs) {
+        printf("== K block %d, tiles per region %s, multicast cluster <= %d ==\n", c.kb, c.max_nt ? "capped at 1" : "auto", c.cluster);
+        tc_set_max_nt(c.max_nt);
+        tc_set_max_cluster(c.cluster);
+        unsigned seed = 1;
+        bool all = true;
+        for (const Shape& s : shapes) {
+            Problem p; make_problem(p, s.B, s.H, s.W, s.pitch, s.coff, s.Cin, s.N, seed++, c.kb);
+            g_tol = 4e-5 + 1e-5 * (9.0 * s.Cin / 1000.0);
+            bool ok = check_raw(p, c.max_nt);
+            if (ok) ok &= check_epilogues(p, c.max_nt);
+            all &= ok;
+            cudaFree(p.d_hi); cudaFree(p.d_w); cudaFree(p.d_b); tc_free(p.tw);
         }
-        printf("== K block %d: %s ==\n", kbs[ki], kb_ok[ki] ? "PASS" : "FAIL");
+        printf("== %s ==\n", all ? "PASS" : "FAIL");
+        kb_ok[c.kb == 32 ? 1 : 0] &= all;
     }
     printf("RESULT kb16 %d kb32 %d\n", kb_ok[0], kb_ok[1]);
     return kb_ok[want_kb == 32 ? 1 : 0] ? 0 : 1;
