@@ -234,9 +234,9 @@ def run_ours(args):
     for _ in range(prof_steps):
         eng.evaluate_resident(resident, structure, out=fit_dev)
     eng.lib.check(eng.lib.eig_profile_end(eng.ctx, ms, cnt))
-    cls_names = ["render", "conv_simt", "conv_tcgen05", "elementwise", "flow", "score"]
-    cls_ms = {cls_names[i]: ms[i] / prof_steps for i in range(6)}
-    cls_n = {cls_names[i]: int(cnt[i] // prof_steps) for i in range(6)}
+    cls_names = ["render", "conv_simt", "conv_tcgen05", "elementwise", "flow", "score", "layer0_fused"]
+    cls_ms = {cls_names[i]: ms[i] / prof_steps for i in range(7)}
+    cls_n = {cls_names[i]: int(cnt[i] // prof_steps) for i in range(7)}
 
     if rank == 0:
         peaks = measured_peaks()

@@ -1,0 +1,260 @@
+// PredNet layer-0 kernels (full image resolution, C0 = 1 or 3 channels): exact-fp32 SIMT, HBM/L2-bound.
+// These stages have no tensor-core shape (K <= 9*57, N <= 48) - they are fused so that every pixel-sized tensor is
+// read and written once per time step:
+//   l0_conva1_kernel : E0 = [relu(x-P0), relu(P0-x)] on the fly -> ConvA1 (2*C0 -> C1) -> relu -> 2x2 max-pool
+//                      -> E1 = [relu(A1-P1), relu(P1-A1)] into the layer-1 concat buffer        (net.py:187-194)
+//   l0_lstm_kernel   : ConvLSTM0 on [E0 | up2x(R1) | h0]: E0 recomputed from x and P0, R1 read at half resolution
+//                      straight from the layer-1 buffer (no up-sampled copy in HBM), 4 gates + cell update fused
+//                                                                                               (net.py:94-126,202-203)
+//   l0_convp_kernel  : P0 = min(relu(ConvP0(h0)), 1)                                              (net.py:207)
+// Accumulation order: input channel, then ky, then kx, with fused multiply-add (same as conv_simt.cuh).
+#pragma once
+#include "common.cuh"
+#include "conv_simt.cuh"
+
+namespace eig {
+
+struct L0Args {
+    int B, H, W, C0, C1;
+    const float* x;        // [B,H,W,C0] input frame of this step (== P0 on the self-fed extension steps)
+    const float* P0;       // [B,H,W,C0] prediction of the previous step
+    // ConvA1
+    const float* wA;       // [9][2*C0][C1pad]
+    const float* bA;       // [C1]
+    int C1pad;
+    const float* P1;       // [B,H/2,W/2,C1]
+    View dstE1;            // layer-1 concat buffer, channels [0, 2*C1)
+    // ConvLSTM0
+    const float* wL;       // [9][ctot0][4*C0], ctot0 = 2*C0 + C1 + C0
+    const float* bL;       // [4*C0] gate-interleaved
+    const float* peep;     // [H,W,C0,4]
+    const float* R1;       // layer-1 concat buffer holding h1 of this step
+    int R1_pitch, R1_coff;
+    const float* h_prev;   // [B,H,W,C0]
+    float* h_next;         // [B,H,W,C0]
+    float* cstate;         // [B,H,W,C0]
+    // ConvP0
+    const float* wP;       // [9][C0][C0pad]
+    const float* bP;       // [C0]
+    int C0pad;
+    float* P0_out;         // [B,H,W,C0]
+};
+
+enum { L0_TW = 32, L0_TH = 8 };
+
+// ---------------------------------------------------------------------------------------------- ConvA1
+// CTA = 32x8 full-resolution pixels of one genome = 16x4 pooled pixels; thread = one pooled pixel x CPT channels.
+template <int CPT>
+__global__ void __launch_bounds__(256) l0_conva1_kernel(L0Args a) {
+    constexpr int SW = L0_TW + 2, SH = L0_TH + 2;
+    EIG_DYN_SMEM(smem);
+    float* sE = reinterpret_cast<float*>(smem);                 // [2*C0][SH][SW]
+    float* sW = sE + 2 * a.C0 * SH * SW;                        // [9][2*C0][C1pad]
+    const int tiles_x = (a.W + L0_TW - 1) / L0_TW;
+    const int x0 = (blockIdx.x % tiles_x) * L0_TW, y0 = (blockIdx.x / tiles_x) * L0_TH;
+    const int b = blockIdx.y;
+    const int cin = 2 * a.C0;
+    const long long img = (long long)b * a.H * a.W;
+    for (int i = threadIdx.x; i < SH * SW; i += blockDim.x) {
+        const int cy = i / SW, cx = i - cy * SW;
+        const int gy = y0 + cy - 1, gx = x0 + cx - 1;
+        const bool in = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+        for (int c = 0; c < a.C0; ++c) {
+            float ep = 0.f, en = 0.f;
+            if (in) {
+                const long long idx = (img + (long long)gy * a.W + gx) * a.C0 + c;
+                const float xv = a.x[idx], pv = a.P0[idx];
+                ep = __fsub_rn(xv, pv); en = __fsub_rn(pv, xv);
+                ep = ep > 0.f ? ep : 0.f; en = en > 0.f ? en : 0.f;
+            }
+            sE[(c * SH + cy) * SW + cx] = ep;
+            sE[((a.C0 + c) * SH + cy) * SW + cx] = en;
+        }
+    }
+    for (int i = threadIdx.x; i < 9 * cin * a.C1pad; i += blockDim.x) sW[i] = a.wA[i];
+    __syncthreads();
+
+    const int pp = threadIdx.x & 63, grp = threadIdx.x >> 6;    // pooled pixel in the tile, channel group
+    const int px = pp & 15, py = pp >> 4;
+    const int n0 = grp * CPT;
+    float acc[4][CPT];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int n = 0; n < CPT; ++n) acc[j][n] = 0.f;
+    for (int c = 0; c < cin; ++c) {
+        float in[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) in[r][q] = sE[(c * SH + 2 * py + r) * SW + 2 * px + q];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float* wrow = sW + ((ky * 3 + kx) * cin + c) * a.C1pad + n0;
+                float wv[CPT];
+#pragma unroll
+                for (int n = 0; n < CPT; n += 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(wrow + n);
+                    wv[n] = q.x; wv[n + 1] = q.y; wv[n + 2] = q.z; wv[n + 3] = q.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int n = 0; n < CPT; ++n)
+                        acc[j][n] = __fmaf_rn(in[(j >> 1) + ky][(j & 1) + kx], wv[n], acc[j][n]);
+            }
+    }
+    const int Hp = a.H >> 1, Wp = a.W >> 1;
+    const int gpy = (y0 >> 1) + py, gpx = (x0 >> 1) + px;
+    if (gpy >= Hp || gpx >= Wp) return;
+    const long long ppos = ((long long)b * Hp + gpy) * Wp + gpx;
+#pragma unroll
+    for (int n = 0; n < CPT; ++n) {
+        if (n0 + n >= a.C1) continue;
+        const float bn = a.bA[n0 + n];
+        float m = fmaxf(fmaxf(__fadd_rn(acc[0][n], bn), __fadd_rn(acc[1][n], bn)),
+                        fmaxf(__fadd_rn(acc[2][n], bn), __fadd_rn(acc[3][n], bn)));
+        m = fmaxf(m, 0.f);  // relu commutes with max
+        const float pv = a.P1[ppos * a.C1 + n0 + n];
+        const float ep = __fsub_rn(m, pv), en = __fsub_rn(pv, m);
+        view_store(a.dstE1, ppos, n0 + n, ep > 0.f ? ep : 0.f);
+        view_store(a.dstE1, ppos, a.C1 + n0 + n, en > 0.f ? en : 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- ConvLSTM0
+// CTA = 32x8 pixels of one genome, 64 threads, thread = 1x4 pixel strip x all NG = 4*C0 gate columns.
+// Input channels are streamed through shared memory in chunks of <= L0_CHUNK.
+enum { L0_CHUNK = 20 };
+template <int NG>
+__global__ void __launch_bounds__(64) l0_lstm_kernel(L0Args a) {
+    constexpr int SW = L0_TW + 2, SH = L0_TH + 2, C0 = NG / 4;
+    __shared__ float sIn[L0_CHUNK][SH][SW];
+    __shared__ __align__(16) float sWt[9 * L0_CHUNK * NG];
+    const int tiles_x = (a.W + L0_TW - 1) / L0_TW;
+    const int x0 = (blockIdx.x % tiles_x) * L0_TW, y0 = (blockIdx.x / tiles_x) * L0_TH;
+    const int b = blockIdx.y;
+    const int ctot = 2 * C0 + a.C1 + C0;
+    const long long img = (long long)b * a.H * a.W;
+    const int H1 = a.H >> 1, W1 = a.W >> 1;
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;   // strip: columns 4*tx .. 4*tx+3 of row ty
+    float acc[4][NG];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int n = 0; n < NG; ++n) acc[j][n] = 0.f;
+
+    for (int c0 = 0; c0 < ctot; c0 += L0_CHUNK) {
+        const int nc = ctot - c0 < L0_CHUNK ? ctot - c0 : L0_CHUNK;
+        for (int i = threadIdx.x; i < SH * SW; i += blockDim.x) {
+            const int cy = i / SW, cx = i - cy * SW;
+            const int gy = y0 + cy - 1, gx = x0 + cx - 1;
+            const bool in = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+            const long long pix = img + (long long)gy * a.W + gx;
+            const long long pix1 = ((long long)b * H1 + (gy >> 1)) * W1 + (gx >> 1);
+            for (int k = 0; k < nc; ++k) {
+                const int c = c0 + k;
+                float v = 0.f;
+                if (in) {
+                    if (c < 2 * C0) {
+                        const int cc = c < C0 ? c : c - C0;
+                        const float xv = a.x[pix * C0 + cc], pv = a.P0[pix * C0 + cc];
+                        v = c < C0 ? __fsub_rn(xv, pv) : __fsub_rn(pv, xv);
+                        v = v > 0.f ? v : 0.f;
+                    } else if (c < 2 * C0 + a.C1) {
+                        v = a.R1[pix1 * a.R1_pitch + a.R1_coff + (c - 2 * C0)];   // nearest-neighbour x2 up-sampling
+                    } else {
+                        v = a.h_prev[pix * C0 + (c - 2 * C0 - a.C1)];
+                    }
+                }
+                sIn[k][cy][cx] = v;
+            }
+        }
+        for (int i = threadIdx.x; i < 9 * nc * NG; i += blockDim.x) {
+            const int n = i % NG, r = i / NG;
+            const int k = r % nc, tap = r / nc;
+            sWt[(tap * L0_CHUNK + k) * NG + n] = a.wL[((long long)tap * ctot + c0 + k) * NG + n];
+        }
+        __syncthreads();
+        for (int k = 0; k < nc; ++k) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                float in[6];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) in[q] = sIn[k][ty + ky][4 * tx + q];
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float* wrow = sWt + ((ky * 3 + kx) * L0_CHUNK + k) * NG;
+                    float wv[NG];
+#pragma unroll
+                    for (int n = 0; n < NG; n += 4) {
+                        const float4 q = *reinterpret_cast<const float4*>(wrow + n);
+                        wv[n] = q.x; wv[n + 1] = q.y; wv[n + 2] = q.z; wv[n + 3] = q.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int n = 0; n < NG; ++n) acc[j][n] = __fmaf_rn(in[j + kx], wv[n], acc[j][n]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int gy = y0 + ty;
+    if (gy >= a.H) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int gx = x0 + 4 * tx + j;
+        if (gx >= a.W) continue;
+        const long long pix = img + (long long)gy * a.W + gx;
+        const long long ppix = (long long)gy * a.W + gx;
+#pragma unroll
+        for (int r = 0; r < C0; ++r) {
+            const float hnew = lstm_cell(acc[j][r * 4], acc[j][r * 4 + 1], acc[j][r * 4 + 2], acc[j][r * 4 + 3], a.bL + r * 4,
+                                         a.peep + (ppix * C0 + r) * 4, a.cstate + pix * C0 + r);
+            a.h_next[pix * C0 + r] = hnew;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- ConvP0
+template <int C0>
+__global__ void __launch_bounds__(256) l0_convp_kernel(L0Args a) {
+    __shared__ float sW[9 * C0 * C0];
+    __shared__ float sB[C0];
+    for (int i = threadIdx.x; i < 9 * C0 * C0; i += blockDim.x) {
+        const int n = i % C0, r = i / C0;
+        sW[i] = a.wP[(long long)r * a.C0pad + n];
+    }
+    if (threadIdx.x < C0) sB[threadIdx.x] = a.bP[threadIdx.x];
+    __syncthreads();
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long npix = (long long)a.B * a.H * a.W;
+    if (p >= npix) return;
+    const int gx = (int)(p % a.W), gy = (int)((p / a.W) % a.H);
+    float acc[C0];
+#pragma unroll
+    for (int n = 0; n < C0; ++n) acc[n] = 0.f;
+#pragma unroll
+    for (int c = 0; c < C0; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int yy = gy + ky - 1, xx = gx + kx - 1;
+                float v = 0.f;
+                if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) v = a.h_next[(p + (long long)(ky - 1) * a.W + (kx - 1)) * C0 + c];
+#pragma unroll
+                for (int n = 0; n < C0; ++n) acc[n] = __fmaf_rn(v, sW[((ky * 3 + kx) * C0 + c) * C0 + n], acc[n]);
+            }
+#pragma unroll
+    for (int n = 0; n < C0; ++n) {
+        float v = __fadd_rn(acc[n], sB[n]);
+        v = v > 0.f ? v : 0.f;
+        a.P0_out[p * C0 + n] = v > 1.f ? 1.f : v;
+    }
+}
+
+}  // namespace eig

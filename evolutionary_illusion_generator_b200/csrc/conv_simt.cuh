@@ -203,18 +203,6 @@ __global__ void __launch_bounds__(256) conv3x3_simt_kernel(ConvArgs a) {
     }
 }
 
-// E0 = [relu(x - P0), relu(P0 - x)] -> dst view (net.py:187-188).  x and P0 are [B,H,W,C0] fp32.
-__global__ void __launch_bounds__(256) error0_kernel(const float* x, const float* P0, View dst, long long npix, int C0) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npix * C0) return;
-    const long long pix = i / C0;
-    const int c = (int)(i % C0);
-    const float xv = x[i], pv = P0[i];
-    const float ep = __fsub_rn(xv, pv), en = __fsub_rn(pv, xv);
-    view_store(dst, pix, c, ep > 0.f ? ep : 0.f);
-    view_store(dst, pix, C0 + c, en > 0.f ? en : 0.f);
-}
-
 // write_image (call_prednet.py:51-61): u8 = trunc(P0 * 255) in fp32; then cv2 gray (optical_flow.py:62-65):
 // (B*3735 + G*19235 + R*9798 + 16384) >> 15 on the RGB triple, identity for one channel.
 __global__ void __launch_bounds__(256) quantize_gray_kernel(const float* P0, unsigned char* img, unsigned char* gray,

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "render.cuh"
 #include "conv_simt.cuh"
+#include "conv_l0.cuh"
 #include "flow.cuh"
 #include "score.cuh"
 #ifndef EIG_EMU
@@ -40,7 +41,7 @@ static int fail(int code, const std::string& msg) {
 
 // Optional per-kernel-class device timing (bench.py's roofline pass): every launch is bracketed by a pair of
 // CUDA events on the launching stream; eig_profile_end sums them per class.
-enum { CLS_RENDER = 0, CLS_CONV_SIMT = 1, CLS_CONV_TC = 2, CLS_ELEMENTWISE = 3, CLS_FLOW = 4, CLS_SCORE = 5, CLS_COUNT = 8 };
+enum { CLS_RENDER = 0, CLS_CONV_SIMT = 1, CLS_CONV_TC = 2, CLS_ELEMENTWISE = 3, CLS_FLOW = 4, CLS_SCORE = 5, CLS_L0 = 6, CLS_COUNT = 8 };
 struct Profiler {
     bool on = false;
     std::vector<cudaEvent_t> ev;
@@ -86,6 +87,7 @@ struct eig_ctx {
     // activations
     float* X[4][2] = {{nullptr}};    // concat buffers [B][H][W][ctot] = [E_n | up(R_{n+1}) | h_n], double-buffered over time steps
     float* cst[4] = {nullptr};       // cell state [B][H][W][R]
+    float* h0[2] = {nullptr, nullptr};  // layer-0 hidden state [B][h][w][C0], double-buffered over time steps
     float* P[4] = {nullptr};         // predictions [B][H][W][C]
     float* x_in = nullptr;           // [B][h][w][c]
     unsigned char* img = nullptr;    // rendered [B][h][w][c]
@@ -121,6 +123,7 @@ extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, co
     if (!out || !channels || max_genomes <= 0) return fail(EIG_E_INVALID, "eig_create: null/invalid argument");
     if (w % 8 || h % 8 || w <= 0 || h <= 0) return fail(EIG_E_INVALID, "eig_create: w and h must be positive multiples of 8");
     if (c_dim != channels[0] || (c_dim != 1 && c_dim != 3)) return fail(EIG_E_INVALID, "eig_create: c_dim must equal channels[0] and be 1 or 3");
+    if (channels[1] > 64) return fail(EIG_E_INVALID, "eig_create: channels[1] > 64 is not supported by the fused layer-0 kernel");
     if (w <= FLOW_WIN || h <= FLOW_WIN) return fail(EIG_E_INVALID, "eig_create: image must be larger than the 50-px LK window");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
@@ -135,7 +138,8 @@ extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, co
     for (int n = 0; n < 4; ++n) {
         const size_t px = B * c->H[n] * c->W[n];
         for (int k = 0; k < 2; ++k) {
-            CK(dalloc(c, &c->X[n][k], px * c->ctot[n]));
+            if (n >= 1) CK(dalloc(c, &c->X[n][k], px * c->ctot[n]));   // layer 0 keeps no concat buffer (conv_l0.cuh)
+            else CK(dalloc(c, &c->h0[k], px * c->ch[0]));
         }
         CK(dalloc(c, &c->cst[n], px * c->ch[n]));
         CK(dalloc(c, &c->P[n], px * c->ch[n]));
@@ -344,19 +348,41 @@ static int launch_conv(eig_ctx* c, const ConvArgs& a, cudaStream_t s) {
 
 static View mkview(float* hi, float* lo, int pitch, int coff, int C) { View v; v.hi = hi; v.lo = lo; v.pitch = pitch; v.coff = coff; v.C = C; return v; }
 
+static L0Args l0_args(eig_ctx* c, const float* x, int B, int cur, int nxt) {
+    L0Args a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.H = c->h; a.W = c->w; a.C0 = c->ch[0]; a.C1 = c->ch[1];
+    a.x = x; a.P0 = c->P[0];
+    a.wA = c->lw[1].convA; a.bA = c->lw[1].convA_b; a.C1pad = (c->ch[1] + 3) & ~3;
+    a.P1 = c->P[1];
+    a.dstE1 = mkview(c->X[1][cur], nullptr, c->ctot[1], 0, 2 * c->ch[1]);
+    a.wL = c->lw[0].lstm; a.bL = c->lw[0].lstm_b; a.peep = c->lw[0].peep;
+    a.R1 = c->X[1][nxt]; a.R1_pitch = c->ctot[1]; a.R1_coff = 2 * c->ch[1] + c->ch[2];
+    a.h_prev = c->h0[cur]; a.h_next = c->h0[nxt]; a.cstate = c->cst[0];
+    a.wP = c->lw[0].convP; a.bP = c->lw[0].convP_b; a.C0pad = (c->ch[0] + 3) & ~3;
+    a.P0_out = c->P[0];
+    return a;
+}
+
 // One PredNet time step (net.py:175-211) for B genomes.  x: [B][h][w][c] input frame, t: step index.
+// Layer 0 runs on the fused full-resolution kernels of conv_l0.cuh; layers 1..3 on the tcgen05 kernel (conv_mode TC,
+// shapes with N % 16 == 0) or on the exact-fp32 SIMT kernel.
 static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s) {
     const int cur = t & 1, nxt = cur ^ 1;
     const bool tc = c->conv_mode == EIG_CONV_TC;
     int rc;
-    {   // E0 -> X0[cur].E
-        const long long npix = (long long)B * c->h * c->w;
-        const long long tot = npix * c->c_dim;
-        LAUNCH_K(CLS_ELEMENTWISE, error0_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, x, (const float*)c->P[0],
-                   mkview(c->X[0][cur], nullptr, c->ctot[0], 0, 2 * c->ch[0]), npix, c->c_dim);
+    const L0Args l0 = l0_args(c, x, B, cur, nxt);
+    const int l0_tiles = ((c->w + L0_TW - 1) / L0_TW) * ((c->h + L0_TH - 1) / L0_TH);
+    {   // E0 -> ConvA1 -> pool -> E1 (layer-1 concat buffer)
+        const int c1pad = l0.C1pad;
+        const size_t smem = ((size_t)2 * l0.C0 * (L0_TH + 2) * (L0_TW + 2) + (size_t)9 * 2 * l0.C0 * c1pad + 16) * sizeof(float);
+        if (c1pad <= 4) { auto k = l0_conva1_kernel<4>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(64), smem, s, l0); }
+        else if (c1pad <= 16) { auto k = l0_conva1_kernel<8>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(64 * ((c1pad + 7) / 8)), smem, s, l0); }
+        else if (c1pad <= 48) { auto k = l0_conva1_kernel<12>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(64 * ((c1pad + 11) / 12)), smem, s, l0); }
+        else { auto k = l0_conva1_kernel<16>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(64 * ((c1pad + 15) / 16)), smem, s, l0); }
         CKL();
     }
-    for (int n = 1; n < 4; ++n) {  // ConvA_n: E_{n-1} (res n-1) -> pool -> E_n
+    for (int n = 2; n < 4; ++n) {  // ConvA_n: E_{n-1} (res n-1) -> pool -> E_n
         ConvArgs a;
         memset(&a, 0, sizeof a);
         a.in_hi = c->X[n - 1][cur]; a.in_lo = nullptr;
@@ -366,11 +392,11 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         a.epi = EPI_CONVA; a.P = c->P[n];
         a.dstE = mkview(c->X[n][cur], nullptr, c->ctot[n], 0, 2 * c->ch[n]);
 #ifndef EIG_EMU
-        if (tc && n >= 2 && c->lw[n].tcA.ok) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcA, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvA: " + tc_last_error()); continue; }
+        if (tc && c->lw[n].tcA.ok) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcA, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvA: " + tc_last_error()); continue; }
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }
-    for (int n = 3; n >= 0; --n) {  // ConvLSTM_n
+    for (int n = 3; n >= 1; --n) {  // ConvLSTM_n
         ConvArgs a;
         memset(&a, 0, sizeof a);
         a.in_hi = c->X[n][cur]; a.in_lo = nullptr;
@@ -380,13 +406,23 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         a.epi = EPI_LSTM; a.cstate = c->cst[n]; a.peep = c->lw[n].peep;
         const int hoff = 2 * c->ch[n] + (n < 3 ? c->ch[n + 1] : 0);
         a.dstH = mkview(c->X[n][nxt], nullptr, c->ctot[n], hoff, c->ch[n]);
-        if (n >= 1) a.dstUp = mkview(c->X[n - 1][cur], nullptr, c->ctot[n - 1], 2 * c->ch[n - 1], c->ch[n]);
+        // R_n up-sampled x2 into the concat buffer of layer n-1 (layer 0 reads R_1 at half resolution instead)
+        if (n >= 2) a.dstUp = mkview(c->X[n - 1][cur], nullptr, c->ctot[n - 1], 2 * c->ch[n - 1], c->ch[n]);
 #ifndef EIG_EMU
-        if (tc && n >= 1 && c->lw[n].tcL.ok) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); continue; }
+        if (tc && c->lw[n].tcL.ok) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); continue; }
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }
-    for (int n = 0; n < 4; ++n) {  // ConvP_n: R_n -> P_n
+    {   // ConvLSTM_0 on [E0 | up(R1) | h0], then ConvP_0 -> P0 (this step's prediction)
+        if (c->ch[0] == 1) { auto k = l0_lstm_kernel<4>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(64), 0, s, l0); }
+        else { auto k = l0_lstm_kernel<12>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(64), 0, s, l0); }
+        CKL();
+        const long long npix = (long long)B * c->h * c->w;
+        if (c->ch[0] == 1) { auto k = l0_convp_kernel<1>; LAUNCH_K(CLS_L0, k, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, l0); }
+        else { auto k = l0_convp_kernel<3>; LAUNCH_K(CLS_L0, k, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, l0); }
+        CKL();
+    }
+    for (int n = 1; n < 4; ++n) {  // ConvP_n: R_n -> P_n
         ConvArgs a;
         memset(&a, 0, sizeof a);
         const int hoff = 2 * c->ch[n] + (n < 3 ? c->ch[n + 1] : 0);
@@ -394,9 +430,9 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         a.in_pitch = c->ctot[n]; a.in_coff = hoff; a.Cin = c->ch[n];
         a.B = B; a.H = c->H[n]; a.W = c->W[n];
         a.wgt = c->lw[n].convP; a.bias = c->lw[n].convP_b; a.N = c->ch[n]; a.Npad = (c->ch[n] + 3) & ~3;
-        a.epi = EPI_CONVP; a.outP = c->P[n]; a.clip = n == 0;
+        a.epi = EPI_CONVP; a.outP = c->P[n]; a.clip = 0;
 #ifndef EIG_EMU
-        if (tc && n >= 1 && c->lw[n].tcP.ok) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcP, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvP: " + tc_last_error()); continue; }
+        if (tc && c->lw[n].tcP.ok) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcP, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvP: " + tc_last_error()); continue; }
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }
@@ -407,7 +443,8 @@ static int prednet_reset(eig_ctx* c, int B, cudaStream_t s) {
     for (int n = 0; n < 4; ++n) {
         const size_t px = (size_t)B * c->H[n] * c->W[n];
         for (int k = 0; k < 2; ++k) {
-            CK(cudaMemsetAsync(c->X[n][k], 0, px * c->ctot[n] * sizeof(float), s));
+            if (n >= 1) CK(cudaMemsetAsync(c->X[n][k], 0, px * c->ctot[n] * sizeof(float), s));
+            else CK(cudaMemsetAsync(c->h0[k], 0, px * c->ch[0] * sizeof(float), s));
         }
         CK(cudaMemsetAsync(c->cst[n], 0, px * c->ch[n] * sizeof(float), s));
         CK(cudaMemsetAsync(c->P[n], 0, px * c->ch[n] * sizeof(float), s));

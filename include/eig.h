@@ -99,8 +99,8 @@ int eig_debug_buffers(eig_ctx* ctx, uint8_t** d_img, uint8_t** d_frames, float**
 int eig_memcpy_d2h(void* h_dst, const void* d_src, int64_t bytes);
 
 /* Per-kernel-class device timing for bench.py's roofline pass: between begin and end every kernel launch is
- * bracketed by CUDA events on its stream.  Classes: 0 render, 1 conv SIMT, 2 conv tcgen05, 3 element-wise,
- * 4 flow, 5 score (arrays of 8).  eig_profile_end synchronises the device. */
+ * bracketed by CUDA events on its stream.  Classes: 0 render, 1 conv SIMT (layers 1-3), 2 conv tcgen05, 3 element-wise,
+ * 4 flow, 5 score, 6 fused layer-0 kernels (arrays of 8).  eig_profile_end synchronises the device. */
 int eig_profile_begin(eig_ctx* ctx);
 int eig_profile_end(eig_ctx* ctx, double* ms_per_class, int64_t* launches_per_class);
 
