@@ -108,7 +108,7 @@ def oracle_evals_per_s(workload, n_sample, threads, flow_impl="cv2"):
     from oracle import pipeline as OPL
     preset, c_dim, ch, w, h, structure, _, _ = WORKLOADS[workload]
     torch.set_num_threads(threads)
-    wts = W.synthetic_weights(w, h, ch, seed=0)
+    wts = W.synthetic_predictor_weights(w, h, ch, seed=0)
     cfg, pop, _ = build_population(preset, c_dim, n_sample, 0)
     gc = cfg.genome_config
     t0 = time.perf_counter()
@@ -162,7 +162,7 @@ def run_ours(args):
     eng = E.Engine(w, h, ch, pop, device=local)
     eng.set_conv_mode(_lib.CONV_TC if args.conv == "tc" else _lib.CONV_SIMT)
     eng.set_grid(structure)
-    eng.load_weights(W.synthetic_weights(w, h, ch, seed=0))
+    eng.load_weights(W.synthetic_predictor_weights(w, h, ch, seed=0))
     _, _, progs = build_population(preset, c_dim, pop, rank * pop)
     blob, offsets, max_slots = G.pack_population(progs)
     resident = eng.upload_programs(progs)
@@ -270,7 +270,7 @@ def run_ours(args):
                 "config": {"workload": args.workload, "pop_per_gpu": pop, "global_pop": world * pop,
                            "resolution": "%dx%d" % (w, h), "channels": list(ch), "neat_config": preset,
                            "structure": "Circles", "prednet_steps": USEFUL_STEPS, "conv": args.conv,
-                           "weights": "synthetic LeCun-normal seed 0", "l2": "flushed between steps (256 MiB memset, untimed)",
+                           "weights": "synthetic_predictor_weights seed 0 (LeCun-normal, layer 0 shaped as an error integrator)", "l2": "flushed between steps (256 MiB memset, untimed)",
                            "parallelism": "genome-sharded dp%d + 1 all-gather/step" % world},
                 "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": int(blob.nbytes + offsets.nbytes),
                         "d2h_bytes_per_step": int(8 * pop), "ms_per_step": e2e_ms / args.steps},

@@ -63,6 +63,32 @@ def synthetic_weights(w, h, channels, seed=0, bias_std=0.0):
     return out
 
 
+def synthetic_predictor_weights(w, h, channels, seed=0, k=1.0, g=1.5, rand0=0.15, b_i=3.0, b_f=5.0, b_o=3.0):
+    """`synthetic_weights` re-shaped so that the random network behaves like a trained predictor (P0 tracks the
+    input, tiny frame-to-frame flow of 0.01-0.05 px, as the published weights give): plain LeCun-normal
+    weights make P0 unrelated to the frame, every flow vector exceeds the plausibility limits of
+    generate_illusion.py:569-597 and every genome scores 0, which would make fitness parity vacuous.
+    Layer 0 becomes an error integrator: the random layer-0 convolutions are scaled by `rand0`, the cell
+    candidate gets +k / -k centre taps on E0 = [relu(x-P0), relu(P0-x)], the gates are biased open (input,
+    output) and to remember (forget), and ConvP0 gets an identity centre tap of gain g.  Layers 1-3 keep the
+    plain initialisation; they modulate layer 0 through the x_*1 convolutions.  Same shapes, same arithmetic
+    cost as any other weight file."""
+    wt = synthetic_weights(w, h, channels, seed=seed)
+    c0 = channels[0]
+    pre = PREFIX + "ConvLSTM0/"
+    for name in wt:
+        if (name.startswith(pre) or name.startswith(PREFIX + "ConvP0/")) and name.endswith("/W") and "/c_" not in name:
+            wt[name] *= np.float32(rand0)
+    for r in range(c0):
+        wt[pre + "x_c0/W"][r, r, 1, 1] += k
+        wt[pre + "x_c0/W"][r, c0 + r, 1, 1] -= k
+        wt[PREFIX + "ConvP0/W"][r, r, 1, 1] += g
+    wt[pre + "h_i/b"][:] = b_i
+    wt[pre + "h_f/b"][:] = b_f
+    wt[pre + "h_o/b"][:] = b_o
+    return wt
+
+
 def save_npz(path, weights):
     np.savez(path, **weights)
 

@@ -138,9 +138,38 @@ def make_flow_and_pipeline():
     print("pipeline.npz, flow_cv2.npz written")
 
 
+def make_pipeline_predictor():
+    """Same as the pipeline cases above but with `synthetic_predictor_weights` (P0 tracks the frame, flow of a
+    few hundredths of a pixel, non-zero fitness for most genomes): oracle only, /root/reference not needed."""
+    import torch
+    torch.set_num_threads(8)
+    out, meta = {}, []
+    cases = [("c2p", "circles_bw", 1, (1, 16, 32, 64), 160, 120, 1, 0, 12),
+             ("c3p", "circles", 3, (3, 48, 96, 192), 160, 120, 1, 0, 6),
+             ("c1p", "circles_bw", 1, (1, 16, 32, 64), 64, 64, 1, 1, 3)]
+    for name, preset, c_dim, ch, w, h, structure, pair, n in cases:
+        wts = W.synthetic_predictor_weights(w, h, ch, seed=0)
+        cfg = G.make_config(2, G.NEAT_PRESETS[preset]["num_outputs"])
+        pop = [G.synthetic_genome(preset, i) for i in range(n)]
+        fit, ex = OPL.evaluate_population(pop, cfg.genome_config.input_keys, cfg.genome_config.output_keys, structure,
+                                          wts, w, h, ch, c_dim, pair_mode=pair, keep=True)
+        out["fitness_" + name] = fit
+        out["nvec_" + name] = np.array([len(e["vectors"]) for e in ex])
+        out["frames_" + name] = np.stack([np.stack(e["frames"]) for e in ex])
+        meta.append(dict(name=name, preset=preset, c_dim=c_dim, channels=ch, w=w, h=h, structure=structure, pair=pair, n=n,
+                         weights="predictor"))
+        print(name, "fitness", np.round(fit, 5), "nvec", out["nvec_" + name])
+    out["meta"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(HERE, "pipeline_predictor.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "predictor":
+        make_pipeline_predictor()
+        sys.exit(0)
     ns = ref_harness.load()
     make_render(ns)
     make_scoring(ns)
     make_cppn_cases()
     make_flow_and_pipeline()
+    make_pipeline_predictor()

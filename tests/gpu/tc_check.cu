@@ -178,10 +178,11 @@ static bool check_epilogues(Problem& p, int mode) {
     return ok;
 }
 
-// timing mode: `tc_check time` runs the PredNet layer shapes at population 32 with the per-role cycle counters on
+static int g_time_kb = 16;
+// timing mode: `tc_check time [kb]` runs the PredNet layer shapes at population 32 with the per-role cycle counters on
 static void time_shape(const char* name, int B, int H, int W, int pitch, int coff, int Cin, int N, int epi, int cluster, int max_nt) {
     tc_set_max_cluster(cluster); tc_set_max_nt(max_nt);
-    Problem p; make_problem(p, B, H, W, pitch, coff, Cin, N, 5, 16);
+    Problem p; make_problem(p, B, H, W, pitch, coff, Cin, N, 5, g_time_kb);
     const size_t px = (size_t)B * H * W;
     ConvArgs a = base_args(p);
     a.epi = epi;
@@ -243,7 +244,7 @@ static int timing_main() {
 
 int main(int argc, char** argv) {
     if (!tc_available()) { printf("tensor-core path unavailable: %s\n", tc_unavailable_reason().c_str()); return 4; }
-    if (argc > 1 && !strcmp(argv[1], "time")) return timing_main();
+    if (argc > 1 && !strcmp(argv[1], "time")) { if (argc > 2) g_time_kb = atoi(argv[2]) == 32 ? 32 : 16; return timing_main(); }
     const int want_kb = argc > 1 ? atoi(argv[1]) : 16;
     struct Shape { int B, H, W, pitch, coff, Cin, N; };
     const Shape shapes[] = {

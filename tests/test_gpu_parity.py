@@ -25,6 +25,21 @@ def _programs(preset, c, idx, evolved=False):
     return cfg, pop, [G.flatten_genome(g, cfg, n_outputs=c if c > 1 else 1) for g in pop]
 
 
+def _pipeline_cases():
+    """(npz, meta) of every whole-path golden case: plain LeCun weights and predictor-structured weights."""
+    for fn in ("pipeline.npz", "pipeline_predictor.npz"):
+        z = np.load(os.path.join(GOLDEN, fn))
+        for m in json.loads(str(z["meta"])):
+            yield z, m
+
+
+def _weights_for(m):
+    w, h, ch = m["w"], m["h"], tuple(m["channels"])
+    if m.get("weights") == "predictor":
+        return W.synthetic_predictor_weights(w, h, ch, seed=0)
+    return W.synthetic_weights(w, h, ch, seed=0)
+
+
 def test_loaded_library_is_the_in_tree_cuda_build(gpu_engine_factory):
     eng = gpu_engine_factory(64, 64, (1, 4, 8, 8), 2)
     assert eng.lib.path.endswith("evolutionary_illusion_generator_b200/libeig.so")
@@ -87,10 +102,10 @@ def test_cppn_known_answers_on_gpu(gpu_engine_factory):
 
 @pytest.mark.parametrize("mode", ["simt", "tc"])
 def test_prednet_frames_vs_oracle(gpu_engine_factory, mode):
-    z = np.load(os.path.join(GOLDEN, "pipeline.npz"))
-    metas = {m["name"]: m for m in json.loads(str(z["meta"]))}
-    for name in ("c2", "c3"):
-        m = metas[name]
+    for z, m in _pipeline_cases():
+        name = m["name"]
+        if name not in ("c2", "c3", "c2p", "c3p"):
+            continue
         c, w, h, ch = m["c_dim"], m["w"], m["h"], tuple(m["channels"])
         eng = gpu_engine_factory(w, h, ch, 8)
         if mode == "tc":
@@ -101,7 +116,7 @@ def test_prednet_frames_vs_oracle(gpu_engine_factory, mode):
         else:
             eng.set_conv_mode(_lib.CONV_SIMT)
         eng.set_grid(m["structure"])
-        eng.load_weights(W.synthetic_weights(w, h, ch, seed=0))
+        eng.load_weights(_weights_for(m))
         n = min(m["n"], 4)
         _, _, progs = _programs(m["preset"], c, list(range(n)))
         _, x = eng.render(progs)
@@ -169,11 +184,10 @@ def test_score_matches_reference_golden(gpu_engine_factory):
 
 @pytest.mark.parametrize("mode", ["simt", "tc"])
 def test_whole_path_fitness_vs_oracle_golden(gpu_engine_factory, mode):
-    z = np.load(os.path.join(GOLDEN, "pipeline.npz"))
     report = []
-    for m in json.loads(str(z["meta"])):
+    for z, m in _pipeline_cases():
         c, w, h, ch, n = m["c_dim"], m["w"], m["h"], tuple(m["channels"]), m["n"]
-        eng = gpu_engine_factory(w, h, ch, 8)
+        eng = gpu_engine_factory(w, h, ch, 16)
         if mode == "tc":
             try:
                 eng.set_conv_mode(_lib.CONV_TC)
@@ -182,7 +196,7 @@ def test_whole_path_fitness_vs_oracle_golden(gpu_engine_factory, mode):
         else:
             eng.set_conv_mode(_lib.CONV_SIMT)
         eng.set_grid(m["structure"])
-        eng.load_weights(W.synthetic_weights(w, h, ch, seed=0))
+        eng.load_weights(_weights_for(m))
         _, _, progs = _programs(m["preset"], c, list(range(n)))
         fit = eng.evaluate(progs, m["structure"], pair_mode=m["pair"])
         want = z["fitness_" + m["name"]]
