@@ -1,5 +1,6 @@
-// tcgen05 tensor-core 3x3 convolution for PredNet layers 1..3 (sm_100a): TMA-staged implicit GEMM, 3xTF32
-// split-precision MMAs accumulating in TMEM, the three PredNet epilogues fused behind tcgen05.ld.
+// tcgen05 tensor-core 3x3 convolution for PredNet layers 1..3 (sm_100a): TMA-staged implicit GEMM on CTA PAIRS
+// (cta_group::2, M = 256), split-precision fp16 MMAs (3 x kind::f16) accumulating in fp32 in TMEM, the three PredNet
+// epilogues fused behind tcgen05.ld.
 //
 // Reference semantics are those of conv_simt.cuh (Chainer `L.Convolution2D(cin, cout, 3, pad=1)` +
 // ConvLSTM / error-unit / pooling epilogues, /root/reference/chainer_prednet/PredNet/net.py:46-62,94-126,
@@ -7,17 +8,26 @@
 //
 // GEMM view: D[m][n] = sum_{tap, c} A[m + shift(tap)][c] * Wt[tap][c][n]
 //   m   = "flat padded" pixel index inside a CTA region: m = h * P + w, P = TW + 2.  The CTA loads ONE halo box
-//         (KBT channels x P columns x NT*TH+2 rows) per channel block with a single 4-D TMA (negative / out of
+//         (32 channels x P columns x NT*TH+2 rows) per channel block with a single 4-D TMA (negative / out of
 //         range coordinates are zero-filled by the TMA unit = the conv's zero padding) and the nine taps are nine
 //         row-shifted views of that box: tap (ky,kx) of MMA tile t starts (t*TH + ky) * P + kx rows into the box.
 //         Rows with w >= TW are computed and dropped (2/P waste); the halo is fetched once instead of 9 times.
-//   K   = KBT channels per block (16 -> 64-byte swizzle rows, 32 -> 128-byte), UMMA_K = 8
-//   N   = output channels of this CTA (<= 256; the 4 gates of an LSTM cell are adjacent columns)
-// 3xTF32: activations live in HBM as plain fp32; the converter warps split each staged box into hi = tf32(v) and
-//   lo = v - hi in shared memory, weights are pre-split on the host; every k-step issues lo*hi + hi*lo + hi*hi into
-//   the same fp32 TMEM accumulator (the lo*lo term, 2^-22 relative, is dropped).
+//   K   = 32 channels per block = one 64-byte fp16 operand row (SWIZZLE_64B), UMMA_K = 16
+//   N   = output channels of this CTA pair (<= 256; the 4 gates of an LSTM cell are adjacent columns)
+// CTA pair: the two CTAs of a cluster compute two spatial regions against the same weight slice with ONE
+//   tcgen05.mma.cta_group::2 (M = 256: rows 0-127 from the leader's shared memory into the leader's TMEM, rows
+//   128-255 from the peer's); each CTA stages only HALF of every weight tile (N/2 rows), so a CTA reads
+//   (128 + N/2) operand rows per MMA instead of (128 + N) - measured on B200 the tensor pipe in SS mode is paced by
+//   those shared-memory operand reads (~64 B/clk), not by the math (profiles/r1).
+// Split precision ("3 x fp16"): activations live in HBM as plain fp32; the converter warps scale each staged box by
+//   2^4 and split it into hi = fp16(v) and lo = fp16(v - hi) (11 + 11 mantissa bits, the same coverage as a TF32
+//   split at twice the MMA rate and half the operand bytes), weights are pre-split on the host with a per-conv power of
+//   two scale; every k-step issues lo*hi + hi*lo + hi*hi into the same fp32 TMEM accumulator (the lo*lo term, 2^-22
+//   relative, is dropped) and the epilogue multiplies by the exact inverse scale.  |activation| must stay below 4094
+//   (fp16 range after scaling); PredNet activations are O(1).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <algorithm>
 #include <map>
 #include <string>
@@ -29,13 +39,14 @@
 namespace eig {
 
 enum { EPI_RAW = 3 };  // test only: out = acc + bias, no activation (conv3x3_tc_kernel only)
-enum { TC_THREADS = 512, TC_SMEM_LIMIT = 227 * 1024 };
+enum { TC_THREADS = 512, TC_SMEM_LIMIT = 227 * 1024, TC_KB = 32, TC_ROW = 64, TC_RAW_ROW = 128, TC_SR = 2 };
+#define TC_ACT_SCALE 16.0f
 
 struct TcWeights {
-    float* d = nullptr;  // [2 planes][9 taps][KBn][N][KBT] fp32 (hi plane, then lo plane)
-    int cin = 0, N = 0, KBT = 16, KBn = 0, Ncta = 0, gz = 1;
-    CUtensorMap map[3];  // weight-tile boxes of Ncta, Ncta/2, Ncta/4 rows (cluster size 1, 2, 4)
-    int max_csize = 1;
+    __half* d = nullptr;  // [2 planes][9 taps][KBn][Npad][32] fp16 (hi plane, then lo plane), scaled by wscale
+    int cin = 0, N = 0, Npad = 0, KBn = 0, Ncta = 0, gz = 1;
+    float wscale = 1.f;   // power of two
+    CUtensorMap map;      // weight-tile box: Ncta/2 rows (each CTA of the pair stages its half)
     bool ok = false;
 };
 
@@ -43,12 +54,13 @@ struct TcParams {
     int B, H, W;
     int TW, TH, P, NT;
     int tiles_x, tiles_y, regions;  // regions = spatial CTA regions (tiles_x * tiles_y * B)
-    int csize, groups_per_nz, groups;  // cluster size, groups (= csize regions sharing one weight slice) per N slice, total
+    int groups_per_nz, groups;      // group = 2 regions (one per CTA of the pair) x one weight slice
     int KBn, Ncta, N;
-    int a_plane_bytes, b_plane_bytes, a_box_bytes;
+    int a_plane_bytes, b_plane_bytes, raw_bytes, a_box_bytes;
     int SA, SB;
     int tmem_cols;
     int staging_bytes, stage_ld;  // ConvA pooling tile: 128 rows x stage_ld floats
+    float inv_scale;              // 1 / (activation scale * weight scale), exact power of two
     long long* dbg;               // optional [grid][16] cycle counters per role (tests/gpu/tc_check timing mode), else null
     ConvArgs ca;
 };
@@ -62,11 +74,12 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// cluster-scope acquire: some of the arrivals come from the peer CTA of the pair
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
@@ -78,6 +91,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
         if (it > (1u << 24)) __trap();
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
     asm volatile(
@@ -85,24 +110,17 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+// pair load: the bytes land in THIS CTA's shared memory, the transaction count is credited to `cluster_bar`, which may
+// live in the leader CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"((unsigned long long)map), "r"(cluster_bar), "r"(c0), "r"(c1)
         : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 // one elected lane of a converged warp; the surrounding code stays warp-uniform so that descriptors, barrier
 // addresses and loop counters live in uniform registers (an `if (lane == 0)` around the issue loop makes ptxas wrap
-// every tcgen05.mma in an R2UR "waterfall" of ~85 cycles - measured, see profiles/)
+// every tcgen05.mma in an R2UR "waterfall" of ~85 cycles - measured)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -118,16 +136,17 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// completion of all MMAs issued so far -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
@@ -152,78 +171,60 @@ __device__ __forceinline__ float lstm_cell_v(float gi, float gf, float gc, float
 
 __device__ __forceinline__ void view_store4(const View& v, long long pix, int c, const float* val) {
     const long long idx = pix * v.pitch + v.coff + c;
-    if ((v.pitch | v.coff) & 3) {  // layer-0 concat buffer (pitch 2*C0 + R1 + C0): not 16-byte aligned
+    if ((v.pitch | v.coff) & 3) {  // not 16-byte aligned
 #pragma unroll
         for (int i = 0; i < 4; ++i) view_store(v, pix, c + i, val[i]);
         return;
     }
-    if (v.lo) {
-        float4 h, l;
-        h.x = tf32_round(val[0]); h.y = tf32_round(val[1]); h.z = tf32_round(val[2]); h.w = tf32_round(val[3]);
-        l.x = __fsub_rn(val[0], h.x); l.y = __fsub_rn(val[1], h.y); l.z = __fsub_rn(val[2], h.z); l.w = __fsub_rn(val[3], h.w);
-        *reinterpret_cast<float4*>(v.hi + idx) = h;
-        *reinterpret_cast<float4*>(v.lo + idx) = l;
-    } else {
-        *reinterpret_cast<float4*>(v.hi + idx) = make_float4(val[0], val[1], val[2], val[3]);
-    }
+    *reinterpret_cast<float4*>(v.hi + idx) = make_float4(val[0], val[1], val[2], val[3]);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int KBT> struct TcSwz;
-template <> struct TcSwz<32> { static constexpr uint64_t layout = 2, sbo = 1024; };  // SWIZZLE_128B
-template <> struct TcSwz<16> { static constexpr uint64_t layout = 4, sbo = 512; };   // SWIZZLE_64B
-
-// K-major swizzled shared-memory matrix descriptor (rows of KBT*4 bytes, 8-row atoms `sbo` bytes apart).  Measured on
+// K-major SWIZZLE_64B shared-memory matrix descriptor (rows of 64 bytes, 8-row atoms 512 bytes apart).  Measured on
 // B200 (tests/gpu/tc_check): the swizzle XOR is a function of the absolute smem address, so a start address shifted by
 // whole rows is legal with base offset 0 - that is what makes the nine taps nine views of one halo box.
-template <int KBT>
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(TcSwz<KBT>::sbo >> 4) << 32;  // stride byte offset: next 8-row group
-    d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
-    d |= TcSwz<KBT>::layout << 61;
+    d |= (uint64_t)1 << 16;               // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(512 >> 4) << 32;      // stride byte offset: next 8-row group
+    d |= (uint64_t)1 << 46;               // descriptor version (sm_100)
+    d |= (uint64_t)4 << 61;               // SWIZZLE_64B
     return d;
 }
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
-// Work decomposition: a *group* is `csize` spatially consecutive CTA regions that use the same weight slice n0; the
-// CTAs of one cluster walk the groups in lockstep (cluster k takes groups k, k + #clusters, ...), CTA rank r of the
-// cluster computes region r of the group, and every weight tile is fetched once per cluster (each CTA loads 1/csize
-// of it and multicasts).  A rank without a region (tail group) still loads its slice and releases the stages.
+// Work decomposition: a *group* is two spatially consecutive CTA regions that use the same weight slice n0; CTA pair k
+// takes groups k, k + #pairs, ...; CTA rank r of the pair computes region r of the group.  A rank without a region
+// (odd tail) recomputes rank 0's region with its stores disabled, so both CTAs always run the same pipeline.
 struct TcRegion { int x0, y0, b, n0; bool active; };
 __device__ __forceinline__ TcRegion tc_region(const TcParams& p, int group, int rank) {
     TcRegion r;
     const int nz = group / p.groups_per_nz;
-    const int sp = (group - nz * p.groups_per_nz) * p.csize + rank;
+    int sp = (group - nz * p.groups_per_nz) * 2 + rank;
     r.active = sp < p.regions;
+    if (!r.active) sp -= 1;
     const int tiles = p.tiles_x * p.tiles_y;
     const int tile = sp % tiles;
-    r.b = r.active ? sp / tiles : 0;
+    r.b = sp / tiles;
     r.n0 = nz * p.Ncta;
     r.x0 = (tile % p.tiles_x) * p.TW;
     r.y0 = (tile / p.tiles_x) * (p.NT * p.TH);
     return r;
 }
 
-// Persistent, warp-specialised: grid = min(regions, #SM) CTAs of 512 threads, each looping over CTA regions
-// (NT stacked MMA tiles of one genome x Ncta output channels).
-//   warps 0-3   converter: raw fp32 halo box (TMA) -> hi = tf32(v) in place, lo = v - hi in the second plane
-//   warp  4     weight producer (one thread): per-tap weight tiles, hi and lo planes (pre-split on the host)
-//   warp  5     MMA issuer (one thread) + TMEM allocator; accumulators double-buffered in TMEM
-//   warp  6     activation producer (one thread): one halo box per channel block, runs SA stages ahead
+// Persistent, warp-specialised: grid = 2 * min(groups, #SM / 2) CTAs of 512 threads in clusters of 2.
+//   warps 0-3   converter: raw fp32 halo box (TMA) -> hi / lo fp16 operand planes (SWIZZLE_64B layout written by hand)
+//   warp  4     weight producer (one thread): this CTA's half of every per-tap weight tile, hi and lo planes
+//   warp  5     TMEM allocator; in the leader CTA also the MMA issuer (one elected thread) for BOTH CTAs
+//   warp  6     activation producer (one thread): one raw halo box per channel block into a 2-deep ring
 //   warp  7     idle
 //   warps 8-15  epilogue (TMEM lane quarter = warp & 3, column half = (warp - 8) >> 2): drains accumulator set i
 //               while set i^1 is being computed
-template <int KBT>
+// Barriers: rawFull/rawEmpty (TMA <-> converter, CTA local), convA (converters of both CTAs -> leader's MMA warp),
+//   emptyA / emptyB / accFull (tcgen05.commit multicast to both CTAs), fullB (both CTAs' weight TMAs -> leader),
+//   accEmpty (epilogue warps of both CTAs -> leader).
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, const TcParams p) {
-    constexpr int RB = KBT * 4;       // bytes per operand row
-    constexpr int KSTEPS = KBT / 8;   // UMMA_K = 8 for tf32
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -231,63 +232,77 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     const uint32_t sbase = raw_addr + pad;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    const int crank = p.csize > 1 ? (int)cluster_rank() : 0;
-    const int cluster_id = blockIdx.x / p.csize, n_clusters = gridDim.x / p.csize;
-    const uint16_t cmask = (uint16_t)((1u << p.csize) - 1u);
+    const int crank = (int)cluster_rank();
+    const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     const int a_stage_bytes = 2 * p.a_plane_bytes, b_stage_bytes = 2 * p.b_plane_bytes;
-    const uint32_t sA = sbase, sB = sbase + p.SA * a_stage_bytes;
-    const uint32_t pipe_bytes = p.SA * a_stage_bytes + p.SB * b_stage_bytes;
+    const uint32_t off_raw = p.SA * a_stage_bytes, off_b = off_raw + TC_SR * p.raw_bytes;
+    const uint32_t sA = sbase, sRaw = sbase + off_raw, sB = sbase + off_b;
+    const uint32_t pipe_bytes = off_b + p.SB * b_stage_bytes;
     float* stage = reinterpret_cast<float*>(smem + pipe_bytes);
     const uint32_t sBar = sbase + pipe_bytes + p.staging_bytes;
-    // barriers: fullA[SA] convA[SA] emptyA[SA] fullB[SB] emptyB[SB] accFull[2] accEmpty[2]
-    const uint32_t fullA = sBar, convA = fullA + 8 * p.SA, emptyA = convA + 8 * p.SA;
+    // barriers: rawFull[SR] rawEmpty[SR] convA[SA] emptyA[SA] fullB[SB] emptyB[SB] accFull[2] accEmpty[2]
+    const uint32_t rawFull = sBar, rawEmpty = rawFull + 8 * TC_SR, convA = rawEmpty + 8 * TC_SR, emptyA = convA + 8 * p.SA;
     const uint32_t fullB = emptyA + 8 * p.SA, emptyB = fullB + 8 * p.SB;
     const uint32_t accFull = emptyB + 8 * p.SB, accEmpty = accFull + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pipe_bytes + p.staging_bytes + 8 * (3 * p.SA + 2 * p.SB + 4));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pipe_bytes + p.staging_bytes + 8 * (2 * TC_SR + 2 * p.SA + 2 * p.SB + 4));
 
     if (warp == 4 && lane == 0) {
-        for (int i = 0; i < p.SA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(convA + 8 * i, 4); mbar_init(emptyA + 8 * i, 1); }
-        for (int i = 0; i < p.SB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, p.csize); }
-        for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, 1); mbar_init(accEmpty + 8 * i, 8); }
+        for (int i = 0; i < TC_SR; ++i) { mbar_init(rawFull + 8 * i, 1); mbar_init(rawEmpty + 8 * i, 4); }
+        for (int i = 0; i < p.SA; ++i) { mbar_init(convA + 8 * i, 8); mbar_init(emptyA + 8 * i, 1); }
+        for (int i = 0; i < p.SB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, 1); mbar_init(accEmpty + 8 * i, 16); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
-    if (p.csize > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
+    cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / pair TMA / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int acc_stride = p.NT * p.Ncta;
 
     if (warp < 4) {
         // ===== converter =====
-        const int chunks = p.a_box_bytes >> 4;
+        const int chunks = p.a_box_bytes >> 4;   // float4 items of the raw box: 8 per pixel row
+        const uint32_t convA_leader = map_to_cta(convA, 0);
         int ia = 0;
         long long c_wait = 0, c0 = clock64(), cq;
-        for (int grp = cluster_id; grp < p.groups; grp += n_clusters) {
-            if (!tc_region(p, grp, crank).active) continue;
+        for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
             for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
-                const int s = ia % p.SA;
+                const int s = ia % p.SA, rs = ia % TC_SR;
                 cq = clock64();
-                mbar_wait(fullA + 8 * s, (ia / p.SA) & 1);
+                mbar_wait(rawFull + 8 * rs, (ia / TC_SR) & 1);
+                mbar_wait(emptyA + 8 * s, ((ia / p.SA) & 1) ^ 1);
                 c_wait += clock64() - cq;
-                float4* p0 = reinterpret_cast<float4*>(smem + s * a_stage_bytes);
-                float4* p1 = reinterpret_cast<float4*>(smem + s * a_stage_bytes + p.a_plane_bytes);
-#pragma unroll 2
+                const float4* src = reinterpret_cast<const float4*>(smem + off_raw + rs * p.raw_bytes);
+                unsigned char* hi = smem + s * a_stage_bytes;
+                unsigned char* lo = hi + p.a_plane_bytes;
+#pragma unroll 4
                 for (int i = threadIdx.x; i < chunks; i += 128) {
-                    const float4 v = p0[i];
-                    float4 h, l;
-                    h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
-                    l.x = __fsub_rn(v.x, h.x); l.y = __fsub_rn(v.y, h.y); l.z = __fsub_rn(v.z, h.z); l.w = __fsub_rn(v.w, h.w);
-                    p0[i] = h;
-                    p1[i] = l;
+                    const float4 v = src[i];
+                    const int row = i >> 3, q = i & 7;
+                    const int off = row * TC_ROW + ((((q >> 1) ^ ((row >> 1) & 3))) << 4) + ((q & 1) << 3);
+                    const float x0 = __fmul_rn(v.x, TC_ACT_SCALE), x1 = __fmul_rn(v.y, TC_ACT_SCALE);
+                    const float x2 = __fmul_rn(v.z, TC_ACT_SCALE), x3 = __fmul_rn(v.w, TC_ACT_SCALE);
+                    const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    const __half2 l01 = __floats2half2_rn(__fsub_rn(x0, f01.x), __fsub_rn(x1, f01.y));
+                    const __half2 l23 = __floats2half2_rn(__fsub_rn(x2, f23.x), __fsub_rn(x3, f23.y));
+                    uint2 uh, ul;
+                    uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
+                    ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
+                    *reinterpret_cast<uint2*>(hi + off) = uh;
+                    *reinterpret_cast<uint2*>(lo + off) = ul;
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("fence.proxy.async;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(convA + 8 * s);
+                if (lane == 0) {
+                    mbar_arrive(rawEmpty + 8 * rs);
+                    mbar_arrive_cluster(convA_leader + 8 * s);
+                }
             }
         }
         if (p.dbg && threadIdx.x == 0) {
@@ -295,45 +310,39 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
             d[7] = clock64() - c0; d[8] = c_wait;
         }
     } else if (warp == 6) {
-        // ===== activation (A) producer =====
+        // ===== activation (A) producer: raw fp32 halo boxes =====
         if (lane == 0) {
             int ia = 0;
-            for (int grp = cluster_id; grp < p.groups; grp += n_clusters) {
+            for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
                 const TcRegion r = tc_region(p, grp, crank);
-                if (!r.active) continue;
                 for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
-                    const int s = ia % p.SA;
-                    mbar_wait(emptyA + 8 * s, ((ia / p.SA) & 1) ^ 1);
-                    mbar_expect_tx(fullA + 8 * s, p.a_box_bytes);
-                    tma_load_4d(sA + s * a_stage_bytes, &mA, fullA + 8 * s, kb * KBT, r.x0 - 1, r.y0 - 1, r.b);
+                    const int rs = ia % TC_SR;
+                    mbar_wait(rawEmpty + 8 * rs, ((ia / TC_SR) & 1) ^ 1);
+                    mbar_expect_tx(rawFull + 8 * rs, p.a_box_bytes);
+                    tma_load_4d(sRaw + rs * p.raw_bytes, &mA, rawFull + 8 * rs, kb * TC_KB, r.x0 - 1, r.y0 - 1, r.b);
                 }
             }
         }
     } else if (warp == 4) {
-        // ===== weight (B) producer: this CTA's 1/csize slice of every tile, multicast to the whole cluster =====
+        // ===== weight (B) producer: this CTA's half (Ncta/2 rows) of every tile; the leader's barrier counts both =====
         if (lane == 0) {
             int ib = 0;
             long long b_wait = 0, b0 = clock64(), bq;
-            const int slice_rows = p.Ncta / p.csize;
-            const uint32_t slice_off = (uint32_t)(crank * slice_rows * RB);
-            for (int grp = cluster_id; grp < p.groups; grp += n_clusters) {
-                const int n0 = (grp / p.groups_per_nz) * p.Ncta + crank * slice_rows;
+            const int half_rows = p.Ncta >> 1;
+            const uint32_t fullB_leader = map_to_cta(fullB, 0);
+            for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
+                const int n0 = (grp / p.groups_per_nz) * p.Ncta + crank * half_rows;
                 for (int kb = 0; kb < p.KBn; ++kb) {
                     for (int tap = 0; tap < 9; ++tap, ++ib) {
                         const int s = ib % p.SB;
                         bq = clock64();
                         mbar_wait(emptyB + 8 * s, ((ib / p.SB) & 1) ^ 1);
                         b_wait += clock64() - bq;
-                        mbar_expect_tx(fullB + 8 * s, 2 * p.b_plane_bytes);
-                        const uint32_t dst = sB + s * b_stage_bytes + slice_off;
+                        if (crank == 0) mbar_expect_tx(fullB + 8 * s, 4 * p.b_plane_bytes);   // 2 planes x 2 CTAs
+                        const uint32_t dst = sB + s * b_stage_bytes;
                         const int row_hi = (tap * p.KBn + kb) * p.N + n0, row_lo = ((9 + tap) * p.KBn + kb) * p.N + n0;
-                        if (p.csize > 1) {
-                            tma_load_2d_mc(dst, &mB, fullB + 8 * s, 0, row_hi, cmask);
-                            tma_load_2d_mc(dst + p.b_plane_bytes, &mB, fullB + 8 * s, 0, row_lo, cmask);
-                        } else {
-                            tma_load_2d(dst, &mB, fullB + 8 * s, 0, row_hi);
-                            tma_load_2d(dst + p.b_plane_bytes, &mB, fullB + 8 * s, 0, row_lo);
-                        }
+                        tma_load_2d_pair(dst, &mB, fullB_leader + 8 * s, 0, row_hi);
+                        tma_load_2d_pair(dst + p.b_plane_bytes, &mB, fullB_leader + 8 * s, 0, row_lo);
                     }
                 }
             }
@@ -343,73 +352,65 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
             }
         }
     } else if (warp == 5) {
-        // ===== MMA issuer: the warp walks the loops together, one elected lane issues =====
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Ncta >> 3) << 17) | ((128u >> 4) << 24);
-        // descriptor = {hi word: constant, lo word: (address >> 4) | LBO}; offsets are plain adds on the lo word
-        const uint64_t desc_hi = tc_smem_desc<KBT>(0) & 0xffffffff00000000ull;
-        const uint32_t lo_flag = 1u << 16;
-        const uint32_t plane_a16 = (uint32_t)p.a_plane_bytes >> 4, plane_b16 = (uint32_t)p.b_plane_bytes >> 4;
-        const uint32_t tile16 = (uint32_t)(p.TH * p.P * RB) >> 4;
-        int ia = 0, ib = 0, it = 0;
-        long long t_acc = 0, t_a = 0, t_b = 0, t0 = clock64(), tq;
-        for (int grp = cluster_id; grp < p.groups; grp += n_clusters) {
-            if (!tc_region(p, grp, crank).active) {
-                // no region for this rank in the tail group: keep the weight ring moving for the cluster
-                for (int k = 0; k < 9 * p.KBn; ++k, ++ib) {
-                    const int sb = ib % p.SB;
-                    mbar_wait(fullB + 8 * sb, (ib / p.SB) & 1);
-                    if (elect_one()) tc_commit_mc(emptyB + 8 * sb, cmask);
-                    __syncwarp();
-                }
-                continue;
-            }
-            const int set = it & 1;
-            tq = clock64();
-            mbar_wait(accEmpty + 8 * set, ((it >> 1) & 1) ^ 1);
-            t_acc += clock64() - tq;
-            tc_fence_after();
-            const uint32_t d0 = tmem_base + (uint32_t)(set * acc_stride);
-            for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
-                const int sa = ia % p.SA;
+        if (crank == 0) {
+            // ===== MMA issuer (leader CTA): the warp walks the loops together, one elected lane issues =====
+            // kind::f16: D fp32, A/B fp16 K-major, N = Ncta, M = 256 over the pair
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Ncta >> 3) << 17) | ((256u >> 4) << 24);
+            // descriptor = {hi word: constant, lo word: (address >> 4) | LBO}; offsets are plain adds on the lo word
+            const uint64_t desc_hi = tc_smem_desc(0) & 0xffffffff00000000ull;
+            const uint32_t lo_flag = 1u << 16;
+            const uint32_t plane_a16 = (uint32_t)p.a_plane_bytes >> 4, plane_b16 = (uint32_t)p.b_plane_bytes >> 4;
+            const uint32_t tile16 = (uint32_t)(p.TH * p.P * TC_ROW) >> 4;
+            int ia = 0, ib = 0, it = 0;
+            long long t_acc = 0, t_a = 0, t_b = 0, t0 = clock64(), tq;
+            for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
+                const int set = it & 1;
                 tq = clock64();
-                mbar_wait(convA + 8 * sa, (ia / p.SA) & 1);
-                t_a += clock64() - tq;
-                const uint32_t a16 = (((sA + sa * a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
-                for (int tap = 0; tap < 9; ++tap, ++ib) {
-                    const int sb = ib % p.SB;
+                mbar_wait(accEmpty + 8 * set, ((it >> 1) & 1) ^ 1);
+                t_acc += clock64() - tq;
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)(set * acc_stride);
+                for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
+                    const int sa = ia % p.SA;
                     tq = clock64();
-                    mbar_wait(fullB + 8 * sb, (ib / p.SB) & 1);
-                    t_b += clock64() - tq;
-                    tc_fence_after();
-                    const uint32_t tap16 = (uint32_t)(((tap / 3) * p.P + (tap % 3)) * RB) >> 4;
-                    const uint32_t b16 = (((sB + sb * b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
-                    const uint32_t acc0 = (kb | tap) ? 1u : 0u;
-                    if (elect_one()) {
-                        for (int t = 0; t < p.NT; ++t) {
-                            const uint32_t at16 = a16 + tap16 + (uint32_t)t * tile16;
-                            const uint32_t d = d0 + (uint32_t)(t * p.Ncta);
+                    mbar_wait(convA + 8 * sa, (ia / p.SA) & 1);
+                    t_a += clock64() - tq;
+                    const uint32_t a16 = (((sA + sa * a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
+                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                        const int sb = ib % p.SB;
+                        tq = clock64();
+                        mbar_wait(fullB + 8 * sb, (ib / p.SB) & 1);
+                        t_b += clock64() - tq;
+                        tc_fence_after();
+                        const uint32_t tap16 = (uint32_t)(((tap / 3) * p.P + (tap % 3)) * TC_ROW) >> 4;
+                        const uint32_t b16 = (((sB + sb * b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
+                        const uint32_t acc0 = (kb | tap) ? 1u : 0u;
+                        if (elect_one()) {
+                            for (int t = 0; t < p.NT; ++t) {
+                                const uint32_t at16 = a16 + tap16 + (uint32_t)t * tile16;
+                                const uint32_t d = d0 + (uint32_t)(t * p.Ncta);
 #pragma unroll
-                            for (int ks = 0; ks < KSTEPS; ++ks) {
-                                const uint64_t dah = desc_hi | (at16 + 2 * ks), dal = desc_hi | (at16 + plane_a16 + 2 * ks);
-                                const uint64_t dbh = desc_hi | (b16 + 2 * ks), dbl = desc_hi | (b16 + plane_b16 + 2 * ks);
-                                tc_mma_tf32(d, dal, dbh, idesc, ks ? 1u : acc0);
-                                tc_mma_tf32(d, dah, dbl, idesc, 1u);
-                                tc_mma_tf32(d, dah, dbh, idesc, 1u);
+                                for (int ks = 0; ks < 2; ++ks) {   // 2 x UMMA_K(16) = 32 channels
+                                    const uint64_t dah = desc_hi | (at16 + 2 * ks), dal = desc_hi | (at16 + plane_a16 + 2 * ks);
+                                    const uint64_t dbh = desc_hi | (b16 + 2 * ks), dbl = desc_hi | (b16 + plane_b16 + 2 * ks);
+                                    tc_mma_f16_pair(d, dal, dbh, idesc, ks ? 1u : acc0);
+                                    tc_mma_f16_pair(d, dah, dbl, idesc, 1u);
+                                    tc_mma_f16_pair(d, dah, dbh, idesc, 1u);
+                                }
                             }
+                            tc_commit_pair(emptyB + 8 * sb);
+                            if (tap == 8) tc_commit_pair(emptyA + 8 * sa);
+                            if (tap == 8 && kb == p.KBn - 1) tc_commit_pair(accFull + 8 * set);
                         }
-                        if (p.csize > 1) tc_commit_mc(emptyB + 8 * sb, cmask);
-                        else tc_commit(emptyB + 8 * sb);
-                        if (tap == 8) tc_commit(emptyA + 8 * sa);
-                        if (tap == 8 && kb == p.KBn - 1) tc_commit(accFull + 8 * set);
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
+                ++it;
             }
-            ++it;
-        }
-        if (p.dbg && lane == 0) {
-            long long* d = p.dbg + (long long)blockIdx.x * 16;
-            d[0] = clock64() - t0; d[1] = t_acc; d[2] = t_a; d[3] = t_b; d[4] = it;
+            if (p.dbg && lane == 0) {
+                long long* d = p.dbg + (long long)blockIdx.x * 16;
+                d[0] = clock64() - t0; d[1] = t_acc; d[2] = t_a; d[3] = t_b; d[4] = it;
+            }
         }
     } else if (warp >= 8) {
         // ===== epilogue warps 8..15 =====
@@ -418,18 +419,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
         const int m = q4 * 32 + lane;
         const int etid = (warp - 8) * 32 + lane;
         const int hh = m / p.P, ww = m - hh * p.P;
+        const uint32_t accEmpty_leader = map_to_cta(accEmpty, 0);
+        const float inv = p.inv_scale;
         int it = 0;
         long long e_wait = 0, e0 = clock64(), eq;
-        for (int grp = cluster_id; grp < p.groups; grp += n_clusters) {
+        for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
             const TcRegion r = tc_region(p, grp, crank);
-            if (!r.active) continue;
             const int set = it & 1, b = r.b, n0 = r.n0;
             eq = clock64();
             mbar_wait(accFull + 8 * set, (it >> 1) & 1);
             e_wait += clock64() - eq;
             tc_fence_after();
             const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(set * acc_stride);
-            for (int t = 0; t < p.NT; ++t) {
+            const int ncols = min(p.Ncta, a.N - n0);   // the last slice may be padded up to a multiple of 32
+            for (int t = 0; r.active && t < p.NT; ++t) {
                 const int y = r.y0 + t * p.TH + hh, x = r.x0 + ww;
                 const bool valid = hh < p.TH && ww < p.TW && y < p.H && x < p.W;
                 const long long pix = valid ? ((long long)b * p.H + y) * p.W + x : 0;
@@ -440,13 +443,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                     // software pipeline: the state / peephole loads of chunk c+32 are in flight while chunk c is computed
                     float4 cold, pq[4];
                     int c0 = half * 16;
-                    if (c0 < p.Ncta) {
+                    if (c0 < ncols) {
                         const int r0 = (n0 + c0) >> 2;
                         cold = *reinterpret_cast<const float4*>(a.cstate + pix * R + r0);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) pq[q] = *reinterpret_cast<const float4*>(a.peep + (ppix * R + r0 + q) * 4);
                     }
-                    for (; c0 < p.Ncta; c0 += 32) {
+                    for (; c0 < ncols; c0 += 32) {
                         float v[16];
                         tmem_ld16(tcol + c0, v);
                         const int r0 = (n0 + c0) >> 2;
@@ -454,7 +457,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                         float4 pcur[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) pcur[q] = pq[q];
-                        if (c0 + 32 < p.Ncta) {
+                        if (c0 + 32 < ncols) {
                             const int r1 = (n0 + c0 + 32) >> 2;
                             cold = *reinterpret_cast<const float4*>(a.cstate + pix * R + r1);
 #pragma unroll
@@ -466,7 +469,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float4 bq = *reinterpret_cast<const float4*>(a.bias + n0 + c0 + q * 4);
-                            hn[q] = lstm_cell_v(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3], bq, pcur[q], co[q], &cn[q]);
+                            hn[q] = lstm_cell_v(__fmul_rn(v[q * 4], inv), __fmul_rn(v[q * 4 + 1], inv), __fmul_rn(v[q * 4 + 2], inv),
+                                                __fmul_rn(v[q * 4 + 3], inv), bq, pcur[q], co[q], &cn[q]);
                         }
                         *reinterpret_cast<float4*>(a.cstate + pix * R + r0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
                         view_store4(a.dstH, pix, r0, hn);
@@ -480,15 +484,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                         }
                     }
                 } else if (a.epi == EPI_CONVP || a.epi == EPI_RAW) {
-                    for (int c0 = half * 16; c0 < p.Ncta; c0 += 32) {
+                    for (int c0 = half * 16; c0 < ncols; c0 += 32) {
                         float v[16];
                         tmem_ld16(tcol + c0, v);
                         if (!valid) continue;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float4 bq = *reinterpret_cast<const float4*>(a.bias + n0 + c0 + q * 4);
-                            float o[4] = {__fadd_rn(v[q * 4], bq.x), __fadd_rn(v[q * 4 + 1], bq.y), __fadd_rn(v[q * 4 + 2], bq.z),
-                                          __fadd_rn(v[q * 4 + 3], bq.w)};
+                            float o[4] = {__fadd_rn(__fmul_rn(v[q * 4], inv), bq.x), __fadd_rn(__fmul_rn(v[q * 4 + 1], inv), bq.y),
+                                          __fadd_rn(__fmul_rn(v[q * 4 + 2], inv), bq.z), __fadd_rn(__fmul_rn(v[q * 4 + 3], inv), bq.w)};
                             if (a.epi == EPI_CONVP) {
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
@@ -500,18 +504,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                         }
                     }
                 } else {  // EPI_CONVA: relu -> staging tile -> 2x2 max-pool -> error units at half resolution
-                    for (int c0 = half * 16; c0 < p.Ncta; c0 += 32) {
+                    for (int c0 = half * 16; c0 < ncols; c0 += 32) {
                         float v[16];
                         tmem_ld16(tcol + c0, v);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float o = __fadd_rn(v[i], a.bias[n0 + c0 + i]);
+                            const float o = __fadd_rn(__fmul_rn(v[i], inv), a.bias[n0 + c0 + i]);
                             stage[m * p.stage_ld + c0 + i] = o > 0.f ? o : 0.f;
                         }
                     }
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                     const int Hp = p.H >> 1, Wp = p.W >> 1, tw2 = p.TW >> 1, th2 = p.TH >> 1;
-                    const int items = th2 * tw2 * p.Ncta;
+                    const int items = th2 * tw2 * ncols;
                     for (int base = 0; base < items; base += 4 * 256) {
                         float mx[4], pv[4];
                         long long ppos[4];
@@ -521,7 +525,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                         for (int u = 0; u < 4; ++u) {   // loads first: four independent global reads in flight
                             const int idx = base + u * 256 + etid;
                             okk[u] = idx < items;
-                            const int n = idx % p.Ncta, pp = idx / p.Ncta;
+                            const int n = idx % ncols, pp = idx / ncols;
                             const int ph = pp / tw2, pw = pp - ph * tw2;
                             const int py = ((r.y0 + t * p.TH) >> 1) + ph, px = (r.x0 >> 1) + pw;
                             okk[u] = okk[u] && py < Hp && px < Wp;
@@ -545,7 +549,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(accEmpty + 8 * set);
+            if (lane == 0) mbar_arrive_cluster(accEmpty_leader + 8 * set);
             ++it;
         }
         if (p.dbg && warp == 8 && lane == 0) {
@@ -555,10 +559,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
-    if (p.csize > 1) cluster_sync_all();   // nobody exits while a peer may still multicast into / arrive on this CTA
+    cluster_sync_all();   // nobody exits while the peer may still read this CTA's operands / arrive on its barriers
     if (warp == 5) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
 }
 
@@ -571,14 +575,11 @@ struct TcState {
     EigEncodeTiledFn encode = nullptr;
     bool probed = false, available = false;
     std::string reason, last_error;
-    int kbt = 16;      // channels per K block (EIG_TC_KB = 16 | 32)
     int force_nt = 0;  // EIG_TC_NT: cap on MMA tiles per CTA region
     long long* dbg = nullptr;  // device buffer for the per-role cycle counters (tests only)
-    int last_grid = 0, last_csize = 0, last_nt = 0, last_sa = 0, last_sb = 0;
-    int max_cluster = 4;  // EIG_TC_CLUSTER: cap on the multicast cluster size (1, 2 or 4)
-    std::map<std::tuple<int, int, size_t>, int> max_clusters;  // (KBT, csize, smem) -> co-resident clusters
-    int n_sm = 148;
-    std::map<std::tuple<const void*, int, int, int, int, int, int, int, int>, CUtensorMap> amaps;
+    int last_grid = 0, last_csize = 2, last_nt = 0, last_sa = 0, last_sb = 0;
+    int n_sm = 148, max_pairs = 0;
+    std::map<std::tuple<const void*, int, int, int, int, int, int, int>, CUtensorMap> amaps;
 };
 inline TcState& tc_state() { static TcState s; return s; }
 
@@ -598,33 +599,20 @@ inline bool tc_available() {
         return false;
     }
     s.encode = (EigEncodeTiledFn)fn;
-    if (cudaFuncSetAttribute(conv3x3_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess ||
-        cudaFuncSetAttribute(conv3x3_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
         s.reason = "cannot raise the dynamic shared memory limit";
         cudaGetLastError();
         return false;
     }
-    if (const char* e = getenv("EIG_TC_KB")) s.kbt = atoi(e) == 32 ? 32 : 16;
     if (const char* e = getenv("EIG_TC_NT")) s.force_nt = atoi(e);
-    if (const char* e = getenv("EIG_TC_CLUSTER")) s.max_cluster = atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1);
     s.available = true;
     return true;
 }
 inline std::string tc_unavailable_reason() { return tc_state().reason; }
 inline std::string tc_last_error() { return tc_state().last_error; }
-inline void tc_set_kb(int kbt) { tc_state().kbt = kbt == 32 ? 32 : 16; }
+inline void tc_set_kb(int) {}           // kept for tests/gpu/tc_check: the K block is fixed at 32 channels now
 inline void tc_set_max_nt(int nt) { tc_state().force_nt = nt; }
-inline void tc_set_max_cluster(int c) { tc_state().max_cluster = c >= 4 ? 4 : (c >= 2 ? 2 : 1); }
-
-inline float tc_host_tf32(float v) {
-    uint32_t u;
-    memcpy(&u, &v, 4);
-    if ((u & 0x7f800000u) == 0x7f800000u) return v;
-    u = (u + 0x1000u) & ~0x1fffu;  // round to nearest, ties away (cvt.rna.tf32.f32)
-    float r;
-    memcpy(&r, &u, 4);
-    return r;
-}
+inline void tc_set_max_cluster(int) {}  // the cluster is always the CTA pair
 
 inline void tc_free(TcWeights& w) {
     if (w.d) cudaFree(w.d);
@@ -632,55 +620,58 @@ inline void tc_free(TcWeights& w) {
     w.ok = false;
 }
 
-// wv: [9][cin][npad] fp32 (the SIMT layout), N valid columns; max_ncta caps the output channels of one CTA
+inline int tc_round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// wv: [9][cin][npad] fp32 (the SIMT layout), N valid columns; max_ncta caps the output channels of one CTA pair
 inline int tc_pack(TcWeights& w, const float* wv, int cin, int N, int npad, int max_ncta = 256) {
     if (!tc_available()) return 0;  // no tensor-core path on this device: nothing to pack
     TcState& s = tc_state();
     tc_free(w);
     if (N % 16 || cin % 4) return 0;  // not a tensor-core shape: w.ok stays false, the caller keeps the SIMT kernel
-    const int KBT = s.kbt;
-    w.cin = cin; w.N = N; w.KBT = KBT; w.KBn = (cin + KBT - 1) / KBT;
-    w.gz = (N + max_ncta - 1) / max_ncta;
-    while (N % w.gz || (N / w.gz) % 16) ++w.gz;
-    w.Ncta = N / w.gz;
-    const size_t plane = (size_t)9 * w.KBn * N * KBT;
-    std::vector<float> pk(2 * plane, 0.f);
+    w.cin = cin; w.N = N; w.KBn = (cin + TC_KB - 1) / TC_KB;
+    w.Npad = tc_round_up(N, 32);      // each CTA of the pair stages Ncta/2 rows, a multiple of 16
+    w.gz = (w.Npad + max_ncta - 1) / max_ncta;
+    while (w.Npad % w.gz || (w.Npad / w.gz) % 32) ++w.gz;
+    w.Ncta = w.Npad / w.gz;
+    float amax = 0.f;
+    for (int tap = 0; tap < 9; ++tap)
+        for (int c = 0; c < cin; ++c)
+            for (int n = 0; n < N; ++n) amax = std::max(amax, fabsf(wv[((size_t)tap * cin + c) * npad + n]));
+    int e = 0;
+    if (amax > 0.f && std::isfinite(amax)) { frexpf(amax, &e); e = 12 - e; }   // amax * 2^e in [2^11, 2^12)
+    e = std::max(-24, std::min(24, e));
+    w.wscale = ldexpf(1.f, e);
+    const size_t plane = (size_t)9 * w.KBn * w.Npad * TC_KB;
+    std::vector<__half> pk(2 * plane, __float2half(0.f));
     for (int tap = 0; tap < 9; ++tap)
         for (int c = 0; c < cin; ++c)
             for (int n = 0; n < N; ++n) {
-                const float v = wv[((size_t)tap * cin + c) * npad + n];
-                const float hi = tc_host_tf32(v);
-                const size_t o = (((size_t)tap * w.KBn + c / KBT) * N + n) * KBT + c % KBT;
+                const float v = wv[((size_t)tap * cin + c) * npad + n] * w.wscale;
+                const __half hi = __float2half_rn(v);
+                const __half lo = __float2half_rn(v - __half2float(hi));
+                const size_t o = (((size_t)tap * w.KBn + c / TC_KB) * w.Npad + n) * TC_KB + c % TC_KB;
                 pk[o] = hi;
-                pk[plane + o] = v - hi;
+                pk[plane + o] = lo;
             }
-    if (cudaMalloc((void**)&w.d, pk.size() * sizeof(float)) != cudaSuccess) { s.last_error = "tc_pack: cudaMalloc failed"; return -1; }
-    if (cudaMemcpy(w.d, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { s.last_error = "tc_pack: upload failed"; return -1; }
-    const cuuint64_t gdim[2] = {(cuuint64_t)KBT, (cuuint64_t)2 * 9 * w.KBn * N};
-    const cuuint64_t gstr[1] = {(cuuint64_t)KBT * sizeof(float)};
+    if (cudaMalloc((void**)&w.d, pk.size() * sizeof(__half)) != cudaSuccess) { s.last_error = "tc_pack: cudaMalloc failed"; return -1; }
+    if (cudaMemcpy(w.d, pk.data(), pk.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) { s.last_error = "tc_pack: upload failed"; return -1; }
+    const cuuint64_t gdim[2] = {(cuuint64_t)TC_KB, (cuuint64_t)2 * 9 * w.KBn * w.Npad};
+    const cuuint64_t gstr[1] = {(cuuint64_t)TC_KB * sizeof(__half)};
     const cuuint32_t est[2] = {1, 1};
-    w.max_csize = 1;
-    for (int ci = 0; ci < 3; ++ci) {
-        const int cs = 1 << ci;
-        if (w.Ncta % (8 * cs)) break;   // every CTA's slice must be whole 8-row swizzle atoms
-        const cuuint32_t box[2] = {(cuuint32_t)KBT, (cuuint32_t)(w.Ncta / cs)};
-        const CUresult r = s.encode(&w.map[ci], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w.d, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                    KBT == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { s.last_error = "tc_pack: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return -1; }
-        w.max_csize = cs;
-    }
+    const cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)(w.Ncta / 2)};
+    const CUresult r = s.encode(&w.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w.d, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { s.last_error = "tc_pack: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return -1; }
     w.ok = true;
     return 0;
 }
 
-struct TcGeom { int TW, TH, P, NT, SA, SB, a_plane, b_plane, tmem_cols, tiles_x, tiles_y, regions, staging, stage_ld; size_t smem; };
-
-inline int tc_round_up(int v, int m) { return (v + m - 1) / m * m; }
+struct TcGeom { int TW, TH, P, NT, SA, SB, a_plane, raw, b_plane, tmem_cols, tiles_x, tiles_y, regions, staging, stage_ld; size_t smem; };
 
 // Picks the flat-padded tile (TW x TH, P = TW + 2, (TH-1)*P + TW <= 128) with the best MMA-row efficiency, then the
-// number of stacked tiles per CTA region (weight-tile reuse) that still load-balances over the SMs and fits shared memory.
-inline bool tc_geometry(int B, int H, int W, int KBT, int Ncta, int gz, bool pooled, int force_nt, int n_sm, int csize, TcGeom& g) {
+// number of stacked tiles per CTA region (weight-tile reuse) that still load-balances over the CTA pairs and fits
+// shared memory.
+inline bool tc_geometry(int B, int H, int W, int Ncta, int gz, bool pooled, int force_nt, int n_pairs, TcGeom& g) {
     double best = -1.0;
     int bTW = 0, bTH = 0;
     const int step = pooled ? 2 : 1;
@@ -698,8 +689,7 @@ inline bool tc_geometry(int B, int H, int W, int KBT, int Ncta, int gz, bool poo
     g.TW = bTW; g.TH = bTH; g.P = bTW + 2;
     g.tiles_x = (W + g.TW - 1) / g.TW;
     const int row_tiles = (H + g.TH - 1) / g.TH;
-    const int RB = KBT * 4;
-    g.b_plane = Ncta * RB;
+    g.b_plane = (Ncta / 2) * TC_ROW;
     g.stage_ld = Ncta + 1;
     g.staging = pooled ? tc_round_up(128 * g.stage_ld * 4, 1024) : 0;
     int nt_cap = 256 / Ncta;  // two accumulator sets of NT * Ncta columns in the 512 TMEM columns
@@ -710,28 +700,31 @@ inline bool tc_geometry(int B, int H, int W, int KBT, int Ncta, int gz, bool poo
     double pick_eff = -1.0;
     TcGeom cand[9];
     for (int NT = nt_cap; NT >= 1; --NT) {
-        const int rows = std::max((NT * g.TH + 2) * g.P, (NT - 1) * g.TH * g.P + 2 * g.P + 2 + 128);
-        const int a_plane = tc_round_up(rows * RB, 1024);
+        const int box_rows = (NT * g.TH + 2) * g.P;
+        if (NT * g.TH + 2 > 256) continue;   // TMA box dimension limit
+        const int rows = std::max(box_rows, (NT - 1) * g.TH * g.P + 2 * g.P + 2 + 128);
+        const int a_plane = tc_round_up(rows * TC_ROW, 1024);
+        const int raw = tc_round_up(box_rows * TC_RAW_ROW, 1024);
         int SA = 3, SB = 0;
-        for (; SA >= 2; --SA) {   // three activation stages when the weight ring still gets >= 4
-            const long long left = (long long)TC_SMEM_LIMIT - 4096 - g.staging - (long long)SA * 2 * a_plane;
+        for (; SA >= 2; --SA) {   // three operand stages when the weight ring still gets >= 4
+            const long long left = (long long)TC_SMEM_LIMIT - 4096 - g.staging - (long long)TC_SR * raw - (long long)SA * 2 * a_plane;
             SB = left > 0 ? (int)(left / (2 * g.b_plane)) : 0;
-            if (SB > 8) SB = 8;
+            if (SB > 10) SB = 10;
             if (SB >= (SA == 3 ? 4 : 2)) break;
         }
         if (SA < 2) continue;
         TcGeom c = g;
-        c.NT = NT; c.SA = SA; c.SB = SB; c.a_plane = a_plane;
+        c.NT = NT; c.SA = SA; c.SB = SB; c.a_plane = a_plane; c.raw = raw;
         c.tiles_y = (row_tiles + NT - 1) / NT;
         c.regions = c.tiles_x * c.tiles_y * B;
         int cols = 32;
         while (cols < 2 * NT * Ncta) cols <<= 1;
         c.tmem_cols = cols;
-        c.smem = (size_t)SA * 2 * a_plane + (size_t)SB * 2 * g.b_plane + g.staging + 8 * (3 * SA + 2 * SB + 4) + 16 + 1024;
-        const int slots = n_sm / csize;                                    // clusters that run side by side
-        const int groups = ((c.regions + csize - 1) / csize) * gz;
-        const int rounds = (groups + slots - 1) / slots;
-        const double eff = (double)c.regions * gz / ((double)rounds * slots * csize);
+        c.smem = (size_t)SA * 2 * a_plane + (size_t)TC_SR * raw + (size_t)SB * 2 * g.b_plane + g.staging +
+                 8 * (2 * TC_SR + 2 * SA + 2 * SB + 4) + 16 + 1024;
+        const int groups = ((c.regions + 1) / 2) * gz;
+        const int rounds = (groups + n_pairs - 1) / n_pairs;
+        const double eff = (double)c.regions * gz / ((double)rounds * n_pairs * 2);
         cand[NT] = c;
         if (eff >= 0.85) { pick = NT; break; }       // largest NT that still fills the machine evenly
         if (eff > pick_eff) { pick_eff = eff; pick = NT; }
@@ -751,21 +744,32 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     const bool pooled = a.epi == EPI_CONVA;
     if (pooled && ((a.H | a.W) & 1)) { s.last_error = "tc_conv: pooled conv needs even H, W"; return -1; }
     if (pooled && w.Ncta > 128) { s.last_error = "tc_conv: pooled conv needs <= 128 channels per CTA"; return -1; }
-    int csize = std::min(w.max_csize, s.max_cluster);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(TC_THREADS); cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    if (s.max_pairs == 0) {   // how many CTA pairs can be resident at once
+        int n = 0;
+        cfg.gridDim = dim3(s.n_sm / 2 * 2);
+        cfg.dynamicSmemBytes = TC_SMEM_LIMIT;
+        if (cudaOccupancyMaxActiveClusters(&n, conv3x3_tc_kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = s.n_sm / 2; }
+        s.max_pairs = std::min(n, s.n_sm / 2);
+    }
     TcGeom g;
-    if (!tc_geometry(a.B, a.H, a.W, w.KBT, w.Ncta, w.gz, pooled, s.force_nt, s.n_sm, csize, g)) { s.last_error = "tc_conv: no tile geometry fits"; return -1; }
-    while (csize > 1 && g.regions < csize) csize >>= 1;
+    if (!tc_geometry(a.B, a.H, a.W, w.Ncta, w.gz, pooled, s.force_nt, s.max_pairs, g)) { s.last_error = "tc_conv: no tile geometry fits"; return -1; }
     const int box_rows = g.NT * g.TH + 2;
-    auto key = std::make_tuple((const void*)(a.in_hi + a.in_coff), a.Cin, a.W, a.H, a.B, a.in_pitch, g.P, box_rows, w.KBT);
+    auto key = std::make_tuple((const void*)(a.in_hi + a.in_coff), a.Cin, a.W, a.H, a.B, a.in_pitch, g.P, box_rows);
     auto it = s.amaps.find(key);
     if (it == s.amaps.end()) {
         CUtensorMap map;
         const cuuint64_t gdim[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
         const cuuint64_t gstr[3] = {(cuuint64_t)a.in_pitch * 4, (cuuint64_t)a.W * a.in_pitch * 4, (cuuint64_t)a.H * a.W * a.in_pitch * 4};
-        const cuuint32_t box[4] = {(cuuint32_t)w.KBT, (cuuint32_t)g.P, (cuuint32_t)box_rows, 1};
+        const cuuint32_t box[4] = {(cuuint32_t)TC_KB, (cuuint32_t)g.P, (cuuint32_t)box_rows, 1};
         const cuuint32_t est[4] = {1, 1, 1, 1};
         const CUresult r = s.encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(a.in_hi + a.in_coff), gdim, gstr, box, est,
-                                    CU_TENSOR_MAP_INTERLEAVE_NONE, w.KBT == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { s.last_error = "tc_conv: cuTensorMapEncodeTiled(A) failed (" + std::to_string((int)r) + ")"; return -1; }
         it = s.amaps.emplace(key, map).first;
@@ -774,40 +778,21 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     memset(&p, 0, sizeof p);
     p.B = a.B; p.H = a.H; p.W = a.W;
     p.TW = g.TW; p.TH = g.TH; p.P = g.P; p.NT = g.NT; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y; p.regions = g.regions;
-    p.KBn = w.KBn; p.Ncta = w.Ncta; p.N = w.N;
-    p.a_plane_bytes = g.a_plane; p.b_plane_bytes = g.b_plane; p.a_box_bytes = w.KBT * 4 * g.P * box_rows;
+    p.KBn = w.KBn; p.Ncta = w.Ncta; p.N = w.Npad;
+    p.a_plane_bytes = g.a_plane; p.b_plane_bytes = g.b_plane; p.raw_bytes = g.raw; p.a_box_bytes = TC_RAW_ROW * g.P * box_rows;
     p.SA = g.SA; p.SB = g.SB; p.tmem_cols = g.tmem_cols;
     p.staging_bytes = g.staging; p.stage_ld = g.stage_ld;
+    p.inv_scale = 1.0f / (TC_ACT_SCALE * w.wscale);
     p.ca = a;
     if (g.smem > TC_SMEM_LIMIT) { s.last_error = "tc_conv: shared memory budget exceeded"; return -1; }
-    p.csize = csize;
     p.dbg = s.dbg;
-    p.groups_per_nz = (g.regions + csize - 1) / csize;
+    p.groups_per_nz = (g.regions + 1) / 2;
     p.groups = p.groups_per_nz * w.gz;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = g.smem; cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
-    void (*kern)(const CUtensorMap, const CUtensorMap, const TcParams) = w.KBT == 32 ? conv3x3_tc_kernel<32> : conv3x3_tc_kernel<16>;
-    int slots = s.n_sm / csize;
-    if (csize > 1) {   // how many clusters can be resident at once (GPC boundaries cost a few SMs)
-        auto ck = std::make_tuple(w.KBT, csize, g.smem);
-        auto ci = s.max_clusters.find(ck);
-        if (ci == s.max_clusters.end()) {
-            int n = 0;
-            cfg.gridDim = dim3(s.n_sm / csize * csize);
-            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = s.n_sm / csize / 2; }
-            ci = s.max_clusters.emplace(ck, n).first;
-        }
-        slots = std::min(slots, ci->second);
-    }
-    const int n_clusters = std::min(p.groups, slots);
-    cfg.gridDim = dim3(n_clusters * csize);
-    s.last_grid = n_clusters * csize; s.last_csize = csize; s.last_nt = g.NT; s.last_sa = g.SA; s.last_sb = g.SB;
-    const int ci_map = csize == 4 ? 2 : (csize == 2 ? 1 : 0);
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, it->second, w.map[ci_map], p);
+    const int n_pairs = std::min(p.groups, s.max_pairs);
+    cfg.gridDim = dim3(n_pairs * 2);
+    cfg.dynamicSmemBytes = g.smem;
+    s.last_grid = n_pairs * 2; s.last_nt = g.NT; s.last_sa = g.SA; s.last_sb = g.SB;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel, it->second, w.map, p);
     if (le != cudaSuccess) { s.last_error = std::string("tc_conv launch: ") + cudaGetErrorString(le); cudaGetLastError(); return -1; }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { s.last_error = std::string("tc_conv launch: ") + cudaGetErrorString(e); return -1; }

@@ -33,7 +33,7 @@ enum { EIG_BANDS = 0, EIG_CIRCLES = 1, EIG_FREE = 2, EIG_CIRCLES_FREE = 3 };
 /* frame pairing: population path (generate_illusion.py:543-546: prediction #20 vs extension #1) or the
  * single-image path (fitness_calculator.py:493-498: input image vs extension #2) */
 enum { EIG_PAIR_POPULATION = 0, EIG_PAIR_SINGLE_IMAGE = 1 };
-/* convolution engine for PredNet layers 1..3: exact-fp32 SIMT kernels, or tcgen05 tensor cores (3xTF32) */
+/* convolution engine for PredNet layers 1..3: exact-fp32 SIMT kernels, or tcgen05 tensor cores (CTA pairs, 3-pass split fp16 with fp32 accumulation) */
 enum { EIG_CONV_SIMT = 0, EIG_CONV_TC = 1 };
 
 const char* eig_last_error(void);

@@ -225,9 +225,9 @@ static void time_shape(const char* name, int B, int H, int W, int pitch, int cof
 }
 
 static int timing_main() {
-    for (int cluster = 1; cluster <= 4; cluster *= 2) {
+    for (int cluster = 2; cluster <= 2; cluster *= 2) {
         for (int max_nt = 0; max_nt <= 1; ++max_nt) {
-            printf("--- cluster <= %d, tiles per region %s\n", cluster, max_nt ? "1" : "auto");
+            printf("--- CTA pairs, tiles per region %s\n", max_nt ? "1" : "auto");
             time_shape("LSTM1", 32, 60, 80, 80, 0, 80, 64, EPI_LSTM, cluster, max_nt);
             time_shape("LSTM2", 32, 30, 40, 160, 0, 160, 128, EPI_LSTM, cluster, max_nt);
             time_shape("LSTM3", 32, 15, 20, 192, 0, 192, 256, EPI_LSTM, cluster, max_nt);
@@ -259,7 +259,7 @@ int main(int argc, char** argv) {
     };
     bool kb_ok[2] = {true, true};
     struct Cfg { int kb, max_nt, cluster; };
-    const Cfg cfgs[] = {{16, 0, 4}, {16, 0, 2}, {16, 1, 1}, {16, 0, 1}, {32, 0, 4}, {32, 1, 1}};
+    const Cfg cfgs[] = {{16, 0, 2}, {16, 1, 2}};   // the K block is fixed (32 channels, fp16) and the cluster is the CTA pair
     for (const Cfg& c : cfgs) {
         printf("== K block %d, tiles per region %s, multicast cluster <= %d ==\n", c.kb, c.max_nt ? "capped at 1" : "auto", c.cluster);
         tc_set_max_nt(c.max_nt);
