@@ -3,9 +3,9 @@
 // read and written once per time step:
 //   l0_conva1_kernel : E0 = [relu(x-P0), relu(P0-x)] on the fly -> ConvA1 (2*C0 -> C1) -> relu -> 2x2 max-pool
 //                      -> E1 = [relu(A1-P1), relu(P1-A1)] into the layer-1 concat buffer        (net.py:187-194)
-//   l0_lstm_kernel   : ConvLSTM0 on [E0 | up2x(R1) | h0]: E0 recomputed from x and P0, R1 read at half resolution
-//                      straight from the layer-1 buffer (no up-sampled copy in HBM), 4 gates + cell update fused
-//                                                                                               (net.py:94-126,202-203)
+//   l0_lstm_kernel   : ConvLSTM0 on [E0 | up2x(R1) | h0]: E0 recomputed from x and P0; the up2x(R1) taps arrive as
+//                      half-resolution partial sums Z computed on the tensor cores next to ConvP1 (no up-sampled copy
+//                      in HBM, 6x fewer CUDA-core MACs); 4 gates + cell update fused          (net.py:94-126,202-203)
 //   l0_convp_kernel  : P0 = min(relu(ConvP0(h0)), 1)                                              (net.py:207)
 // Accumulation order: input channel, then ky, then kx, with fused multiply-add (same as conv_simt.cuh).
 #pragma once
@@ -28,8 +28,7 @@ struct L0Args {
     const float* wL;       // [9][ctot0][4*C0], ctot0 = 2*C0 + C1 + C0
     const float* bL;       // [4*C0] gate-interleaved
     const float* peep;     // [H,W,C0,4]
-    const float* R1;       // layer-1 concat buffer holding h1 of this step
-    int R1_pitch, R1_coff;
+    const float* Z;        // [B,H/2,W/2,4*4*C0] half-resolution partial sums of the up-sampled-R1 taps (see l0_lstm_kernel)
     const float* h_prev;   // [B,H,W,C0]
     float* h_next;         // [B,H,W,C0]
     float* cstate;         // [B,H,W,C0]
@@ -125,88 +124,83 @@ __global__ void __launch_bounds__(256) l0_conva1_kernel(L0Args a) {
 }
 
 // ---------------------------------------------------------------------------------------------- ConvLSTM0
-// CTA = 32x8 pixels of one genome, 64 threads, thread = 1x4 pixel strip x all NG = 4*C0 gate columns.
-// Input channels are streamed through shared memory in chunks of <= L0_CHUNK.
-enum { L0_CHUNK = 20 };
-template <int NG>
-__global__ void __launch_bounds__(64) l0_lstm_kernel(L0Args a) {
-    constexpr int SW = L0_TW + 2, SH = L0_TH + 2, C0 = NG / 4;
-    __shared__ float sIn[L0_CHUNK][SH][SW];
-    __shared__ __align__(16) float sWt[9 * L0_CHUNK * NG];
+// The 3x3 taps over the nearest-neighbour up-sampled R1 are NOT evaluated here: for the four pixel parities they
+// collapse to 2x2 taps over R1 at half resolution, i.e. to one 3x3 convolution of R1 with 4 * NG output columns
+// (column = parity * NG + gate column; weights pre-summed at load time, eig_api.cu:build_z_weights).  That convolution
+// rides along with ConvP1 on the layer-1 conv kernel (ConvArgs::outZ) and this kernel starts its accumulators from Z,
+// leaving only the E0 and h0 taps (3*C0 input channels) for the CUDA cores.
+// CTA = 32x8 pixels of one genome, 128 threads, thread = 1x2 pixel strip x all NG = 4*C0 gate columns.
+template <int C0>
+__global__ void __launch_bounds__(128) l0_lstm_kernel(L0Args a) {
+    constexpr int NG = 4 * C0, CIN = 3 * C0, SW = L0_TW + 2, SH = L0_TH + 2;
+    __shared__ float sIn[CIN][SH][SW];
+    __shared__ __align__(16) float sWt[9 * CIN * NG];
     const int tiles_x = (a.W + L0_TW - 1) / L0_TW;
     const int x0 = (blockIdx.x % tiles_x) * L0_TW, y0 = (blockIdx.x / tiles_x) * L0_TH;
     const int b = blockIdx.y;
     const int ctot = 2 * C0 + a.C1 + C0;
     const long long img = (long long)b * a.H * a.W;
-    const int H1 = a.H >> 1, W1 = a.W >> 1;
-    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;   // strip: columns 4*tx .. 4*tx+3 of row ty
-    float acc[4][NG];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int n = 0; n < NG; ++n) acc[j][n] = 0.f;
-
-    for (int c0 = 0; c0 < ctot; c0 += L0_CHUNK) {
-        const int nc = ctot - c0 < L0_CHUNK ? ctot - c0 : L0_CHUNK;
-        for (int i = threadIdx.x; i < SH * SW; i += blockDim.x) {
-            const int cy = i / SW, cx = i - cy * SW;
-            const int gy = y0 + cy - 1, gx = x0 + cx - 1;
-            const bool in = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
-            const long long pix = img + (long long)gy * a.W + gx;
-            const long long pix1 = ((long long)b * H1 + (gy >> 1)) * W1 + (gx >> 1);
-            for (int k = 0; k < nc; ++k) {
-                const int c = c0 + k;
-                float v = 0.f;
-                if (in) {
-                    if (c < 2 * C0) {
-                        const int cc = c < C0 ? c : c - C0;
-                        const float xv = a.x[pix * C0 + cc], pv = a.P0[pix * C0 + cc];
-                        v = c < C0 ? __fsub_rn(xv, pv) : __fsub_rn(pv, xv);
-                        v = v > 0.f ? v : 0.f;
-                    } else if (c < 2 * C0 + a.C1) {
-                        v = a.R1[pix1 * a.R1_pitch + a.R1_coff + (c - 2 * C0)];   // nearest-neighbour x2 up-sampling
-                    } else {
-                        v = a.h_prev[pix * C0 + (c - 2 * C0 - a.C1)];
-                    }
-                }
-                sIn[k][cy][cx] = v;
-            }
+    for (int i = threadIdx.x; i < SH * SW * C0; i += blockDim.x) {
+        const int c = i % C0, pp = i / C0;
+        const int cy = pp / SW, cx = pp - cy * SW;
+        const int gy = y0 + cy - 1, gx = x0 + cx - 1;
+        float ep = 0.f, en = 0.f, hv = 0.f;
+        if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+            const long long idx = (img + (long long)gy * a.W + gx) * C0 + c;
+            const float xv = a.x[idx], pv = a.P0[idx];
+            ep = __fsub_rn(xv, pv); en = __fsub_rn(pv, xv);
+            ep = ep > 0.f ? ep : 0.f; en = en > 0.f ? en : 0.f;
+            hv = a.h_prev[idx];
         }
-        for (int i = threadIdx.x; i < 9 * nc * NG; i += blockDim.x) {
-            const int n = i % NG, r = i / NG;
-            const int k = r % nc, tap = r / nc;
-            sWt[(tap * L0_CHUNK + k) * NG + n] = a.wL[((long long)tap * ctot + c0 + k) * NG + n];
-        }
-        __syncthreads();
-        for (int k = 0; k < nc; ++k) {
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                float in[6];
-#pragma unroll
-                for (int q = 0; q < 6; ++q) in[q] = sIn[k][ty + ky][4 * tx + q];
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const float* wrow = sWt + ((ky * 3 + kx) * L0_CHUNK + k) * NG;
-                    float wv[NG];
-#pragma unroll
-                    for (int n = 0; n < NG; n += 4) {
-                        const float4 q = *reinterpret_cast<const float4*>(wrow + n);
-                        wv[n] = q.x; wv[n + 1] = q.y; wv[n + 2] = q.z; wv[n + 3] = q.w;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int n = 0; n < NG; ++n) acc[j][n] = __fmaf_rn(in[j + kx], wv[n], acc[j][n]);
-                }
-            }
-        }
-        __syncthreads();
+        sIn[c][cy][cx] = ep;
+        sIn[C0 + c][cy][cx] = en;
+        sIn[2 * C0 + c][cy][cx] = hv;
     }
-    const int gy = y0 + ty;
-    if (gy >= a.H) return;
+    for (int i = threadIdx.x; i < 9 * CIN * NG; i += blockDim.x) {
+        const int n = i % NG, r = i / NG;
+        const int k = r % CIN, tap = r / CIN;
+        const int c = k < 2 * C0 ? k : k + a.C1;   // skip the R1 channels of the full weight tensor
+        sWt[i] = a.wL[((long long)tap * ctot + c) * NG + n];
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // strip: columns 2*tx, 2*tx+1 of row ty
+    const int gy = y0 + ty, gx0 = x0 + 2 * tx;
+    if (gy >= a.H || gx0 >= a.W) return;
+    const int H1 = a.H >> 1, W1 = a.W >> 1;
+    float acc[2][NG];
+    {   // both pixels of the strip share the half-resolution pixel; parity = (y & 1) * 2 + (x & 1)
+        const float* z = a.Z + (((long long)b * H1 + (gy >> 1)) * W1 + (gx0 >> 1)) * (4 * NG) + (gy & 1) * 2 * NG;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int gx = x0 + 4 * tx + j;
+        for (int n = 0; n < NG; n += 4) {
+            const float4 z0 = *reinterpret_cast<const float4*>(z + n), z1 = *reinterpret_cast<const float4*>(z + NG + n);
+            acc[0][n] = z0.x; acc[0][n + 1] = z0.y; acc[0][n + 2] = z0.z; acc[0][n + 3] = z0.w;
+            acc[1][n] = z1.x; acc[1][n + 1] = z1.y; acc[1][n + 2] = z1.z; acc[1][n + 3] = z1.w;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            float in[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) in[q] = sIn[k][ty + ky][2 * tx + q];
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float* wrow = sWt + ((ky * 3 + kx) * CIN + k) * NG;
+#pragma unroll
+                for (int n = 0; n < NG; n += 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(wrow + n);
+                    acc[0][n] = __fmaf_rn(in[kx], q.x, acc[0][n]); acc[0][n + 1] = __fmaf_rn(in[kx], q.y, acc[0][n + 1]);
+                    acc[0][n + 2] = __fmaf_rn(in[kx], q.z, acc[0][n + 2]); acc[0][n + 3] = __fmaf_rn(in[kx], q.w, acc[0][n + 3]);
+                    acc[1][n] = __fmaf_rn(in[kx + 1], q.x, acc[1][n]); acc[1][n + 1] = __fmaf_rn(in[kx + 1], q.y, acc[1][n + 1]);
+                    acc[1][n + 2] = __fmaf_rn(in[kx + 1], q.z, acc[1][n + 2]); acc[1][n + 3] = __fmaf_rn(in[kx + 1], q.w, acc[1][n + 3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int gx = gx0 + j;
         if (gx >= a.W) continue;
         const long long pix = img + (long long)gy * a.W + gx;
         const long long ppix = (long long)gy * a.W + gx;

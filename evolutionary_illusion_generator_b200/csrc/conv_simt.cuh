@@ -30,9 +30,13 @@ struct ConvArgs {
     const float* bias;  // [N] (gate-interleaved for LSTM)
     int N, Npad;
     int epi;
-    // EPI_CONVP: out = relu(acc + b) (clipped to 1 when clip != 0) -> outP [B,H,W,N] plain fp32
+    // EPI_CONVP: out = relu(acc + b) (clipped to 1 when clip != 0) -> outP [B,H,W,nP] plain fp32.
+    // When nP != 0 only the first nP columns are ConvP outputs; columns [nP, N) are written raw (no bias, no relu) to
+    // outZ [B,H,W,N-nP]: the half-resolution partial sums of ConvLSTM0's up-sampled-R1 taps (conv_l0.cuh).
     float* outP;
     int clip;
+    int nP;
+    float* outZ;
     // EPI_CONVA: A = maxpool2x2(relu(acc + b)); E = [relu(A-P), relu(P-A)] -> dstE view at (H/2, W/2)
     const float* P;  // [B, H/2, W/2, N]
     View dstE;
@@ -147,10 +151,12 @@ __global__ void __launch_bounds__(256) conv3x3_simt_kernel(ConvArgs a) {
 #pragma unroll
             for (int n = 0; n < TN; ++n) {
                 if (n0 + n >= a.N) continue;
+                const int nP = a.nP ? a.nP : a.N;
+                if (n0 + n >= nP) { a.outZ[pix * (a.N - nP) + n0 + n - nP] = acc[j][n]; continue; }
                 float v = __fadd_rn(acc[j][n], a.bias[n0 + n]);
                 v = v > 0.f ? v : 0.f;
                 if (a.clip && v > 1.f) v = 1.f;
-                a.outP[pix * a.N + n0 + n] = v;
+                a.outP[pix * nP + n0 + n] = v;
             }
         }
     } else if (a.epi == EPI_CONVA) {

@@ -484,12 +484,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                         }
                     }
                 } else if (a.epi == EPI_CONVP || a.epi == EPI_RAW) {
+                    const int nP = a.nP ? a.nP : a.N;
                     for (int c0 = half * 16; c0 < ncols; c0 += 32) {
                         float v[16];
                         tmem_ld16(tcol + c0, v);
                         if (!valid) continue;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
+                            const int col = n0 + c0 + q * 4;
+                            if (col >= nP) {   // raw partial sums for ConvLSTM0 (see ConvArgs::outZ)
+                                *reinterpret_cast<float4*>(a.outZ + pix * (a.N - nP) + col - nP) =
+                                    make_float4(__fmul_rn(v[q * 4], inv), __fmul_rn(v[q * 4 + 1], inv), __fmul_rn(v[q * 4 + 2], inv), __fmul_rn(v[q * 4 + 3], inv));
+                                continue;
+                            }
                             const float4 bq = *reinterpret_cast<const float4*>(a.bias + n0 + c0 + q * 4);
                             float o[4] = {__fadd_rn(__fmul_rn(v[q * 4], inv), bq.x), __fadd_rn(__fmul_rn(v[q * 4 + 1], inv), bq.y),
                                           __fadd_rn(__fmul_rn(v[q * 4 + 2], inv), bq.z), __fadd_rn(__fmul_rn(v[q * 4 + 3], inv), bq.w)};
@@ -500,7 +507,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                                     if (a.clip && o[i] > 1.f) o[i] = 1.f;
                                 }
                             }
-                            *reinterpret_cast<float4*>(a.outP + pix * a.N + n0 + c0 + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4*>(a.outP + pix * nP + col) = make_float4(o[0], o[1], o[2], o[3]);
                         }
                     }
                 } else {  // EPI_CONVA: relu -> staging tile -> 2x2 max-pool -> error units at half resolution

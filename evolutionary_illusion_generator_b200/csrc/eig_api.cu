@@ -89,6 +89,8 @@ struct eig_ctx {
     float* cst[4] = {nullptr};       // cell state [B][H][W][R]
     float* h0[2] = {nullptr, nullptr};  // layer-0 hidden state [B][h][w][C0], double-buffered over time steps
     float* P[4] = {nullptr};         // predictions [B][H][W][C]
+    float* Z = nullptr;              // [B][H/2][W/2][16*C0] partial sums of ConvLSTM0's up-sampled-R1 taps (conv_l0.cuh)
+    int npz = 0;                     // columns of the layer-1 ConvP+Z convolution: C1 + 16*C0
     float* x_in = nullptr;           // [B][h][w][c]
     unsigned char* img = nullptr;    // rendered [B][h][w][c]
     unsigned char* frames = nullptr; // [3][B][h][w][c]
@@ -145,6 +147,8 @@ extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, co
         CK(dalloc(c, &c->P[n], px * c->ch[n]));
     }
     const size_t npx = B * w * h;
+    c->npz = c->ch[1] + 16 * c->ch[0];
+    CK(dalloc(c, &c->Z, B * c->H[1] * c->W[1] * 16 * c->ch[0]));
     CK(dalloc(c, &c->x_in, npx * c_dim));
     CK(dalloc(c, &c->img, npx * c_dim));
     CK(dalloc(c, &c->frames, 3 * npx * c_dim));
@@ -237,6 +241,30 @@ void scatter_conv(std::vector<float>& dst, int cin_total, int npad, int cin_off,
                 dst[((size_t)tap * cin_total + cin_off + ci) * npad + n * col_mul + col_add] =
                     t->p[((size_t)n * cin + ci) * 9 + tap];
 }
+// ConvLSTM0's 3x3 taps over the nearest-neighbour up-sampled R1, folded to half resolution: output pixel (2Y+py, 2X+px)
+// reads full-resolution row 2Y+py+ky-1 = low-resolution row Y + floor((py+ky-1)/2), so per parity the taps {0,1,2}
+// collapse onto low-resolution offsets {-1,0,0} (p = 0) or {0,0,+1} (p = 1).  Zero padding agrees on both grids.
+// dst: [9][C1][npad]; Z columns start at col0 = C1: column col0 + (py*2+px)*NG + n, NG = 4*C0.
+// w0: ConvLSTM0 weights [9][ctot0][NG]; the R1 channels are [2*C0, 2*C0 + C1).
+void build_z_weights(std::vector<float>& dst, int npad, int C1, const std::vector<float>& w0, int C0, int ctot0) {
+    const int NG = 4 * C0;
+    static const int lowoff[2][3] = {{-1, 0, 0}, {0, 0, 1}};
+    std::vector<double> acc((size_t)9 * C1 * 4 * NG, 0.0);
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px)
+            for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int tap_lr = (lowoff[py][ky] + 1) * 3 + (lowoff[px][kx] + 1);
+                    for (int ch = 0; ch < C1; ++ch)
+                        for (int n = 0; n < NG; ++n)
+                            acc[((size_t)tap_lr * C1 + ch) * 4 * NG + (py * 2 + px) * NG + n] +=
+                                (double)w0[((size_t)(ky * 3 + kx) * ctot0 + 2 * C0 + ch) * NG + n];
+                }
+    for (int tap = 0; tap < 9; ++tap)
+        for (int ch = 0; ch < C1; ++ch)
+            for (int j = 0; j < 4 * NG; ++j)
+                dst[((size_t)tap * C1 + ch) * npad + C1 + j] = (float)acc[((size_t)tap * C1 + ch) * 4 * NG + j];
+}
 }  // namespace
 
 extern "C" int eig_load_weights(eig_ctx* c, int nt, const char* const* names, const float* const* ptrs, const int64_t* shapes) {
@@ -252,6 +280,7 @@ extern "C" int eig_load_weights(eig_ctx* c, int nt, const char* const* names, co
         m[k] = t;
     }
     const char gates[4] = {'i', 'f', 'c', 'o'};
+    std::vector<float> lstm0_host;   // [9][ctot0][4*C0], needed again for the layer-1 ConvP+Z weights
     for (int n = 0; n < 4; ++n) {
         LayerW& L = c->lw[n];
         const int C = c->ch[n], R = C, Hn = c->H[n], Wn = c->W[n];
@@ -273,17 +302,19 @@ extern "C" int eig_load_weights(eig_ctx* c, int nt, const char* const* names, co
 #endif
         }
         {
-            const int cin = R, npad = (C + 3) & ~3;
-            std::vector<float> wv((size_t)9 * cin * npad, 0.f), bv(C);
+            // layer 1 carries the Z columns of ConvLSTM0 next to its ConvP columns (see build_z_weights)
+            const int cin = R, ncol = n == 1 ? c->npz : C, npad = (ncol + 3) & ~3;
+            std::vector<float> wv((size_t)9 * cin * npad, 0.f), bv(npad, 0.f);
             snprintf(nm, sizeof nm, "ConvP%d/W", n);
             if ((rc = need(m, nm, C, cin, 3, 3, &t))) return rc;
             scatter_conv(wv, cin, npad, 0, t, C, cin, 1, 0);
             snprintf(nm, sizeof nm, "ConvP%d/b", n);
             if ((rc = need(m, nm, C, 1, 1, 1, &t))) return rc;
             for (int i = 0; i < C; ++i) bv[i] = t->p[i];
+            if (n == 1) build_z_weights(wv, npad, C, lstm0_host, c->ch[0], c->ctot[0]);
             CK(upload(c, &L.convP, wv)); CK(upload(c, &L.convP_b, bv));
 #ifndef EIG_EMU
-            if (n >= 1 && (rc = tc_pack(L.tcP, wv.data(), cin, C, npad))) return fail(EIG_E_CUDA, "tc_pack ConvP: " + tc_last_error());
+            if (n >= 1 && (rc = tc_pack(L.tcP, wv.data(), cin, ncol, npad))) return fail(EIG_E_CUDA, "tc_pack ConvP: " + tc_last_error());
 #endif
         }
         {
@@ -316,6 +347,7 @@ extern "C" int eig_load_weights(eig_ctx* c, int nt, const char* const* names, co
                             pv[(((size_t)y * Wn + x) * R + r) * 4 + g] = t->p[((size_t)r * Hn + y) * Wn + x];
             }
             CK(upload(c, &L.lstm, wv)); CK(upload(c, &L.lstm_b, bv)); CK(upload(c, &L.peep, pv));
+            if (n == 0) lstm0_host = wv;
 #ifndef EIG_EMU
             if (n >= 1 && (rc = tc_pack(L.tcL, wv.data(), ctot, N, N))) return fail(EIG_E_CUDA, "tc_pack ConvLSTM: " + tc_last_error());
 #endif
@@ -357,7 +389,7 @@ static L0Args l0_args(eig_ctx* c, const float* x, int B, int cur, int nxt) {
     a.P1 = c->P[1];
     a.dstE1 = mkview(c->X[1][cur], nullptr, c->ctot[1], 0, 2 * c->ch[1]);
     a.wL = c->lw[0].lstm; a.bL = c->lw[0].lstm_b; a.peep = c->lw[0].peep;
-    a.R1 = c->X[1][nxt]; a.R1_pitch = c->ctot[1]; a.R1_coff = 2 * c->ch[1] + c->ch[2];
+    a.Z = c->Z;
     a.h_prev = c->h0[cur]; a.h_next = c->h0[nxt]; a.cstate = c->cst[0];
     a.wP = c->lw[0].convP; a.bP = c->lw[0].convP_b; a.C0pad = (c->ch[0] + 3) & ~3;
     a.P0_out = c->P[0];
@@ -396,6 +428,22 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }
+    auto conv_p = [&](int n) -> int {   // ConvP_n: R_n -> P_n (layer 1 also emits Z for ConvLSTM0)
+        ConvArgs a;
+        memset(&a, 0, sizeof a);
+        const int hoff = 2 * c->ch[n] + (n < 3 ? c->ch[n + 1] : 0);
+        a.in_hi = c->X[n][nxt]; a.in_lo = nullptr;
+        a.in_pitch = c->ctot[n]; a.in_coff = hoff; a.Cin = c->ch[n];
+        a.B = B; a.H = c->H[n]; a.W = c->W[n];
+        a.wgt = c->lw[n].convP; a.bias = c->lw[n].convP_b;
+        a.N = n == 1 ? c->npz : c->ch[n]; a.Npad = (a.N + 3) & ~3;
+        a.epi = EPI_CONVP; a.outP = c->P[n]; a.clip = 0;
+        if (n == 1) { a.nP = c->ch[1]; a.outZ = c->Z; }
+#ifndef EIG_EMU
+        if (tc && c->lw[n].tcP.ok) { prof_pre(CLS_CONV_TC, s); const int r2 = tc_conv(c->lw[n].tcP, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (r2) return fail(EIG_E_CUDA, "tc_conv ConvP: " + tc_last_error()); return EIG_OK; }
+#endif
+        return launch_conv(c, a, s);
+    };
     for (int n = 3; n >= 1; --n) {  // ConvLSTM_n
         ConvArgs a;
         memset(&a, 0, sizeof a);
@@ -406,36 +454,25 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         a.epi = EPI_LSTM; a.cstate = c->cst[n]; a.peep = c->lw[n].peep;
         const int hoff = 2 * c->ch[n] + (n < 3 ? c->ch[n + 1] : 0);
         a.dstH = mkview(c->X[n][nxt], nullptr, c->ctot[n], hoff, c->ch[n]);
-        // R_n up-sampled x2 into the concat buffer of layer n-1 (layer 0 reads R_1 at half resolution instead)
+        // R_n up-sampled x2 into the concat buffer of layer n-1 (layer 0 gets R_1 through Z instead)
         if (n >= 2) a.dstUp = mkview(c->X[n - 1][cur], nullptr, c->ctot[n - 1], 2 * c->ch[n - 1], c->ch[n]);
 #ifndef EIG_EMU
         if (tc && c->lw[n].tcL.ok) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); continue; }
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }
-    {   // ConvLSTM_0 on [E0 | up(R1) | h0], then ConvP_0 -> P0 (this step's prediction)
-        if (c->ch[0] == 1) { auto k = l0_lstm_kernel<4>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(64), 0, s, l0); }
-        else { auto k = l0_lstm_kernel<12>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(64), 0, s, l0); }
+    if ((rc = conv_p(1))) return rc;   // P_1 and Z (half-resolution partial sums of ConvLSTM0's R1 taps)
+    {   // ConvLSTM_0 on [E0 | up(R1) | h0] (R1 taps via Z), then ConvP_0 -> P0 (this step's prediction)
+        if (c->ch[0] == 1) { auto k = l0_lstm_kernel<1>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(128), 0, s, l0); }
+        else { auto k = l0_lstm_kernel<3>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(128), 0, s, l0); }
         CKL();
         const long long npix = (long long)B * c->h * c->w;
         if (c->ch[0] == 1) { auto k = l0_convp_kernel<1>; LAUNCH_K(CLS_L0, k, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, l0); }
         else { auto k = l0_convp_kernel<3>; LAUNCH_K(CLS_L0, k, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, l0); }
         CKL();
     }
-    for (int n = 1; n < 4; ++n) {  // ConvP_n: R_n -> P_n
-        ConvArgs a;
-        memset(&a, 0, sizeof a);
-        const int hoff = 2 * c->ch[n] + (n < 3 ? c->ch[n + 1] : 0);
-        a.in_hi = c->X[n][nxt]; a.in_lo = nullptr;
-        a.in_pitch = c->ctot[n]; a.in_coff = hoff; a.Cin = c->ch[n];
-        a.B = B; a.H = c->H[n]; a.W = c->W[n];
-        a.wgt = c->lw[n].convP; a.bias = c->lw[n].convP_b; a.N = c->ch[n]; a.Npad = (c->ch[n] + 3) & ~3;
-        a.epi = EPI_CONVP; a.outP = c->P[n]; a.clip = 0;
-#ifndef EIG_EMU
-        if (tc && c->lw[n].tcP.ok) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcP, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvP: " + tc_last_error()); continue; }
-#endif
-        if ((rc = launch_conv(c, a, s))) return rc;
-    }
+    for (int n = 2; n < 4; ++n)
+        if ((rc = conv_p(n))) return rc;
     return EIG_OK;
 }
 
