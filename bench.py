@@ -310,6 +310,7 @@ def tc_compiled():
         from evolutionary_illusion_generator_b200 import _lib, engine as E
         if not torch.cuda.is_available():
             return False
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         e = E.Engine(64, 64, (1, 4, 8, 8), 2)
         try:
             e.set_conv_mode(_lib.CONV_TC)

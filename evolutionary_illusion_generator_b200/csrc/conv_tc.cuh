@@ -226,6 +226,7 @@ __device__ __forceinline__ TcRegion tc_region(const TcParams& p, int group, int 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
+    const long long k_t0 = clock64();
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
     unsigned char* smem = smem_raw + pad;
@@ -263,6 +264,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int acc_stride = p.NT * p.Ncta;
+    const long long k_t1 = clock64();
 
     if (warp < 4) {
         // ===== converter =====
@@ -566,10 +568,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    const long long k_t2 = clock64();
     cluster_sync_all();   // nobody exits while the peer may still read this CTA's operands / arrive on its barriers
     if (warp == 5) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+    if (p.dbg && threadIdx.x == 160) {   // warp 5: prologue / body / teardown cycles of this CTA
+        long long* d = p.dbg + (long long)blockIdx.x * 16;
+        d[11] = k_t1 - k_t0; d[12] = k_t2 - k_t1; d[13] = clock64() - k_t2;
     }
 }
 
@@ -586,6 +593,7 @@ struct TcState {
     long long* dbg = nullptr;  // device buffer for the per-role cycle counters (tests only)
     int last_grid = 0, last_csize = 2, last_nt = 0, last_sa = 0, last_sb = 0;
     int n_sm = 148, max_pairs = 0;
+    std::map<int, bool> smem_attr_set;   // cudaFuncSetAttribute is per device
     std::map<std::tuple<const void*, int, int, int, int, int, int, int>, CUtensorMap> amaps;
 };
 inline TcState& tc_state() { static TcState s; return s; }
@@ -751,6 +759,14 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     const bool pooled = a.epi == EPI_CONVA;
     if (pooled && ((a.H | a.W) & 1)) { s.last_error = "tc_conv: pooled conv needs even H, W"; return -1; }
     if (pooled && w.Ncta > 128) { s.last_error = "tc_conv: pooled conv needs <= 128 channels per CTA"; return -1; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!s.smem_attr_set[dev]) {
+        if (cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
+            s.last_error = "tc_conv: cannot raise the dynamic shared memory limit on this device"; cudaGetLastError(); return -1;
+        }
+        s.smem_attr_set[dev] = true;
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cudaLaunchAttribute attr[1];

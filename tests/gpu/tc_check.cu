@@ -213,12 +213,13 @@ static void time_shape(const char* name, int B, int H, int W, int pitch, int cof
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     std::vector<long long> d = host(dbg, 160 * 16);
     const int grid = tc_state().last_grid;
-    double s[11] = {0};
-    for (int c = 0; c < grid; ++c) for (int k = 0; k < 11; ++k) s[k] += (double)d[c * 16 + k] / grid;
+    double s[14] = {0};
+    for (int c = 0; c < grid; ++c) for (int k = 0; k < 14; ++k) s[k] += (double)d[c * 16 + k] / grid;
+    for (int k = 0; k < 5; ++k) s[k] *= 2;   // the MMA warp only runs in the leader CTA of each pair
     const double flop = 2.0 * px * 9.0 * Cin * N;
-    printf("%-8s B%d %dx%d Cin%d N%d cluster %d NT %d SA %d SB %d grid %d: %7.1f us  %6.1f TFLOP/s(fp32-equiv) | MMA thr: total %6.0f waitAcc %5.0f waitA %5.0f waitB %5.0f regions %.1f | epi: total %6.0f wait %6.0f | conv: total %6.0f wait %6.0f | Bprod: wait %6.0f (cycles, avg per CTA)\n",
+    printf("%-8s B%d %dx%d Cin%d N%d cluster %d NT %d SA %d SB %d grid %d: %7.1f us  %6.1f TFLOP/s(fp32-equiv) | MMA thr: total %6.0f waitAcc %5.0f waitA %5.0f waitB %5.0f regions %.1f | epi: total %6.0f wait %6.0f | conv: total %6.0f wait %6.0f | Bprod: wait %6.0f | kernel: prologue %5.0f body %6.0f teardown %5.0f = %.1f us @1.965GHz (cycles, avg per CTA)\n",
            name, B, W, H, Cin, N, tc_state().last_csize, tc_state().last_nt, tc_state().last_sa, tc_state().last_sb, grid, 1e3 * ms / reps,
-           flop / (1e-3 * ms / reps) / 1e12, s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], s[10]);
+           flop / (1e-3 * ms / reps) / 1e12, s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], s[10], s[11], s[12], s[13], (s[11] + s[12] + s[13]) / 1965.0);
     tc_state().dbg = nullptr;
     cudaFree(dbg); cudaFree(out); cudaFree(cst); cudaFree(peep); cudaFree(dh); cudaFree(Pp); cudaFree(dE);
     cudaFree(p.d_hi); cudaFree(p.d_w); cudaFree(p.d_b); tc_free(p.tw);
