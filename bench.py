@@ -34,6 +34,21 @@ WORKLOADS = {
     "c2": ("circles_bw", 1, (1, 16, 32, 64), 160, 120, 1, 32, 37269),
     "c3": ("circles", 3, (3, 48, 96, 192), 160, 120, 1, 128, 335421),
 }
+
+
+def tc_kernel_macs(ch):
+    """Algorithmic MACs per layer-0 pixel per PredNet step that the tcgen05 kernel covers (SURVEY.md §8 a-7 counts):
+    everything except ConvA1, ConvP0 and the E0/h0 taps of ConvLSTM0, which run on the layer-0 SIMT kernels.
+    ConvLSTM0's up-sampled-R1 taps are counted at their reference cost 9*C1*4*C0 (the kernel evaluates them folded to
+    half resolution)."""
+    c0, c1, c2, c3 = ch
+    total = 0.0
+    total += 9 * 2 * c1 * c2 / 4.0 + 9 * 2 * c2 * c3 / 16.0                      # ConvA2, ConvA3
+    total += 9 * (2 * c1 + c2 + c1) * 4 * c1 / 4.0                                # ConvLSTM1
+    total += 9 * (2 * c2 + c3 + c2) * 4 * c2 / 16.0 + 9 * (2 * c3 + c3) * 4 * c3 / 64.0   # ConvLSTM2, ConvLSTM3
+    total += 9 * c1 * c1 / 4.0 + 9 * c2 * c2 / 16.0 + 9 * c3 * c3 / 64.0          # ConvP1..3
+    total += 9 * c1 * 4 * c0                                                      # R1 taps of ConvLSTM0
+    return total
 USEFUL_STEPS = 21  # 20 static frames + 1 self-fed (the reference's 22nd forward is never read)
 METRIC = "NEAT genome fitness evals/sec (CPPN+PredNet+flow) @160x120"
 
@@ -243,17 +258,26 @@ def run_ours(args):
         total = world * pop * args.steps
         value = total / (dev_ms / 1e3)
         e2e = total / (e2e_ms / 1e3)
-        flop_step = 2.0 * macs * w * h * USEFUL_STEPS * pop            # algorithmic conv FLOP of one step, one GPU
+        flop_step = 2.0 * tc_kernel_macs(ch) * w * h * USEFUL_STEPS * pop   # algorithmic FLOP of the tcgen05 launches, one GPU
         conv_ms = cls_ms["conv_simt"] + cls_ms["conv_tcgen05"]
         conv_n = cls_n["conv_simt"] + cls_n["conv_tcgen05"]
         achieved = flop_step / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": "conv3x3 (%s)" % ("tcgen05 cta_group::2, 3-pass split fp16" if args.conv == "tc" else "fp32 SIMT"),
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1", "tc_traffic.json")
+        if args.conv == "tc" and os.path.isfile(tpath) and not args.pop:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get("mean_dram_bytes_per_launch")
+        roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (%s)" % ("tcgen05 cta_group::2, 3-pass split fp16" if args.conv == "tc" else "fp32 SIMT"),
                     "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": achieved / peaks["tf"],
-                    "traffic": None, "peak_source": peaks["source"] + " bf16 dense (sustained)",
+                    "traffic": traffic, "traffic_source": "ncu --set full, profiles/r1/tc_traffic.json (mean over the 8 launch shapes of one PredNet step)" if traffic else None,
+                    "peak_source": peaks["source"] + " bf16 dense (sustained)",
                     "flop_per_launch": flop_step / max(conv_n, 1), "launches_per_step": conv_n,
                     "avg_launch_us": 1e3 * conv_ms / max(conv_n, 1),
+                    "mma_passes": 3 if args.conv == "tc" else None,
+                    "frac_of_3pass_ceiling": 3.0 * achieved / peaks["tf"] if args.conv == "tc" else None,
                     "class_ms_per_step": cls_ms, "class_launches_per_step": cls_n,
-                    "note": "achieved counts each MAC once; the tcgen05 path issues 3 fp16 MMAs per MAC (hi*hi + hi*lo + lo*hi)"}
+                    "whole_path_gflop_per_genome": 2.0 * macs * w * h * USEFUL_STEPS / 1e9,
+                    "note": "achieved counts each algorithmic MAC once; fp32-grade accuracy needs 3 fp16 MMAs per MAC "
+                            "(hi*hi + hi*lo + lo*hi), so 1/3 of the dense 16-bit peak is the ceiling of this kernel"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

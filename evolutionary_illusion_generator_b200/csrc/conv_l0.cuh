@@ -105,21 +105,30 @@ __global__ void __launch_bounds__(256) l0_conva1_kernel(L0Args a) {
                         acc[j][n] = __fmaf_rn(in[(j >> 1) + ky][(j & 1) + kx], wv[n], acc[j][n]);
             }
     }
-    const int Hp = a.H >> 1, Wp = a.W >> 1;
-    const int gpy = (y0 >> 1) + py, gpx = (x0 >> 1) + px;
-    if (gpy >= Hp || gpx >= Wp) return;
-    const long long ppos = ((long long)b * Hp + gpy) * Wp + gpx;
+    // pooled, biased, rectified A1 -> shared memory [64 pooled pixels][C1pad], then the error units are written with
+    // consecutive threads on consecutive channels of one pixel (coalesced rows of the layer-1 concat buffer)
+    float* sOut = sW + 9 * cin * a.C1pad;
+    const int ldo = a.C1pad + 1;   // odd pitch: the 64 pooled pixels of a warp pair hit different banks
 #pragma unroll
     for (int n = 0; n < CPT; ++n) {
         if (n0 + n >= a.C1) continue;
         const float bn = a.bA[n0 + n];
         float m = fmaxf(fmaxf(__fadd_rn(acc[0][n], bn), __fadd_rn(acc[1][n], bn)),
                         fmaxf(__fadd_rn(acc[2][n], bn), __fadd_rn(acc[3][n], bn)));
-        m = fmaxf(m, 0.f);  // relu commutes with max
-        const float pv = a.P1[ppos * a.C1 + n0 + n];
-        const float ep = __fsub_rn(m, pv), en = __fsub_rn(pv, m);
-        view_store(a.dstE1, ppos, n0 + n, ep > 0.f ? ep : 0.f);
-        view_store(a.dstE1, ppos, a.C1 + n0 + n, en > 0.f ? en : 0.f);
+        sOut[pp * ldo + n0 + n] = fmaxf(m, 0.f);  // relu commutes with max
+    }
+    __syncthreads();
+    const int Hp = a.H >> 1, Wp = a.W >> 1;
+    const int c2 = 2 * a.C1;
+    for (int i = threadIdx.x; i < 64 * c2; i += blockDim.x) {
+        const int q = i / c2, ch = i - q * c2;
+        const int gpy = (y0 >> 1) + (q >> 4), gpx = (x0 >> 1) + (q & 15);
+        if (gpy >= Hp || gpx >= Wp) continue;
+        const long long ppos = ((long long)b * Hp + gpy) * Wp + gpx;
+        const int n = ch < a.C1 ? ch : ch - a.C1;
+        const float m = sOut[q * ldo + n], pv = a.P1[ppos * a.C1 + n];
+        const float e = ch < a.C1 ? __fsub_rn(m, pv) : __fsub_rn(pv, m);
+        view_store(a.dstE1, ppos, ch, e > 0.f ? e : 0.f);
     }
 }
 

@@ -74,8 +74,22 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// cluster-scope acquire: some of the arrivals come from the peer CTA of the pair
+// CTA-scope wait (the default, as CUTLASS uses for every pipeline barrier of a 2-SM kernel): enough for barriers
+// completed by TMA transactions, tcgen05.commit and remote arrives that only order async-proxy / TMEM traffic.
+// (A cluster-scope acquire makes ptxas emit CCTL.IVALL - an L1 invalidate - after every successful wait.)
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// cluster-scope acquire: the arrivals publish generic-proxy shared-memory writes of the peer CTA (converter warps)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -89,6 +103,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // bounded spin: a protocol bug traps (launch error) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
+        if (it > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    for (uint32_t it = 0; !mbar_try_wait_cluster(bar, parity); ++it)
         if (it > (1u << 24)) __trap();
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -375,7 +393,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                 for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
                     const int sa = ia % p.SA;
                     tq = clock64();
-                    mbar_wait(convA + 8 * sa, (ia / p.SA) & 1);
+                    mbar_wait_cluster(convA + 8 * sa, (ia / p.SA) & 1);
                     t_a += clock64() - tq;
                     const uint32_t a16 = (((sA + sa * a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
                     for (int tap = 0; tap < 9; ++tap, ++ib) {

@@ -407,7 +407,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
     const int l0_tiles = ((c->w + L0_TW - 1) / L0_TW) * ((c->h + L0_TH - 1) / L0_TH);
     {   // E0 -> ConvA1 -> pool -> E1 (layer-1 concat buffer)
         const int c1pad = l0.C1pad;
-        const size_t smem = ((size_t)2 * l0.C0 * (L0_TH + 2) * (L0_TW + 2) + (size_t)9 * 2 * l0.C0 * c1pad + 16) * sizeof(float);
+        const size_t smem = ((size_t)2 * l0.C0 * (L0_TH + 2) * (L0_TW + 2) + (size_t)9 * 2 * l0.C0 * c1pad + (size_t)64 * (c1pad + 1) + 16) * sizeof(float);
         if (c1pad <= 4) { auto k = l0_conva1_kernel<4>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(64), smem, s, l0); }
         else if (c1pad <= 16) { auto k = l0_conva1_kernel<8>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(64 * ((c1pad + 7) / 8)), smem, s, l0); }
         else if (c1pad <= 48) { auto k = l0_conva1_kernel<12>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(64 * ((c1pad + 11) / 12)), smem, s, l0); }
