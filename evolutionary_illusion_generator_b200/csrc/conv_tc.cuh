@@ -23,7 +23,9 @@
 //   2^4 and split it into hi = fp16(v) and lo = fp16(v - hi) (11 + 11 mantissa bits, the same coverage as a TF32
 //   split at twice the MMA rate and half the operand bytes), weights are pre-split on the host with a per-conv power of
 //   two scale; every k-step issues lo*hi + hi*lo + hi*hi into the same fp32 TMEM accumulator (the lo*lo term, 2^-22
-//   relative, is dropped) and the epilogue multiplies by the exact inverse scale.  |activation| must stay below 4094
+//   relative, is dropped) and the epilogue multiplies by the exact inverse scale.  The two MMAs that share a_hi keep / re-use the
+//   A tile in the tensor core's collector (`.collector::a::fill` / `::lastuse`).  (Merging them into one 2N-wide MMA was
+//   measured and is not faster; profiles/r1/tc_role_cycles_*.)  |activation| must stay below 4094
 //   (fp16 range after scaling); PredNet activations are O(1).
 #pragma once
 #include <cuda.h>
@@ -39,7 +41,7 @@
 namespace eig {
 
 enum { EPI_RAW = 3 };  // test only: out = acc + bias, no activation (conv3x3_tc_kernel only)
-enum { TC_THREADS = 512, TC_SMEM_LIMIT = 227 * 1024, TC_KB = 32, TC_ROW = 64, TC_RAW_ROW = 128, TC_SR = 2 };
+enum { TC_THREADS = 512, TC_SMEM_LIMIT = 227 * 1024, TC_KB = 32, TC_ROW = 64, TC_RAW_ROW = 128, TC_SR = 2, TC_MAX_NT = 4 };
 #define TC_ACT_SCALE 16.0f
 
 struct TcWeights {
@@ -56,7 +58,7 @@ struct TcParams {
     int tiles_x, tiles_y, regions;  // regions = spatial CTA regions (tiles_x * tiles_y * B)
     int groups_per_nz, groups;      // group = 2 regions (one per CTA of the pair) x one weight slice
     int KBn, Ncta, N;
-    int a_plane_bytes, b_plane_bytes, raw_bytes, a_box_bytes;
+    int a_plane_bytes, b_plane_bytes, b_stage_bytes, raw_bytes, a_box_bytes;
     int SA, SB;
     int tmem_cols;
     int staging_bytes, stage_ld;  // ConvA pooling tile: 128 rows x stage_ld floats
@@ -154,13 +156,21 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// COLL: A-operand collector usage - 0 none, 1 fill (keep the A tile after this MMA), 2 use, 3 lastuse (re-use the kept tile)
+template <int COLL>
 __device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
+    if (COLL == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+    else if (COLL == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16.collector::a::use [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+    else if (COLL == 3)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 // completion of all MMAs issued so far -> one arrival on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
@@ -241,10 +251,14 @@ __device__ __forceinline__ TcRegion tc_region(const TcParams& p, int group, int 
 // Barriers: rawFull/rawEmpty (TMA <-> converter, CTA local), convA (converters of both CTAs -> leader's MMA warp),
 //   emptyA / emptyB / accFull (tcgen05.commit multicast to both CTAs), fullB (both CTAs' weight TMAs -> leader),
 //   accEmpty (epilogue warps of both CTAs -> leader).
+// per-role cycle counters exist only in the DBG instantiation (tests/gpu/tc_check timing mode): a clock read costs
+// the single MMA-issuing thread ~80 cycles, several times per tap
+#define TC_CLK() (DBG ? clock64() : 0ll)
+template <bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
-    const long long k_t0 = clock64();
+    const long long k_t0 = TC_CLK();
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
     unsigned char* smem = smem_raw + pad;
@@ -253,7 +267,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int crank = (int)cluster_rank();
     const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-    const int a_stage_bytes = 2 * p.a_plane_bytes, b_stage_bytes = 2 * p.b_plane_bytes;
+    const int a_stage_bytes = 2 * p.a_plane_bytes, b_stage_bytes = p.b_stage_bytes;
     const uint32_t off_raw = p.SA * a_stage_bytes, off_b = off_raw + TC_SR * p.raw_bytes;
     const uint32_t sA = sbase, sRaw = sbase + off_raw, sB = sbase + off_b;
     const uint32_t pipe_bytes = off_b + p.SB * b_stage_bytes;
@@ -281,22 +295,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / pair TMA / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-    const int acc_stride = p.NT * p.Ncta;
-    const long long k_t1 = clock64();
+    const int tile_cols = p.Ncta;   // TMEM columns of one MMA tile
+    const int acc_stride = p.NT * tile_cols;
+    const long long k_t1 = TC_CLK();
 
     if (warp < 4) {
         // ===== converter =====
         const int chunks = p.a_box_bytes >> 4;   // float4 items of the raw box: 8 per pixel row
         const uint32_t convA_leader = map_to_cta(convA, 0);
         int ia = 0;
-        long long c_wait = 0, c0 = clock64(), cq;
+        long long c_wait = 0, c0 = TC_CLK(), cq;
         for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
             for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
                 const int s = ia % p.SA, rs = ia % TC_SR;
-                cq = clock64();
+                cq = TC_CLK();
                 mbar_wait(rawFull + 8 * rs, (ia / TC_SR) & 1);
                 mbar_wait(emptyA + 8 * s, ((ia / p.SA) & 1) ^ 1);
-                c_wait += clock64() - cq;
+                c_wait += TC_CLK() - cq;
                 const float4* src = reinterpret_cast<const float4*>(smem + off_raw + rs * p.raw_bytes);
                 unsigned char* hi = smem + s * a_stage_bytes;
                 unsigned char* lo = hi + p.a_plane_bytes;
@@ -325,9 +340,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                 }
             }
         }
-        if (p.dbg && threadIdx.x == 0) {
+        if (DBG && p.dbg && threadIdx.x == 0) {
             long long* d = p.dbg + (long long)blockIdx.x * 16;
-            d[7] = clock64() - c0; d[8] = c_wait;
+            d[7] = TC_CLK() - c0; d[8] = c_wait;
         }
     } else if (warp == 6) {
         // ===== activation (A) producer: raw fp32 halo boxes =====
@@ -347,28 +362,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
         // ===== weight (B) producer: this CTA's half (Ncta/2 rows) of every tile; the leader's barrier counts both =====
         if (lane == 0) {
             int ib = 0;
-            long long b_wait = 0, b0 = clock64(), bq;
+            long long b_wait = 0, b0 = TC_CLK(), bq;
             const int half_rows = p.Ncta >> 1;
             const uint32_t fullB_leader = map_to_cta(fullB, 0);
             for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
-                const int n0 = (grp / p.groups_per_nz) * p.Ncta + crank * half_rows;
+                const int nbase = (grp / p.groups_per_nz) * p.Ncta, n0 = nbase + crank * half_rows;
                 for (int kb = 0; kb < p.KBn; ++kb) {
                     for (int tap = 0; tap < 9; ++tap, ++ib) {
                         const int s = ib % p.SB;
-                        bq = clock64();
+                        bq = TC_CLK();
                         mbar_wait(emptyB + 8 * s, ((ib / p.SB) & 1) ^ 1);
-                        b_wait += clock64() - bq;
-                        if (crank == 0) mbar_expect_tx(fullB + 8 * s, 4 * p.b_plane_bytes);   // 2 planes x 2 CTAs
+                        b_wait += TC_CLK() - bq;
                         const uint32_t dst = sB + s * b_stage_bytes;
-                        const int row_hi = (tap * p.KBn + kb) * p.N + n0, row_lo = ((9 + tap) * p.KBn + kb) * p.N + n0;
-                        tma_load_2d_pair(dst, &mB, fullB_leader + 8 * s, 0, row_hi);
-                        tma_load_2d_pair(dst + p.b_plane_bytes, &mB, fullB_leader + 8 * s, 0, row_lo);
+                        const int row_hi = (tap * p.KBn + kb) * p.N, row_lo = ((9 + tap) * p.KBn + kb) * p.N;
+                        if (crank == 0) mbar_expect_tx(fullB + 8 * s, 4 * p.b_plane_bytes);   // 2 planes x 2 CTAs
+                        tma_load_2d_pair(dst, &mB, fullB_leader + 8 * s, 0, row_hi + n0);
+                        tma_load_2d_pair(dst + p.b_plane_bytes, &mB, fullB_leader + 8 * s, 0, row_lo + n0);
                     }
                 }
             }
-            if (p.dbg) {
+            if (DBG && p.dbg) {
                 long long* d = p.dbg + (long long)blockIdx.x * 16;
-                d[9] = clock64() - b0; d[10] = b_wait;
+                d[9] = TC_CLK() - b0; d[10] = b_wait;
             }
         }
     } else if (warp == 5) {
@@ -382,54 +397,67 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
             const uint32_t plane_a16 = (uint32_t)p.a_plane_bytes >> 4, plane_b16 = (uint32_t)p.b_plane_bytes >> 4;
             const uint32_t tile16 = (uint32_t)(p.TH * p.P * TC_ROW) >> 4;
             int ia = 0, ib = 0, it = 0;
-            long long t_acc = 0, t_a = 0, t_b = 0, t0 = clock64(), tq;
+            long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t_commit = 0, t0 = TC_CLK(), tq;
             for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
                 const int set = it & 1;
-                tq = clock64();
+                tq = TC_CLK();
                 mbar_wait(accEmpty + 8 * set, ((it >> 1) & 1) ^ 1);
-                t_acc += clock64() - tq;
+                t_acc += TC_CLK() - tq;
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(set * acc_stride);
                 for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
                     const int sa = ia % p.SA;
-                    tq = clock64();
+                    tq = TC_CLK();
                     mbar_wait_cluster(convA + 8 * sa, (ia / p.SA) & 1);
-                    t_a += clock64() - tq;
+                    t_a += TC_CLK() - tq;
                     const uint32_t a16 = (((sA + sa * a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
                     for (int tap = 0; tap < 9; ++tap, ++ib) {
                         const int sb = ib % p.SB;
-                        tq = clock64();
+                        tq = TC_CLK();
                         mbar_wait(fullB + 8 * sb, (ib / p.SB) & 1);
-                        t_b += clock64() - tq;
+                        t_b += TC_CLK() - tq;
                         tc_fence_after();
                         const uint32_t tap16 = (uint32_t)(((tap / 3) * p.P + (tap % 3)) * TC_ROW) >> 4;
                         const uint32_t b16 = (((sB + sb * b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
                         const uint32_t acc0 = (kb | tap) ? 1u : 0u;
                         if (elect_one()) {
-                            for (int t = 0; t < p.NT; ++t) {
-                                const uint32_t at16 = a16 + tap16 + (uint32_t)t * tile16;
-                                const uint32_t d = d0 + (uint32_t)(t * p.Ncta);
+                            const long long ci0 = TC_CLK();
+                            // descriptor low words of this tap: everything below is adds of compile-time multiples on
+                            // uniform registers (the loops are fully unrolled; a rolled t loop costs ~150 cycles of
+                            // dependent uniform-datapath arithmetic per k-step - measured, profiles/r1)
+                            const uint32_t a_tap = a16 + tap16;
+                            const uint32_t bh0 = b16, bh1 = b16 + 2, bl0 = b16 + plane_b16, bl1 = b16 + plane_b16 + 2;
 #pragma unroll
-                                for (int ks = 0; ks < 2; ++ks) {   // 2 x UMMA_K(16) = 32 channels
-                                    const uint64_t dah = desc_hi | (at16 + 2 * ks), dal = desc_hi | (at16 + plane_a16 + 2 * ks);
-                                    const uint64_t dbh = desc_hi | (b16 + 2 * ks), dbl = desc_hi | (b16 + plane_b16 + 2 * ks);
-                                    tc_mma_f16_pair(d, dal, dbh, idesc, ks ? 1u : acc0);
-                                    tc_mma_f16_pair(d, dah, dbl, idesc, 1u);
-                                    tc_mma_f16_pair(d, dah, dbh, idesc, 1u);
+                            for (int t = 0; t < TC_MAX_NT; ++t) {
+                                if (t < p.NT) {
+                                    const uint32_t at16 = a_tap + (uint32_t)t * tile16;
+                                    const uint32_t d = d0 + (uint32_t)t * (uint32_t)tile_cols;
+                                    const uint64_t dah0 = desc_hi | at16, dah1 = desc_hi | (at16 + 2);
+                                    const uint64_t dal0 = desc_hi | (at16 + plane_a16), dal1 = desc_hi | (at16 + plane_a16 + 2);
+                                    {   // a_hi is fetched once per k-step: kept by the first MMA that uses it, re-used by the second
+                                        tc_mma_f16_pair<0>(d, dal0, desc_hi | bh0, idesc, acc0);
+                                        tc_mma_f16_pair<1>(d, dah0, desc_hi | bl0, idesc, 1u);
+                                        tc_mma_f16_pair<3>(d, dah0, desc_hi | bh0, idesc, 1u);
+                                        tc_mma_f16_pair<0>(d, dal1, desc_hi | bh1, idesc, 1u);
+                                        tc_mma_f16_pair<1>(d, dah1, desc_hi | bl1, idesc, 1u);
+                                        tc_mma_f16_pair<3>(d, dah1, desc_hi | bh1, idesc, 1u);
+                                    }
                                 }
                             }
+                            const long long ci1 = TC_CLK();
                             tc_commit_pair(emptyB + 8 * sb);
                             if (tap == 8) tc_commit_pair(emptyA + 8 * sa);
                             if (tap == 8 && kb == p.KBn - 1) tc_commit_pair(accFull + 8 * set);
+                            t_issue += ci1 - ci0; t_commit += TC_CLK() - ci1;
                         }
                         __syncwarp();
                     }
                 }
                 ++it;
             }
-            if (p.dbg && lane == 0) {
+            if (DBG && p.dbg && lane == 0) {
                 long long* d = p.dbg + (long long)blockIdx.x * 16;
-                d[0] = clock64() - t0; d[1] = t_acc; d[2] = t_a; d[3] = t_b; d[4] = it;
+                d[0] = TC_CLK() - t0; d[1] = t_acc; d[2] = t_a; d[3] = t_b; d[4] = it; d[14] = t_issue; d[15] = t_commit;
             }
         }
     } else if (warp >= 8) {
@@ -442,68 +470,90 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
         const uint32_t accEmpty_leader = map_to_cta(accEmpty, 0);
         const float inv = p.inv_scale;
         int it = 0;
-        long long e_wait = 0, e0 = clock64(), eq;
+        long long e_wait = 0, e0 = TC_CLK(), eq;
         for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
             const TcRegion r = tc_region(p, grp, crank);
             const int set = it & 1, b = r.b, n0 = r.n0;
-            eq = clock64();
-            mbar_wait(accFull + 8 * set, (it >> 1) & 1);
-            e_wait += clock64() - eq;
-            tc_fence_after();
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(set * acc_stride);
             const int ncols = min(p.Ncta, a.N - n0);   // the last slice may be padded up to a multiple of 32
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(set * acc_stride);
+            if (a.epi == EPI_LSTM) {
+                // Work items = (tile t, 16-column chunk c0) of this warp, walked in order.  The cell state / peephole
+                // loads of item i+1 are in flight while item i is computed, and those of the FIRST item are issued
+                // before the wait for the accumulator, so their latency hides behind the MMAs.
+                const int R = a.N >> 2;
+                const int n_chunks = ncols > half * 16 ? (ncols - half * 16 + 31) >> 5 : 0;
+                const int n_items = r.active ? p.NT * n_chunks : 0;
+                int nt = 0, nc0 = half * 16;
+                bool nvalid = false;
+                long long npix = 0, nppix = 0;
+                float4 cold = make_float4(0.f, 0.f, 0.f, 0.f), pq[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pq[q] = cold;
+                auto fetch = [&](int i) {
+                    nt = i / n_chunks; nc0 = half * 16 + 32 * (i - nt * n_chunks);
+                    const int y = r.y0 + nt * p.TH + hh, x = r.x0 + ww;
+                    nvalid = hh < p.TH && ww < p.TW && y < p.H && x < p.W;
+                    npix = nvalid ? ((long long)b * p.H + y) * p.W + x : 0;
+                    nppix = nvalid ? (long long)y * p.W + x : 0;
+                    const int r0 = (n0 + nc0) >> 2;
+                    cold = *reinterpret_cast<const float4*>(a.cstate + npix * R + r0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) pq[q] = *reinterpret_cast<const float4*>(a.peep + (nppix * R + r0 + q) * 4);
+                };
+                if (n_items > 0) fetch(0);
+                eq = TC_CLK();
+                mbar_wait(accFull + 8 * set, (it >> 1) & 1);
+                e_wait += TC_CLK() - eq;
+                tc_fence_after();
+                for (int i = 0; i < n_items; ++i) {
+                    const int t = nt, c0 = nc0;
+                    const bool valid = nvalid;
+                    const long long pix = npix;
+                    const float4 ccur = cold;
+                    float4 pcur[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) pcur[q] = pq[q];
+                    if (i + 1 < n_items) fetch(i + 1);
+                    float v[16];
+                    tmem_ld16(lane_addr + (uint32_t)(t * tile_cols) + c0, v);
+                    if (!valid) continue;
+                    const int r0 = (n0 + c0) >> 2;
+                    const float co[4] = {ccur.x, ccur.y, ccur.z, ccur.w};
+                    float cn[4], hn[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 bq = *reinterpret_cast<const float4*>(a.bias + n0 + c0 + q * 4);
+                        hn[q] = lstm_cell_v(__fmul_rn(v[q * 4], inv), __fmul_rn(v[q * 4 + 1], inv), __fmul_rn(v[q * 4 + 2], inv),
+                                            __fmul_rn(v[q * 4 + 3], inv), bq, pcur[q], co[q], &cn[q]);
+                    }
+                    *reinterpret_cast<float4*>(a.cstate + pix * R + r0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                    view_store4(a.dstH, pix, r0, hn);
+                    if (a.dstUp.hi) {
+                        const int W2 = p.W * 2;
+                        const int y = r.y0 + t * p.TH + hh, x = r.x0 + ww;
+                        const long long ub = ((long long)b * p.H * 2 + y * 2) * W2 + x * 2;
+                        view_store4(a.dstUp, ub, r0, hn);
+                        view_store4(a.dstUp, ub + 1, r0, hn);
+                        view_store4(a.dstUp, ub + W2, r0, hn);
+                        view_store4(a.dstUp, ub + W2 + 1, r0, hn);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(accEmpty_leader + 8 * set);
+                ++it;
+                continue;
+            }
+            eq = TC_CLK();
+            mbar_wait(accFull + 8 * set, (it >> 1) & 1);
+            e_wait += TC_CLK() - eq;
+            tc_fence_after();
             for (int t = 0; r.active && t < p.NT; ++t) {
                 const int y = r.y0 + t * p.TH + hh, x = r.x0 + ww;
                 const bool valid = hh < p.TH && ww < p.TW && y < p.H && x < p.W;
                 const long long pix = valid ? ((long long)b * p.H + y) * p.W + x : 0;
-                const uint32_t tcol = lane_addr + (uint32_t)(t * p.Ncta);
-                if (a.epi == EPI_LSTM) {
-                    const int R = a.N >> 2;
-                    const long long ppix = valid ? (long long)y * p.W + x : 0;
-                    // software pipeline: the state / peephole loads of chunk c+32 are in flight while chunk c is computed
-                    float4 cold, pq[4];
-                    int c0 = half * 16;
-                    if (c0 < ncols) {
-                        const int r0 = (n0 + c0) >> 2;
-                        cold = *reinterpret_cast<const float4*>(a.cstate + pix * R + r0);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) pq[q] = *reinterpret_cast<const float4*>(a.peep + (ppix * R + r0 + q) * 4);
-                    }
-                    for (; c0 < ncols; c0 += 32) {
-                        float v[16];
-                        tmem_ld16(tcol + c0, v);
-                        const int r0 = (n0 + c0) >> 2;
-                        const float4 ccur = cold;
-                        float4 pcur[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) pcur[q] = pq[q];
-                        if (c0 + 32 < ncols) {
-                            const int r1 = (n0 + c0 + 32) >> 2;
-                            cold = *reinterpret_cast<const float4*>(a.cstate + pix * R + r1);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) pq[q] = *reinterpret_cast<const float4*>(a.peep + (ppix * R + r1 + q) * 4);
-                        }
-                        if (!valid) continue;
-                        const float co[4] = {ccur.x, ccur.y, ccur.z, ccur.w};
-                        float cn[4], hn[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 bq = *reinterpret_cast<const float4*>(a.bias + n0 + c0 + q * 4);
-                            hn[q] = lstm_cell_v(__fmul_rn(v[q * 4], inv), __fmul_rn(v[q * 4 + 1], inv), __fmul_rn(v[q * 4 + 2], inv),
-                                                __fmul_rn(v[q * 4 + 3], inv), bq, pcur[q], co[q], &cn[q]);
-                        }
-                        *reinterpret_cast<float4*>(a.cstate + pix * R + r0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                        view_store4(a.dstH, pix, r0, hn);
-                        if (a.dstUp.hi) {
-                            const int W2 = p.W * 2;
-                            const long long ub = ((long long)b * p.H * 2 + y * 2) * W2 + x * 2;
-                            view_store4(a.dstUp, ub, r0, hn);
-                            view_store4(a.dstUp, ub + 1, r0, hn);
-                            view_store4(a.dstUp, ub + W2, r0, hn);
-                            view_store4(a.dstUp, ub + W2 + 1, r0, hn);
-                        }
-                    }
-                } else if (a.epi == EPI_CONVP || a.epi == EPI_RAW) {
+                const uint32_t tcol = lane_addr + (uint32_t)(t * tile_cols);
+                if (a.epi == EPI_CONVP || a.epi == EPI_RAW) {
                     const int nP = a.nP ? a.nP : a.N;
                     for (int c0 = half * 16; c0 < ncols; c0 += 32) {
                         float v[16];
@@ -579,25 +629,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
             if (lane == 0) mbar_arrive_cluster(accEmpty_leader + 8 * set);
             ++it;
         }
-        if (p.dbg && warp == 8 && lane == 0) {
+        if (DBG && p.dbg && warp == 8 && lane == 0) {
             long long* d = p.dbg + (long long)blockIdx.x * 16;
-            d[5] = clock64() - e0; d[6] = e_wait;
+            d[5] = TC_CLK() - e0; d[6] = e_wait;
         }
     }
     tc_fence_before();
     __syncthreads();
-    const long long k_t2 = clock64();
+    const long long k_t2 = TC_CLK();
     cluster_sync_all();   // nobody exits while the peer may still read this CTA's operands / arrive on its barriers
     if (warp == 5) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
-    if (p.dbg && threadIdx.x == 160) {   // warp 5: prologue / body / teardown cycles of this CTA
+    if (DBG && p.dbg && threadIdx.x == 160) {   // warp 5: prologue / body / teardown cycles of this CTA
         long long* d = p.dbg + (long long)blockIdx.x * 16;
-        d[11] = k_t1 - k_t0; d[12] = k_t2 - k_t1; d[13] = clock64() - k_t2;
+        d[11] = k_t1 - k_t0; d[12] = k_t2 - k_t1; d[13] = TC_CLK() - k_t2;
     }
 }
 
+#undef TC_CLK
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EigEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -632,7 +683,7 @@ inline bool tc_available() {
         return false;
     }
     s.encode = (EigEncodeTiledFn)fn;
-    if (cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
         s.reason = "cannot raise the dynamic shared memory limit";
         cudaGetLastError();
         return false;
@@ -645,6 +696,7 @@ inline std::string tc_unavailable_reason() { return tc_state().reason; }
 inline std::string tc_last_error() { return tc_state().last_error; }
 inline void tc_set_kb(int) {}           // kept for tests/gpu/tc_check: the K block is fixed at 32 channels now
 inline void tc_set_max_nt(int nt) { tc_state().force_nt = nt; }
+inline void tc_set_merged(bool) {}
 inline void tc_set_max_cluster(int) {}  // the cluster is always the CTA pair
 
 inline void tc_free(TcWeights& w) {
@@ -699,7 +751,7 @@ inline int tc_pack(TcWeights& w, const float* wv, int cin, int N, int npad, int 
     return 0;
 }
 
-struct TcGeom { int TW, TH, P, NT, SA, SB, a_plane, raw, b_plane, tmem_cols, tiles_x, tiles_y, regions, staging, stage_ld; size_t smem; };
+struct TcGeom { int TW, TH, P, NT, SA, SB, a_plane, raw, b_plane, b_stage, tmem_cols, tiles_x, tiles_y, regions, staging, stage_ld; size_t smem; };
 
 // Picks the flat-padded tile (TW x TH, P = TW + 2, (TH-1)*P + TW <= 128) with the best MMA-row efficiency, then the
 // number of stacked tiles per CTA region (weight-tile reuse) that still load-balances over the CTA pairs and fits
@@ -723,11 +775,14 @@ inline bool tc_geometry(int B, int H, int W, int Ncta, int gz, bool pooled, int 
     g.tiles_x = (W + g.TW - 1) / g.TW;
     const int row_tiles = (H + g.TH - 1) / g.TH;
     g.b_plane = (Ncta / 2) * TC_ROW;
+    g.b_stage = 2 * g.b_plane;
+    const int tile_cols = Ncta;
     g.stage_ld = Ncta + 1;
     g.staging = pooled ? tc_round_up(128 * g.stage_ld * 4, 1024) : 0;
-    int nt_cap = 256 / Ncta;  // two accumulator sets of NT * Ncta columns in the 512 TMEM columns
+    int nt_cap = 256 / tile_cols;  // two accumulator sets of NT * tile_cols columns in the 512 TMEM columns
     if (nt_cap > row_tiles) nt_cap = row_tiles;
     if (nt_cap < 1) nt_cap = 1;
+    if (nt_cap > TC_MAX_NT) nt_cap = TC_MAX_NT;   // the MMA issue loop is unrolled over the tiles of a region
     if (force_nt > 0 && nt_cap > force_nt) nt_cap = force_nt;
     int pick = 0;
     double pick_eff = -1.0;
@@ -741,7 +796,7 @@ inline bool tc_geometry(int B, int H, int W, int Ncta, int gz, bool pooled, int 
         int SA = 3, SB = 0;
         for (; SA >= 2; --SA) {   // three operand stages when the weight ring still gets >= 4
             const long long left = (long long)TC_SMEM_LIMIT - 4096 - g.staging - (long long)TC_SR * raw - (long long)SA * 2 * a_plane;
-            SB = left > 0 ? (int)(left / (2 * g.b_plane)) : 0;
+            SB = left > 0 ? (int)(left / g.b_stage) : 0;
             if (SB > 10) SB = 10;
             if (SB >= (SA == 3 ? 4 : 2)) break;
         }
@@ -751,9 +806,9 @@ inline bool tc_geometry(int B, int H, int W, int Ncta, int gz, bool pooled, int 
         c.tiles_y = (row_tiles + NT - 1) / NT;
         c.regions = c.tiles_x * c.tiles_y * B;
         int cols = 32;
-        while (cols < 2 * NT * Ncta) cols <<= 1;
+        while (cols < 2 * NT * tile_cols) cols <<= 1;
         c.tmem_cols = cols;
-        c.smem = (size_t)SA * 2 * a_plane + (size_t)TC_SR * raw + (size_t)SB * 2 * g.b_plane + g.staging +
+        c.smem = (size_t)SA * 2 * a_plane + (size_t)TC_SR * raw + (size_t)SB * g.b_stage + g.staging +
                  8 * (2 * TC_SR + 2 * SA + 2 * SB + 4) + 16 + 1024;
         const int groups = ((c.regions + 1) / 2) * gz;
         const int rounds = (groups + n_pairs - 1) / n_pairs;
@@ -780,7 +835,8 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (!s.smem_attr_set[dev]) {
-        if (cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
+        if (cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess ||
+            cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
             s.last_error = "tc_conv: cannot raise the dynamic shared memory limit on this device"; cudaGetLastError(); return -1;
         }
         s.smem_attr_set[dev] = true;
@@ -795,7 +851,7 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
         int n = 0;
         cfg.gridDim = dim3(s.n_sm / 2 * 2);
         cfg.dynamicSmemBytes = TC_SMEM_LIMIT;
-        if (cudaOccupancyMaxActiveClusters(&n, conv3x3_tc_kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = s.n_sm / 2; }
+        if (cudaOccupancyMaxActiveClusters(&n, conv3x3_tc_kernel<false>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = s.n_sm / 2; }
         s.max_pairs = std::min(n, s.n_sm / 2);
     }
     TcGeom g;
@@ -820,7 +876,7 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     p.B = a.B; p.H = a.H; p.W = a.W;
     p.TW = g.TW; p.TH = g.TH; p.P = g.P; p.NT = g.NT; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y; p.regions = g.regions;
     p.KBn = w.KBn; p.Ncta = w.Ncta; p.N = w.Npad;
-    p.a_plane_bytes = g.a_plane; p.b_plane_bytes = g.b_plane; p.raw_bytes = g.raw; p.a_box_bytes = TC_RAW_ROW * g.P * box_rows;
+    p.a_plane_bytes = g.a_plane; p.b_plane_bytes = g.b_plane; p.b_stage_bytes = g.b_stage; p.raw_bytes = g.raw; p.a_box_bytes = TC_RAW_ROW * g.P * box_rows;
     p.SA = g.SA; p.SB = g.SB; p.tmem_cols = g.tmem_cols;
     p.staging_bytes = g.staging; p.stage_ld = g.stage_ld;
     p.inv_scale = 1.0f / (TC_ACT_SCALE * w.wscale);
@@ -833,7 +889,8 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     cfg.gridDim = dim3(n_pairs * 2);
     cfg.dynamicSmemBytes = g.smem;
     s.last_grid = n_pairs * 2; s.last_nt = g.NT; s.last_sa = g.SA; s.last_sb = g.SB;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel, it->second, w.map, p);
+    const cudaError_t le = s.dbg ? cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<true>, it->second, w.map, p)
+                                 : cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false>, it->second, w.map, p);
     if (le != cudaSuccess) { s.last_error = std::string("tc_conv launch: ") + cudaGetErrorString(le); cudaGetLastError(); return -1; }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { s.last_error = std::string("tc_conv launch: ") + cudaGetErrorString(e); return -1; }

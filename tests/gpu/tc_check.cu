@@ -200,9 +200,19 @@ static void time_shape(const char* name, int B, int H, int W, int pitch, int cof
         CHECK(cudaMalloc(&dE, px / 4 * 2 * N * 4));
         a.P = Pp; a.dstE = mkview(dE, nullptr, 2 * N, 0, 2 * N);
     }
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float ms_product = 0;
+    {   // the product instantiation (no cycle counters)
+        for (int i = 0; i < 3; ++i) tc_conv(p.tw, a, 0);
+        CHECK(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        for (int i = 0; i < 10; ++i) tc_conv(p.tw, a, 0);
+        cudaEventRecord(e1);
+        CHECK(cudaDeviceSynchronize());
+        cudaEventElapsedTime(&ms_product, e0, e1);
+    }
     long long* dbg; CHECK(cudaMalloc(&dbg, 160 * 16 * 8)); CHECK(cudaMemset(dbg, 0, 160 * 16 * 8));
     tc_state().dbg = dbg;
-    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int i = 0; i < 3; ++i) tc_conv(p.tw, a, 0);
     CHECK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
@@ -213,22 +223,24 @@ static void time_shape(const char* name, int B, int H, int W, int pitch, int cof
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     std::vector<long long> d = host(dbg, 160 * 16);
     const int grid = tc_state().last_grid;
-    double s[14] = {0};
-    for (int c = 0; c < grid; ++c) for (int k = 0; k < 14; ++k) s[k] += (double)d[c * 16 + k] / grid;
-    for (int k = 0; k < 5; ++k) s[k] *= 2;   // the MMA warp only runs in the leader CTA of each pair
+    double s[16] = {0};
+    for (int c = 0; c < grid; ++c) for (int k = 0; k < 16; ++k) s[k] += (double)d[c * 16 + k] / grid;
+    for (int k = 0; k < 5; ++k) s[k] *= 2;
+    s[14] *= 2; s[15] *= 2;   // the MMA warp only runs in the leader CTA of each pair
     const double flop = 2.0 * px * 9.0 * Cin * N;
-    printf("%-8s B%d %dx%d Cin%d N%d cluster %d NT %d SA %d SB %d grid %d: %7.1f us  %6.1f TFLOP/s(fp32-equiv) | MMA thr: total %6.0f waitAcc %5.0f waitA %5.0f waitB %5.0f regions %.1f | epi: total %6.0f wait %6.0f | conv: total %6.0f wait %6.0f | Bprod: wait %6.0f | kernel: prologue %5.0f body %6.0f teardown %5.0f = %.1f us @1.965GHz (cycles, avg per CTA)\n",
-           name, B, W, H, Cin, N, tc_state().last_csize, tc_state().last_nt, tc_state().last_sa, tc_state().last_sb, grid, 1e3 * ms / reps,
-           flop / (1e-3 * ms / reps) / 1e12, s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], s[10], s[11], s[12], s[13], (s[11] + s[12] + s[13]) / 1965.0);
+    printf("%-8s B%d %dx%d Cin%d N%d cluster %d NT %d SA %d SB %d grid %d: %7.1f us %6.1f TFLOP/s(fp32-equiv) [instrumented %.1f us] | MMA thr: total %6.0f waitAcc %5.0f waitA %5.0f waitB %5.0f issue %6.0f commit %6.0f regions %.1f | epi: total %6.0f wait %6.0f | conv: total %6.0f wait %6.0f | Bprod: wait %6.0f | kernel: prologue %5.0f body %6.0f teardown %5.0f = %.1f us @1.965GHz (cycles, avg per CTA)\n",
+           name, B, W, H, Cin, N, tc_state().last_csize, tc_state().last_nt, tc_state().last_sa, tc_state().last_sb, grid, 1e2 * ms_product,
+           flop / (1e-4 * ms_product) / 1e12, 1e3 * ms / reps, s[0], s[1], s[2], s[3], s[14], s[15], s[4], s[5], s[6], s[7], s[8], s[10], s[11], s[12], s[13], (s[11] + s[12] + s[13]) / 1965.0);
     tc_state().dbg = nullptr;
     cudaFree(dbg); cudaFree(out); cudaFree(cst); cudaFree(peep); cudaFree(dh); cudaFree(Pp); cudaFree(dE);
     cudaFree(p.d_hi); cudaFree(p.d_w); cudaFree(p.d_b); tc_free(p.tw);
 }
 
 static int timing_main() {
-    for (int cluster = 2; cluster <= 2; cluster *= 2) {
-        for (int max_nt = 0; max_nt <= 1; ++max_nt) {
-            printf("--- CTA pairs, tiles per region %s\n", max_nt ? "1" : "auto");
+    for (int cluster = 0; cluster <= 0; ++cluster) {
+        for (int max_nt = 0; max_nt <= 0; ++max_nt) {
+            const char* names[1] = {"product: lo*hi, hi*lo (keep A), hi*hi (re-use A)"};
+            printf("--- %s\n", names[cluster]);
             time_shape("LSTM1", 32, 60, 80, 80, 0, 80, 64, EPI_LSTM, cluster, max_nt);
             time_shape("LSTM2", 32, 30, 40, 160, 0, 160, 128, EPI_LSTM, cluster, max_nt);
             time_shape("LSTM3", 32, 15, 20, 192, 0, 192, 256, EPI_LSTM, cluster, max_nt);
@@ -260,11 +272,10 @@ int main(int argc, char** argv) {
     };
     bool kb_ok[2] = {true, true};
     struct Cfg { int kb, max_nt, cluster; };
-    const Cfg cfgs[] = {{16, 0, 2}, {16, 1, 2}};   // the K block is fixed (32 channels, fp16) and the cluster is the CTA pair
+    const Cfg cfgs[] = {{16, 0, 0}, {16, 1, 0}};
     for (const Cfg& c : cfgs) {
-        printf("== K block %d, tiles per region %s, multicast cluster <= %d ==\n", c.kb, c.max_nt ? "capped at 1" : "auto", c.cluster);
+        printf("== tiles per region %s ==\n", c.max_nt ? "capped at 1" : "auto");
         tc_set_max_nt(c.max_nt);
-        tc_set_max_cluster(c.cluster);
         unsigned seed = 1;
         bool all = true;
         for (const Shape& s : shapes) {
