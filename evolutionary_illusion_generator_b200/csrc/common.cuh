@@ -17,44 +17,81 @@ struct LaunchCounter { long long n; };
 inline LaunchCounter& launch_counter() { static LaunchCounter c{0}; return c; }
 #define EIG_COUNT_LAUNCH() (++::eig::launch_counter().n)
 
-// View of an NHWC fp32 activation tensor living inside a wider "concat" buffer.
-// When `lo` is non-null the value is stored split for the 3xTF32 tensor-core path:
-// hi = tf32-rounded value, lo = value - hi (exact), so hi + lo reconstructs the fp32 value bit-exactly.
+// View of an NHWC activation tensor living inside a wider "concat" buffer.
+//   lo == nullptr : plain fp32 at `hi` (exact-fp32 SIMT mode).
+//   lo != nullptr : SPLIT-FP16 storage for the tensor-core path: `hi` and `lo` point to two fp16 planes of the same
+//                   geometry holding hi = fp16(16 v) and lo = fp16(16 v - hi), i.e. 22 significant bits of v in the same
+//                   4 bytes per element.  The planes are exactly the MMA operands (conv_tc.cuh loads them with TMA
+//                   straight into swizzled shared memory); every other reader uses view_load (value = (hi + lo) / 16).
 struct View {
     float* hi;
     float* lo;
-    int pitch;  // floats per pixel of the underlying buffer
+    int pitch;  // elements per pixel of the underlying buffer
     int coff;   // first channel of this view
     int C;      // channels in this view
 };
 
-__device__ __forceinline__ float tf32_round(float v) {
+typedef unsigned short h16;   // raw IEEE binary16 bits
+#define EIG_ACT_SCALE 16.0f
+#define EIG_ACT_INV 0.0625f
+
 #ifdef EIG_EMU
-    unsigned u = __float_as_uint(v);
-    u = (u + 0x1000u) & ~0x1fffu;
-    return __uint_as_float(u);
-#else
-    unsigned u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-    return __uint_as_float(u);
-#endif
+// software binary16 conversions for the g++ kernel-source emulator (round to nearest even, subnormals, inf)
+inline h16 f2h(float f) {
+    unsigned x;
+    memcpy(&x, &f, 4);
+    const unsigned sign = (x >> 16) & 0x8000u;
+    x &= 0x7fffffffu;
+    if (x >= 0x7f800000u) return (h16)(sign | (x > 0x7f800000u ? 0x7e00u : 0x7c00u));
+    if (x >= 0x477ff000u) return (h16)(sign | 0x7c00u);   // >= 65520 rounds to infinity
+    if (x < 0x38800000u) {                                // below 2^-14: subnormal half (or zero)
+        float af;
+        memcpy(&af, &x, 4);
+        return (h16)(sign | (unsigned)lrintf(af * 16777216.0f));
+    }
+    const unsigned mant = x & 0x7fffffu, ex = (x >> 23) - 112u;
+    unsigned h = (ex << 10) | (mant >> 13);
+    const unsigned rem = mant & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+    return (h16)(sign | h);
 }
+inline float h2f(h16 h) {
+    const unsigned sign = ((unsigned)h & 0x8000u) << 16, ex = (h >> 10) & 0x1fu, mant = h & 0x3ffu;
+    float r;
+    if (ex == 0) r = ldexpf((float)mant, -24);
+    else if (ex == 31) r = mant ? NAN : INFINITY;
+    else r = ldexpf((float)(mant | 0x400u), (int)ex - 25);
+    unsigned u;
+    memcpy(&u, &r, 4);
+    u |= sign;
+    memcpy(&r, &u, 4);
+    return r;
+}
+#else
+}  // namespace eig
+#include <cuda_fp16.h>
+namespace eig {
+__host__ __device__ __forceinline__ h16 f2h(float f) { return __half_as_ushort(__float2half_rn(f)); }
+__host__ __device__ __forceinline__ float h2f(h16 h) { return __half2float(__ushort_as_half(h)); }
+#endif
+
+__host__ __device__ __forceinline__ void split16(float v, h16* h, h16* l) {
+    const float x = v * EIG_ACT_SCALE;        // exact (power of two)
+    const h16 hh = f2h(x);
+    *h = hh;
+    *l = f2h(x - h2f(hh));                    // the difference is exact in fp32
+}
+__host__ __device__ __forceinline__ float join16(h16 h, h16 l) { return (h2f(h) + h2f(l)) * EIG_ACT_INV; }   // exact sum
 
 __device__ __forceinline__ void view_store(const View& v, long long pix, int c, float val) {
-    long long idx = pix * v.pitch + v.coff + c;
-    if (v.lo) {
-        float h = tf32_round(val);
-        v.hi[idx] = h;
-        v.lo[idx] = __fsub_rn(val, h);
-    } else {
-        v.hi[idx] = val;
-    }
+    const long long idx = pix * v.pitch + v.coff + c;
+    if (v.lo) split16(val, reinterpret_cast<h16*>(v.hi) + idx, reinterpret_cast<h16*>(v.lo) + idx);
+    else v.hi[idx] = val;
 }
 
 __device__ __forceinline__ float view_load(const float* hi, const float* lo, long long idx) {
-    float v = hi[idx];
-    if (lo) v = __fadd_rn(v, lo[idx]);
-    return v;
+    if (lo) return join16(reinterpret_cast<const h16*>(hi)[idx], reinterpret_cast<const h16*>(lo)[idx]);
+    return hi[idx];
 }
 
 }  // namespace eig

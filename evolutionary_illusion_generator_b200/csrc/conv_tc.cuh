@@ -19,10 +19,11 @@
 //   128-255 from the peer's); each CTA stages only HALF of every weight tile (N/2 rows), so a CTA reads
 //   (128 + N/2) operand rows per MMA instead of (128 + N) - measured on B200 the tensor pipe in SS mode is paced by
 //   those shared-memory operand reads (~64 B/clk), not by the math (profiles/r1).
-// Split precision ("3 x fp16"): activations live in HBM as plain fp32; the converter warps scale each staged box by
-//   2^4 and split it into hi = fp16(v) and lo = fp16(v - hi) (11 + 11 mantissa bits, the same coverage as a TF32
-//   split at twice the MMA rate and half the operand bytes), weights are pre-split on the host with a per-conv power of
-//   two scale; every k-step issues lo*hi + hi*lo + hi*hi into the same fp32 TMEM accumulator (the lo*lo term, 2^-22
+// Split precision ("3 x fp16"): activations live in HBM ALREADY SPLIT (common.cuh View: two fp16 planes holding
+//   hi = fp16(16 v) and lo = fp16(16 v - hi), 11 + 11 mantissa bits in the 4 bytes an fp32 would take - the same coverage
+//   as a TF32 split at twice the MMA rate and half the operand bytes); the producing epilogues write that format, so the
+//   TMA loads ARE the MMA operands: no conversion pass, no staging copy.  Weights are pre-split on the host with a
+//   per-conv power of two scale; every k-step issues lo*hi + hi*lo + hi*hi into the same fp32 TMEM accumulator (the lo*lo term, 2^-22
 //   relative, is dropped) and the epilogue multiplies by the exact inverse scale.  The two MMAs that share a_hi keep / re-use the
 //   A tile in the tensor core's collector (`.collector::a::fill` / `::lastuse`).  (Merging them into one 2N-wide MMA was
 //   measured and is not faster; profiles/r1/tc_role_cycles_*.)  |activation| must stay below 4094
@@ -41,8 +42,7 @@
 namespace eig {
 
 enum { EPI_RAW = 3 };  // test only: out = acc + bias, no activation (conv3x3_tc_kernel only)
-enum { TC_THREADS = 512, TC_SMEM_LIMIT = 227 * 1024, TC_KB = 32, TC_ROW = 64, TC_RAW_ROW = 128, TC_SR = 2, TC_MAX_NT = 4 };
-#define TC_ACT_SCALE 16.0f
+enum { TC_THREADS = 512, TC_SMEM_LIMIT = 227 * 1024, TC_KB = 32, TC_ROW = 64, TC_MAX_NT = 4 };
 
 struct TcWeights {
     __half* d = nullptr;  // [2 planes][9 taps][KBn][Npad][32] fp16 (hi plane, then lo plane), scaled by wscale
@@ -58,7 +58,7 @@ struct TcParams {
     int tiles_x, tiles_y, regions;  // regions = spatial CTA regions (tiles_x * tiles_y * B)
     int groups_per_nz, groups;      // group = 2 regions (one per CTA of the pair) x one weight slice
     int KBn, Ncta, N;
-    int a_plane_bytes, b_plane_bytes, b_stage_bytes, raw_bytes, a_box_bytes;
+    int a_plane_bytes, b_plane_bytes, b_stage_bytes, a_box_bytes;
     int SA, SB;
     int tmem_cols;
     int staging_bytes, stage_ld;  // ConvA pooling tile: 128 rows x stage_ld floats
@@ -130,6 +130,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"((unsigned long long)map), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 // pair load: the bytes land in THIS CTA's shared memory, the transaction count is credited to `cluster_bar`, which may
 // live in the leader CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
@@ -199,9 +205,20 @@ __device__ __forceinline__ float lstm_cell_v(float gi, float gf, float gc, float
 
 __device__ __forceinline__ void view_store4(const View& v, long long pix, int c, const float* val) {
     const long long idx = pix * v.pitch + v.coff + c;
-    if ((v.pitch | v.coff) & 3) {  // not 16-byte aligned
+    if ((v.pitch | v.coff) & 3) {  // not vector aligned
 #pragma unroll
         for (int i = 0; i < 4; ++i) view_store(v, pix, c + i, val[i]);
+        return;
+    }
+    if (v.lo) {   // split-fp16 planes: 4 halves = 8 bytes per plane
+        h16 h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split16(val[i], &h[i], &l[i]);
+        uint2 uh, ul;
+        uh.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16); uh.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
+        ul.x = (uint32_t)l[0] | ((uint32_t)l[1] << 16); ul.y = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
+        *reinterpret_cast<uint2*>(reinterpret_cast<h16*>(v.hi) + idx) = uh;
+        *reinterpret_cast<uint2*>(reinterpret_cast<h16*>(v.lo) + idx) = ul;
         return;
     }
     *reinterpret_cast<float4*>(v.hi + idx) = make_float4(val[0], val[1], val[2], val[3]);
@@ -241,22 +258,21 @@ __device__ __forceinline__ TcRegion tc_region(const TcParams& p, int group, int 
 }
 
 // Persistent, warp-specialised: grid = 2 * min(groups, #SM / 2) CTAs of 512 threads in clusters of 2.
-//   warps 0-3   converter: raw fp32 halo box (TMA) -> hi / lo fp16 operand planes (SWIZZLE_64B layout written by hand)
+//   warps 0-3   idle (the in-kernel fp32 -> fp16 converter of earlier versions is gone: operands arrive split from HBM)
 //   warp  4     weight producer (one thread): this CTA's half of every per-tap weight tile, hi and lo planes
 //   warp  5     TMEM allocator; in the leader CTA also the MMA issuer (one elected thread) for BOTH CTAs
-//   warp  6     activation producer (one thread): one raw halo box per channel block into a 2-deep ring
+//   warp  6     activation producer (one thread): the hi and lo halo boxes of each channel block, SA stages ahead
 //   warp  7     idle
 //   warps 8-15  epilogue (TMEM lane quarter = warp & 3, column half = (warp - 8) >> 2): drains accumulator set i
 //               while set i^1 is being computed
-// Barriers: rawFull/rawEmpty (TMA <-> converter, CTA local), convA (converters of both CTAs -> leader's MMA warp),
-//   emptyA / emptyB / accFull (tcgen05.commit multicast to both CTAs), fullB (both CTAs' weight TMAs -> leader),
-//   accEmpty (epilogue warps of both CTAs -> leader).
-// per-role cycle counters exist only in the DBG instantiation (tests/gpu/tc_check timing mode): a clock read costs
-// the single MMA-issuing thread ~80 cycles, several times per tap
+// Barriers: fullA / fullB (TMA transactions of BOTH CTAs -> the leader's MMA warp), emptyA / emptyB / accFull
+//   (tcgen05.commit multicast to both CTAs), accEmpty (epilogue warps of both CTAs -> leader).
+// per-role cycle counters exist only in the DBG instantiation (tests/gpu/tc_check timing mode)
 #define TC_CLK() (DBG ? clock64() : 0ll)
 template <bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, const TcParams p) {
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+                  const __grid_constant__ CUtensorMap mB, const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
     const long long k_t0 = TC_CLK();
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -268,20 +284,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     const int crank = (int)cluster_rank();
     const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     const int a_stage_bytes = 2 * p.a_plane_bytes, b_stage_bytes = p.b_stage_bytes;
-    const uint32_t off_raw = p.SA * a_stage_bytes, off_b = off_raw + TC_SR * p.raw_bytes;
-    const uint32_t sA = sbase, sRaw = sbase + off_raw, sB = sbase + off_b;
+    const uint32_t off_b = p.SA * a_stage_bytes;
+    const uint32_t sA = sbase, sB = sbase + off_b;
     const uint32_t pipe_bytes = off_b + p.SB * b_stage_bytes;
     float* stage = reinterpret_cast<float*>(smem + pipe_bytes);
     const uint32_t sBar = sbase + pipe_bytes + p.staging_bytes;
-    // barriers: rawFull[SR] rawEmpty[SR] convA[SA] emptyA[SA] fullB[SB] emptyB[SB] accFull[2] accEmpty[2]
-    const uint32_t rawFull = sBar, rawEmpty = rawFull + 8 * TC_SR, convA = rawEmpty + 8 * TC_SR, emptyA = convA + 8 * p.SA;
+    // barriers: fullA[SA] emptyA[SA] fullB[SB] emptyB[SB] accFull[2] accEmpty[2]
+    const uint32_t fullA = sBar, emptyA = fullA + 8 * p.SA;
     const uint32_t fullB = emptyA + 8 * p.SA, emptyB = fullB + 8 * p.SB;
     const uint32_t accFull = emptyB + 8 * p.SB, accEmpty = accFull + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pipe_bytes + p.staging_bytes + 8 * (2 * TC_SR + 2 * p.SA + 2 * p.SB + 4));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pipe_bytes + p.staging_bytes + 8 * (2 * p.SA + 2 * p.SB + 4));
 
     if (warp == 4 && lane == 0) {
-        for (int i = 0; i < TC_SR; ++i) { mbar_init(rawFull + 8 * i, 1); mbar_init(rawEmpty + 8 * i, 4); }
-        for (int i = 0; i < p.SA; ++i) { mbar_init(convA + 8 * i, 8); mbar_init(emptyA + 8 * i, 1); }
+        for (int i = 0; i < p.SA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
         for (int i = 0; i < p.SB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, 1); mbar_init(accEmpty + 8 * i, 16); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -299,62 +314,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     const int acc_stride = p.NT * tile_cols;
     const long long k_t1 = TC_CLK();
 
-    if (warp < 4) {
-        // ===== converter =====
-        const int chunks = p.a_box_bytes >> 4;   // float4 items of the raw box: 8 per pixel row
-        const uint32_t convA_leader = map_to_cta(convA, 0);
-        int ia = 0;
-        long long c_wait = 0, c0 = TC_CLK(), cq;
-        for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
-            for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
-                const int s = ia % p.SA, rs = ia % TC_SR;
-                cq = TC_CLK();
-                mbar_wait(rawFull + 8 * rs, (ia / TC_SR) & 1);
-                mbar_wait(emptyA + 8 * s, ((ia / p.SA) & 1) ^ 1);
-                c_wait += TC_CLK() - cq;
-                const float4* src = reinterpret_cast<const float4*>(smem + off_raw + rs * p.raw_bytes);
-                unsigned char* hi = smem + s * a_stage_bytes;
-                unsigned char* lo = hi + p.a_plane_bytes;
-#pragma unroll 4
-                for (int i = threadIdx.x; i < chunks; i += 128) {
-                    const float4 v = src[i];
-                    const int row = i >> 3, q = i & 7;
-                    const int off = row * TC_ROW + ((((q >> 1) ^ ((row >> 1) & 3))) << 4) + ((q & 1) << 3);
-                    const float x0 = __fmul_rn(v.x, TC_ACT_SCALE), x1 = __fmul_rn(v.y, TC_ACT_SCALE);
-                    const float x2 = __fmul_rn(v.z, TC_ACT_SCALE), x3 = __fmul_rn(v.w, TC_ACT_SCALE);
-                    const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
-                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                    const __half2 l01 = __floats2half2_rn(__fsub_rn(x0, f01.x), __fsub_rn(x1, f01.y));
-                    const __half2 l23 = __floats2half2_rn(__fsub_rn(x2, f23.x), __fsub_rn(x3, f23.y));
-                    uint2 uh, ul;
-                    uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
-                    ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
-                    *reinterpret_cast<uint2*>(hi + off) = uh;
-                    *reinterpret_cast<uint2*>(lo + off) = ul;
-                }
-                asm volatile("fence.proxy.async;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(rawEmpty + 8 * rs);
-                    mbar_arrive_cluster(convA_leader + 8 * s);
-                }
-            }
-        }
-        if (DBG && p.dbg && threadIdx.x == 0) {
-            long long* d = p.dbg + (long long)blockIdx.x * 16;
-            d[7] = TC_CLK() - c0; d[8] = c_wait;
-        }
-    } else if (warp == 6) {
-        // ===== activation (A) producer: raw fp32 halo boxes =====
+    if (warp == 6) {
+        // ===== activation (A) producer: hi and lo halo boxes of this CTA's region; the leader's barrier counts both CTAs =====
         if (lane == 0) {
             int ia = 0;
+            const uint32_t fullA_leader = map_to_cta(fullA, 0);
             for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
                 const TcRegion r = tc_region(p, grp, crank);
                 for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
-                    const int rs = ia % TC_SR;
-                    mbar_wait(rawEmpty + 8 * rs, ((ia / TC_SR) & 1) ^ 1);
-                    mbar_expect_tx(rawFull + 8 * rs, p.a_box_bytes);
-                    tma_load_4d(sRaw + rs * p.raw_bytes, &mA, rawFull + 8 * rs, kb * TC_KB, r.x0 - 1, r.y0 - 1, r.b);
+                    const int s = ia % p.SA;
+                    mbar_wait(emptyA + 8 * s, ((ia / p.SA) & 1) ^ 1);
+                    if (crank == 0) mbar_expect_tx(fullA + 8 * s, 4 * p.a_box_bytes);   // 2 planes x 2 CTAs
+                    const uint32_t dst = sA + s * a_stage_bytes;
+                    tma_load_4d_pair(dst, &mAh, fullA_leader + 8 * s, kb * TC_KB, r.x0 - 1, r.y0 - 1, r.b);
+                    tma_load_4d_pair(dst + p.a_plane_bytes, &mAl, fullA_leader + 8 * s, kb * TC_KB, r.x0 - 1, r.y0 - 1, r.b);
                 }
             }
         }
@@ -408,7 +381,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
                 for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
                     const int sa = ia % p.SA;
                     tq = TC_CLK();
-                    mbar_wait_cluster(convA + 8 * sa, (ia / p.SA) & 1);
+                    mbar_wait(fullA + 8 * sa, (ia / p.SA) & 1);
+                    tc_fence_after();
                     t_a += TC_CLK() - tq;
                     const uint32_t a16 = (((sA + sa * a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
                     for (int tap = 0; tap < 9; ++tap, ++ib) {
@@ -751,7 +725,7 @@ inline int tc_pack(TcWeights& w, const float* wv, int cin, int N, int npad, int 
     return 0;
 }
 
-struct TcGeom { int TW, TH, P, NT, SA, SB, a_plane, raw, b_plane, b_stage, tmem_cols, tiles_x, tiles_y, regions, staging, stage_ld; size_t smem; };
+struct TcGeom { int TW, TH, P, NT, SA, SB, a_plane, b_plane, b_stage, tmem_cols, tiles_x, tiles_y, regions, staging, stage_ld; size_t smem; };
 
 // Picks the flat-padded tile (TW x TH, P = TW + 2, (TH-1)*P + TW <= 128) with the best MMA-row efficiency, then the
 // number of stacked tiles per CTA region (weight-tile reuse) that still load-balances over the CTA pairs and fits
@@ -792,24 +766,22 @@ inline bool tc_geometry(int B, int H, int W, int Ncta, int gz, bool pooled, int 
         if (NT * g.TH + 2 > 256) continue;   // TMA box dimension limit
         const int rows = std::max(box_rows, (NT - 1) * g.TH * g.P + 2 * g.P + 2 + 128);
         const int a_plane = tc_round_up(rows * TC_ROW, 1024);
-        const int raw = tc_round_up(box_rows * TC_RAW_ROW, 1024);
-        int SA = 3, SB = 0;
-        for (; SA >= 2; --SA) {   // three operand stages when the weight ring still gets >= 4
-            const long long left = (long long)TC_SMEM_LIMIT - 4096 - g.staging - (long long)TC_SR * raw - (long long)SA * 2 * a_plane;
+        int SA = 4, SB = 0;
+        for (; SA >= 2; --SA) {   // up to four activation stages while the weight ring still gets >= 4
+            const long long left = (long long)TC_SMEM_LIMIT - 4096 - g.staging - (long long)SA * 2 * a_plane;
             SB = left > 0 ? (int)(left / g.b_stage) : 0;
             if (SB > 10) SB = 10;
-            if (SB >= (SA == 3 ? 4 : 2)) break;
+            if (SB >= (SA >= 3 ? 4 : 2)) break;
         }
         if (SA < 2) continue;
         TcGeom c = g;
-        c.NT = NT; c.SA = SA; c.SB = SB; c.a_plane = a_plane; c.raw = raw;
+        c.NT = NT; c.SA = SA; c.SB = SB; c.a_plane = a_plane;
         c.tiles_y = (row_tiles + NT - 1) / NT;
         c.regions = c.tiles_x * c.tiles_y * B;
         int cols = 32;
         while (cols < 2 * NT * tile_cols) cols <<= 1;
         c.tmem_cols = cols;
-        c.smem = (size_t)SA * 2 * a_plane + (size_t)TC_SR * raw + (size_t)SB * g.b_stage + g.staging +
-                 8 * (2 * TC_SR + 2 * SA + 2 * SB + 4) + 16 + 1024;
+        c.smem = (size_t)SA * 2 * a_plane + (size_t)SB * g.b_stage + g.staging + 8 * (2 * SA + 2 * SB + 4) + 16 + 1024;
         const int groups = ((c.regions + 1) / 2) * gz;
         const int rounds = (groups + n_pairs - 1) / n_pairs;
         const double eff = (double)c.regions * gz / ((double)rounds * n_pairs * 2);
@@ -822,13 +794,16 @@ inline bool tc_geometry(int B, int H, int W, int Ncta, int gz, bool pooled, int 
     return true;
 }
 
+// the TMA maps need 16-byte aligned fp16 channel offsets and pixel pitches; other views stay on the SIMT kernel
+inline bool tc_view_ok(const ConvArgs& a) { return a.in_lo && !(a.in_coff & 7) && !(a.in_pitch & 7); }
+
 inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     TcState& s = tc_state();
     if (!tc_available()) { s.last_error = s.reason; return -1; }
     if (!w.ok) { s.last_error = "tc_conv: weights not packed"; return -1; }
-    if (a.in_lo) { s.last_error = "tc_conv: split activation planes are not used any more (pass in_lo = nullptr)"; return -1; }
+    if (!a.in_lo) { s.last_error = "tc_conv: the input view must be in split-fp16 storage (in_lo = lo plane)"; return -1; }
     if (a.Cin != w.cin || a.N != w.N) { s.last_error = "tc_conv: shape mismatch with packed weights"; return -1; }
-    if ((a.in_coff & 3) || (a.in_pitch & 3)) { s.last_error = "tc_conv: view not 16-byte aligned"; return -1; }
+    if ((a.in_coff & 7) || (a.in_pitch & 7)) { s.last_error = "tc_conv: view not 16-byte aligned"; return -1; }
     const bool pooled = a.epi == EPI_CONVA;
     if (pooled && ((a.H | a.W) & 1)) { s.last_error = "tc_conv: pooled conv needs even H, W"; return -1; }
     if (pooled && w.Ncta > 128) { s.last_error = "tc_conv: pooled conv needs <= 128 channels per CTA"; return -1; }
@@ -857,29 +832,35 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     TcGeom g;
     if (!tc_geometry(a.B, a.H, a.W, w.Ncta, w.gz, pooled, s.force_nt, s.max_pairs, g)) { s.last_error = "tc_conv: no tile geometry fits"; return -1; }
     const int box_rows = g.NT * g.TH + 2;
-    auto key = std::make_tuple((const void*)(a.in_hi + a.in_coff), a.Cin, a.W, a.H, a.B, a.in_pitch, g.P, box_rows);
-    auto it = s.amaps.find(key);
-    if (it == s.amaps.end()) {
-        CUtensorMap map;
-        const cuuint64_t gdim[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
-        const cuuint64_t gstr[3] = {(cuuint64_t)a.in_pitch * 4, (cuuint64_t)a.W * a.in_pitch * 4, (cuuint64_t)a.H * a.W * a.in_pitch * 4};
-        const cuuint32_t box[4] = {(cuuint32_t)TC_KB, (cuuint32_t)g.P, (cuuint32_t)box_rows, 1};
-        const cuuint32_t est[4] = {1, 1, 1, 1};
-        const CUresult r = s.encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(a.in_hi + a.in_coff), gdim, gstr, box, est,
-                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { s.last_error = "tc_conv: cuTensorMapEncodeTiled(A) failed (" + std::to_string((int)r) + ")"; return -1; }
-        it = s.amaps.emplace(key, map).first;
+    // one 4-D map per operand plane (hi, lo): fp16 NHWC view, box = 32 channels x P columns x box_rows rows
+    const CUtensorMap* amap[2] = {nullptr, nullptr};
+    for (int pl = 0; pl < 2; ++pl) {
+        const h16* base = reinterpret_cast<const h16*>(pl ? a.in_lo : a.in_hi) + a.in_coff;
+        auto key = std::make_tuple((const void*)base, a.Cin, a.W, a.H, a.B, a.in_pitch, g.P, box_rows);
+        auto it = s.amaps.find(key);
+        if (it == s.amaps.end()) {
+            CUtensorMap map;
+            const cuuint64_t gdim[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+            const cuuint64_t gstr[3] = {(cuuint64_t)a.in_pitch * 2, (cuuint64_t)a.W * a.in_pitch * 2, (cuuint64_t)a.H * a.W * a.in_pitch * 2};
+            const cuuint32_t box[4] = {(cuuint32_t)TC_KB, (cuuint32_t)g.P, (cuuint32_t)box_rows, 1};
+            const cuuint32_t est[4] = {1, 1, 1, 1};
+            const CUresult r = s.encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, gdim, gstr, box, est,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { s.last_error = "tc_conv: cuTensorMapEncodeTiled(A) failed (" + std::to_string((int)r) + ")"; return -1; }
+            it = s.amaps.emplace(key, map).first;
+        }
+        amap[pl] = &it->second;
     }
     TcParams p;
     memset(&p, 0, sizeof p);
     p.B = a.B; p.H = a.H; p.W = a.W;
     p.TW = g.TW; p.TH = g.TH; p.P = g.P; p.NT = g.NT; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y; p.regions = g.regions;
     p.KBn = w.KBn; p.Ncta = w.Ncta; p.N = w.Npad;
-    p.a_plane_bytes = g.a_plane; p.b_plane_bytes = g.b_plane; p.b_stage_bytes = g.b_stage; p.raw_bytes = g.raw; p.a_box_bytes = TC_RAW_ROW * g.P * box_rows;
+    p.a_plane_bytes = g.a_plane; p.b_plane_bytes = g.b_plane; p.b_stage_bytes = g.b_stage; p.a_box_bytes = TC_ROW * g.P * box_rows;
     p.SA = g.SA; p.SB = g.SB; p.tmem_cols = g.tmem_cols;
     p.staging_bytes = g.staging; p.stage_ld = g.stage_ld;
-    p.inv_scale = 1.0f / (TC_ACT_SCALE * w.wscale);
+    p.inv_scale = 1.0f / (EIG_ACT_SCALE * w.wscale);
     p.ca = a;
     if (g.smem > TC_SMEM_LIMIT) { s.last_error = "tc_conv: shared memory budget exceeded"; return -1; }
     p.dbg = s.dbg;
@@ -889,8 +870,8 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     cfg.gridDim = dim3(n_pairs * 2);
     cfg.dynamicSmemBytes = g.smem;
     s.last_grid = n_pairs * 2; s.last_nt = g.NT; s.last_sa = g.SA; s.last_sb = g.SB;
-    const cudaError_t le = s.dbg ? cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<true>, it->second, w.map, p)
-                                 : cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false>, it->second, w.map, p);
+    const cudaError_t le = s.dbg ? cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<true>, *amap[0], *amap[1], w.map, p)
+                                 : cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false>, *amap[0], *amap[1], w.map, p);
     if (le != cudaSuccess) { s.last_error = std::string("tc_conv launch: ") + cudaGetErrorString(le); cudaGetLastError(); return -1; }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { s.last_error = std::string("tc_conv launch: ") + cudaGetErrorString(e); return -1; }

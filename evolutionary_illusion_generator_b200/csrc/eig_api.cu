@@ -379,6 +379,12 @@ static int launch_conv(eig_ctx* c, const ConvArgs& a, cudaStream_t s) {
 }
 
 static View mkview(float* hi, float* lo, int pitch, int coff, int C) { View v; v.hi = hi; v.lo = lo; v.pitch = pitch; v.coff = coff; v.C = C; return v; }
+// lo plane of a layer's concat buffer: in tensor-core mode the buffer holds two fp16 planes (split-fp16 storage, common.cuh
+// View) in the bytes the fp32 tensor would take; the lo plane starts after cap * H * W * ctot halves.  nullptr = plain fp32.
+static float* lo_plane(eig_ctx* c, int n, float* base) {
+    if (c->conv_mode != EIG_CONV_TC) return nullptr;
+    return reinterpret_cast<float*>(reinterpret_cast<h16*>(base) + (size_t)c->cap * c->H[n] * c->W[n] * c->ctot[n]);
+}
 
 static L0Args l0_args(eig_ctx* c, const float* x, int B, int cur, int nxt) {
     L0Args a;
@@ -387,7 +393,7 @@ static L0Args l0_args(eig_ctx* c, const float* x, int B, int cur, int nxt) {
     a.x = x; a.P0 = c->P[0];
     a.wA = c->lw[1].convA; a.bA = c->lw[1].convA_b; a.C1pad = (c->ch[1] + 3) & ~3;
     a.P1 = c->P[1];
-    a.dstE1 = mkview(c->X[1][cur], nullptr, c->ctot[1], 0, 2 * c->ch[1]);
+    a.dstE1 = mkview(c->X[1][cur], lo_plane(c, 1, c->X[1][cur]), c->ctot[1], 0, 2 * c->ch[1]);
     a.wL = c->lw[0].lstm; a.bL = c->lw[0].lstm_b; a.peep = c->lw[0].peep;
     a.Z = c->Z;
     a.h_prev = c->h0[cur]; a.h_next = c->h0[nxt]; a.cstate = c->cst[0];
@@ -417,14 +423,14 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
     for (int n = 2; n < 4; ++n) {  // ConvA_n: E_{n-1} (res n-1) -> pool -> E_n
         ConvArgs a;
         memset(&a, 0, sizeof a);
-        a.in_hi = c->X[n - 1][cur]; a.in_lo = nullptr;
+        a.in_hi = c->X[n - 1][cur]; a.in_lo = lo_plane(c, n - 1, c->X[n - 1][cur]);
         a.in_pitch = c->ctot[n - 1]; a.in_coff = 0; a.Cin = 2 * c->ch[n - 1];
         a.B = B; a.H = c->H[n - 1]; a.W = c->W[n - 1];
         a.wgt = c->lw[n].convA; a.bias = c->lw[n].convA_b; a.N = c->ch[n]; a.Npad = (c->ch[n] + 3) & ~3;
         a.epi = EPI_CONVA; a.P = c->P[n];
-        a.dstE = mkview(c->X[n][cur], nullptr, c->ctot[n], 0, 2 * c->ch[n]);
+        a.dstE = mkview(c->X[n][cur], lo_plane(c, n, c->X[n][cur]), c->ctot[n], 0, 2 * c->ch[n]);
 #ifndef EIG_EMU
-        if (tc && c->lw[n].tcA.ok) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcA, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvA: " + tc_last_error()); continue; }
+        if (tc && c->lw[n].tcA.ok && tc_view_ok(a)) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcA, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvA: " + tc_last_error()); continue; }
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }
@@ -432,7 +438,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         ConvArgs a;
         memset(&a, 0, sizeof a);
         const int hoff = 2 * c->ch[n] + (n < 3 ? c->ch[n + 1] : 0);
-        a.in_hi = c->X[n][nxt]; a.in_lo = nullptr;
+        a.in_hi = c->X[n][nxt]; a.in_lo = lo_plane(c, n, c->X[n][nxt]);
         a.in_pitch = c->ctot[n]; a.in_coff = hoff; a.Cin = c->ch[n];
         a.B = B; a.H = c->H[n]; a.W = c->W[n];
         a.wgt = c->lw[n].convP; a.bias = c->lw[n].convP_b;
@@ -440,24 +446,24 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         a.epi = EPI_CONVP; a.outP = c->P[n]; a.clip = 0;
         if (n == 1) { a.nP = c->ch[1]; a.outZ = c->Z; }
 #ifndef EIG_EMU
-        if (tc && c->lw[n].tcP.ok) { prof_pre(CLS_CONV_TC, s); const int r2 = tc_conv(c->lw[n].tcP, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (r2) return fail(EIG_E_CUDA, "tc_conv ConvP: " + tc_last_error()); return EIG_OK; }
+        if (tc && c->lw[n].tcP.ok && tc_view_ok(a)) { prof_pre(CLS_CONV_TC, s); const int r2 = tc_conv(c->lw[n].tcP, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (r2) return fail(EIG_E_CUDA, "tc_conv ConvP: " + tc_last_error()); return EIG_OK; }
 #endif
         return launch_conv(c, a, s);
     };
     for (int n = 3; n >= 1; --n) {  // ConvLSTM_n
         ConvArgs a;
         memset(&a, 0, sizeof a);
-        a.in_hi = c->X[n][cur]; a.in_lo = nullptr;
+        a.in_hi = c->X[n][cur]; a.in_lo = lo_plane(c, n, c->X[n][cur]);
         a.in_pitch = c->ctot[n]; a.in_coff = 0; a.Cin = c->ctot[n];
         a.B = B; a.H = c->H[n]; a.W = c->W[n];
         a.wgt = c->lw[n].lstm; a.bias = c->lw[n].lstm_b; a.N = 4 * c->ch[n]; a.Npad = a.N;
         a.epi = EPI_LSTM; a.cstate = c->cst[n]; a.peep = c->lw[n].peep;
         const int hoff = 2 * c->ch[n] + (n < 3 ? c->ch[n + 1] : 0);
-        a.dstH = mkview(c->X[n][nxt], nullptr, c->ctot[n], hoff, c->ch[n]);
+        a.dstH = mkview(c->X[n][nxt], lo_plane(c, n, c->X[n][nxt]), c->ctot[n], hoff, c->ch[n]);
         // R_n up-sampled x2 into the concat buffer of layer n-1 (layer 0 gets R_1 through Z instead)
-        if (n >= 2) a.dstUp = mkview(c->X[n - 1][cur], nullptr, c->ctot[n - 1], 2 * c->ch[n - 1], c->ch[n]);
+        if (n >= 2) a.dstUp = mkview(c->X[n - 1][cur], lo_plane(c, n - 1, c->X[n - 1][cur]), c->ctot[n - 1], 2 * c->ch[n - 1], c->ch[n]);
 #ifndef EIG_EMU
-        if (tc && c->lw[n].tcL.ok) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); continue; }
+        if (tc && c->lw[n].tcL.ok && tc_view_ok(a)) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); continue; }
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }

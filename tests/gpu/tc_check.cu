@@ -50,7 +50,7 @@ static double maxdiff(const std::vector<float>& a, const std::vector<float>& b, 
 struct Problem {
     int B, H, W, pitch, coff, Cin, N;
     std::vector<float> hi, wv, bias;
-    float *d_hi, *d_w, *d_b;
+    float *d_hi, *d_lo, *d_w, *d_b;
     int kb;
     TcWeights tw;
 };
@@ -62,19 +62,29 @@ static void make_problem(Problem& p, int B, int H, int W, int pitch, int coff, i
     std::uniform_real_distribution<float> u(-1.f, 1.f);
     const size_t px = (size_t)B * H * W;
     p.hi.assign(px * pitch, 0.f);
-    for (size_t i = 0; i < px * pitch; ++i) p.hi[i] = u(rng);
+    // the activation buffer is in split-fp16 storage (two fp16 planes: hi, then lo); the references use the value the
+    // planes encode, (hi + lo) / 16
+    std::vector<h16> planes(2 * px * pitch);
+    for (size_t i = 0; i < px * pitch; ++i) {
+        float v = u(rng);
+        if (i % 7 == 3) v *= 1e-3f;     // small values: lo becomes a subnormal half
+        if (i % 11 == 5) v *= 4.f;      // larger activations
+        split16(v, &planes[i], &planes[px * pitch + i]);
+        p.hi[i] = join16(planes[i], planes[px * pitch + i]);
+    }
     p.wv.resize((size_t)9 * Cin * N);
     const float sc = 1.f / sqrtf(9.f * Cin);
     for (auto& v : p.wv) v = u(rng) * sc * 1.7f;
     p.bias.resize(N);
     for (auto& v : p.bias) v = u(rng) * 0.1f;
-    p.d_hi = dev(p.hi); p.d_w = dev(p.wv); p.d_b = dev(p.bias);
+    p.d_hi = reinterpret_cast<float*>(dev(planes)); p.d_w = dev(p.wv); p.d_b = dev(p.bias);
+    p.d_lo = reinterpret_cast<float*>(reinterpret_cast<h16*>(p.d_hi) + px * pitch);
     if (tc_pack(p.tw, p.wv.data(), Cin, N, N, N <= 128 ? 128 : 256) || !p.tw.ok) { printf("tc_pack failed: %s\n", tc_last_error().c_str()); exit(2); }
 }
 
 static ConvArgs base_args(const Problem& p) {
     ConvArgs a; memset(&a, 0, sizeof a);
-    a.in_hi = p.d_hi; a.in_lo = nullptr; a.in_pitch = p.pitch; a.in_coff = p.coff; a.Cin = p.Cin;
+    a.in_hi = p.d_hi; a.in_lo = p.d_lo; a.in_pitch = p.pitch; a.in_coff = p.coff; a.Cin = p.Cin;
     a.B = p.B; a.H = p.H; a.W = p.W; a.wgt = p.d_w; a.bias = p.d_b; a.N = p.N; a.Npad = p.N;
     return a;
 }
@@ -165,14 +175,25 @@ static bool check_epilogues(Problem& p, int mode) {
         for (auto& q : hh) { CHECK(cudaMalloc(&q, px * (R + 8) * 4)); CHECK(cudaMemset(q, 0, px * (R + 8) * 4)); }
         for (auto& q : up) { CHECK(cudaMalloc(&q, px * 4 * (R + 4) * 4)); CHECK(cudaMemset(q, 0, px * 4 * (R + 4) * 4)); }
         ConvArgs a = base_args(p); a.epi = EPI_LSTM; a.peep = dpe;
-        a.cstate = cs[0]; a.dstH = mkview(hh[0], nullptr, R + 8, 4, R); a.dstUp = mkview(up[0], nullptr, R + 4, 4, R);
+        // h goes to a plain fp32 view, the up-sampled copy to a split-fp16 view (the product layout of the concat buffers)
+        const size_t n_up = px * 4 * (R + 4);
+        auto lo_of = [&](float* b) { return reinterpret_cast<float*>(reinterpret_cast<h16*>(b) + n_up); };
+        a.cstate = cs[0]; a.dstH = mkview(hh[0], nullptr, R + 8, 4, R); a.dstUp = mkview(up[0], lo_of(up[0]), R + 4, 4, R);
         if (tc_conv(p.tw, a, 0)) { printf("tc_conv: %s\n", tc_last_error().c_str()); return false; }
-        a.cstate = cs[1]; a.dstH = mkview(hh[1], nullptr, R + 8, 4, R); a.dstUp = mkview(up[1], nullptr, R + 4, 4, R);
+        a.cstate = cs[1]; a.dstH = mkview(hh[1], nullptr, R + 8, 4, R); a.dstUp = mkview(up[1], lo_of(up[1]), R + 4, 4, R);
         launch_simt(a);
         CHECK(cudaDeviceSynchronize());
         ok &= cmp("LSTM c", cs[0], cs[1], px * R, g_tol);
         ok &= cmp("LSTM h", hh[0], hh[1], px * (R + 8), g_tol);
-        ok &= cmp("LSTM up", up[0], up[1], px * 4 * (R + 4), g_tol);
+        {
+            std::vector<h16> ua = host(reinterpret_cast<const h16*>(up[0]), 2 * n_up), ub = host(reinterpret_cast<const h16*>(up[1]), 2 * n_up);
+            std::vector<float> fa(n_up), fb(n_up);
+            for (size_t i = 0; i < n_up; ++i) { fa[i] = join16(ua[i], ua[n_up + i]); fb[i] = join16(ub[i], ub[n_up + i]); }
+            double sc; const double md = maxdiff(fa, fb, &sc);
+            const bool o2 = md <= g_tol * std::max(sc, 1.0);
+            printf("    %-10s max |tc - simt| = %.3e (scale %.2f) %s\n", "LSTM up16", md, sc, o2 ? "ok" : "FAIL");
+            ok &= o2;
+        }
         for (auto& q : cs) cudaFree(q); for (auto& q : hh) cudaFree(q); for (auto& q : up) cudaFree(q); cudaFree(dpe);
     }
     return ok;
@@ -266,7 +287,7 @@ int main(int argc, char** argv) {
         {5, 60, 80, 80, 0, 80, 64},      // gray ConvLSTM1 (partial last 32-channel block)
         {2, 60, 80, 80, 64, 16, 16},     // gray ConvP1 (view at a channel offset)
         {2, 30, 40, 160, 0, 64, 32},     // gray ConvA-like
-        {1, 16, 24, 36, 4, 32, 48},      // odd sizes
+        {1, 16, 24, 40, 8, 32, 48},      // odd sizes
         {40, 30, 40, 96, 0, 96, 96},     // more regions than SMs: the persistent loop + accumulator double buffering
         {3, 30, 40, 480, 0, 480, 384},   // colour ConvLSTM2: N split over two CTA columns
     };
