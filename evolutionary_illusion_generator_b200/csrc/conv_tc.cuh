@@ -61,6 +61,7 @@ struct TcParams {
     int a_plane_bytes, b_plane_bytes, b_stage_bytes, a_box_bytes;
     int SA, SB;
     int tmem_cols;
+    int egroups;                  // epilogue column groups: 2 (warps 8-15) or 3 (+ warps 0-3, for wide accumulators)
     int staging_bytes, stage_ld;  // ConvA pooling tile: 128 rows x stage_ld floats
     float inv_scale;              // 1 / (activation scale * weight scale), exact power of two
     long long* dbg;               // optional [grid][16] cycle counters per role (tests/gpu/tc_check timing mode), else null
@@ -258,13 +259,13 @@ __device__ __forceinline__ TcRegion tc_region(const TcParams& p, int group, int 
 }
 
 // Persistent, warp-specialised: grid = 2 * min(groups, #SM / 2) CTAs of 512 threads in clusters of 2.
-//   warps 0-3   idle (the in-kernel fp32 -> fp16 converter of earlier versions is gone: operands arrive split from HBM)
 //   warp  4     weight producer (one thread): this CTA's half of every per-tap weight tile, hi and lo planes
 //   warp  5     TMEM allocator; in the leader CTA also the MMA issuer (one elected thread) for BOTH CTAs
 //   warp  6     activation producer (one thread): the hi and lo halo boxes of each channel block, SA stages ahead
 //   warp  7     idle
-//   warps 8-15  epilogue (TMEM lane quarter = warp & 3, column half = (warp - 8) >> 2): drains accumulator set i
-//               while set i^1 is being computed
+//   warps 0-3, 8-15  epilogue (TMEM lane quarter = warp & 3, column group = 0 / 1 for warps 8-11 / 12-15, 2 for
+//               warps 0-3; 16-column chunks dealt round-robin to the three groups): drains accumulator set i while set
+//               i^1 is being computed
 // Barriers: fullA / fullB (TMA transactions of BOTH CTAs -> the leader's MMA warp), emptyA / emptyB / accFull
 //   (tcgen05.commit multicast to both CTAs), accEmpty (epilogue warps of both CTAs -> leader).
 // per-role cycle counters exist only in the DBG instantiation (tests/gpu/tc_check timing mode)
@@ -298,7 +299,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
     if (warp == 4 && lane == 0) {
         for (int i = 0; i < p.SA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
         for (int i = 0; i < p.SB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, 1); mbar_init(accEmpty + 8 * i, 16); }
+        for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, 1); mbar_init(accEmpty + 8 * i, 8 * p.egroups); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
@@ -317,40 +318,42 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
     if (warp == 6) {
         // ===== activation (A) producer: hi and lo halo boxes of this CTA's region; the leader's barrier counts both CTAs =====
         if (lane == 0) {
-            int ia = 0;
+            int s = 0;            // ring position and phase are carried, not divided out of a counter (a runtime
+            uint32_t ph = 0;      // division costs the single producer / issuer thread ~400 cycles per use)
             const uint32_t fullA_leader = map_to_cta(fullA, 0);
             for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
                 const TcRegion r = tc_region(p, grp, crank);
-                for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
-                    const int s = ia % p.SA;
-                    mbar_wait(emptyA + 8 * s, ((ia / p.SA) & 1) ^ 1);
+                for (int kb = 0; kb < p.KBn; ++kb) {
+                    mbar_wait(emptyA + 8 * s, ph ^ 1);
                     if (crank == 0) mbar_expect_tx(fullA + 8 * s, 4 * p.a_box_bytes);   // 2 planes x 2 CTAs
                     const uint32_t dst = sA + s * a_stage_bytes;
                     tma_load_4d_pair(dst, &mAh, fullA_leader + 8 * s, kb * TC_KB, r.x0 - 1, r.y0 - 1, r.b);
                     tma_load_4d_pair(dst + p.a_plane_bytes, &mAl, fullA_leader + 8 * s, kb * TC_KB, r.x0 - 1, r.y0 - 1, r.b);
+                    if (++s == p.SA) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 4) {
         // ===== weight (B) producer: this CTA's half (Ncta/2 rows) of every tile; the leader's barrier counts both =====
         if (lane == 0) {
-            int ib = 0;
+            int s = 0;
+            uint32_t ph = 0;
             long long b_wait = 0, b0 = TC_CLK(), bq;
             const int half_rows = p.Ncta >> 1;
             const uint32_t fullB_leader = map_to_cta(fullB, 0);
             for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
                 const int nbase = (grp / p.groups_per_nz) * p.Ncta, n0 = nbase + crank * half_rows;
                 for (int kb = 0; kb < p.KBn; ++kb) {
-                    for (int tap = 0; tap < 9; ++tap, ++ib) {
-                        const int s = ib % p.SB;
+                    for (int tap = 0; tap < 9; ++tap) {
                         bq = TC_CLK();
-                        mbar_wait(emptyB + 8 * s, ((ib / p.SB) & 1) ^ 1);
+                        mbar_wait(emptyB + 8 * s, ph ^ 1);
                         b_wait += TC_CLK() - bq;
                         const uint32_t dst = sB + s * b_stage_bytes;
                         const int row_hi = (tap * p.KBn + kb) * p.N, row_lo = ((9 + tap) * p.KBn + kb) * p.N;
                         if (crank == 0) mbar_expect_tx(fullB + 8 * s, 4 * p.b_plane_bytes);   // 2 planes x 2 CTAs
                         tma_load_2d_pair(dst, &mB, fullB_leader + 8 * s, 0, row_hi + n0);
                         tma_load_2d_pair(dst + p.b_plane_bytes, &mB, fullB_leader + 8 * s, 0, row_lo + n0);
+                        if (++s == p.SB) { s = 0; ph ^= 1; }
                     }
                 }
             }
@@ -369,7 +372,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
             const uint32_t lo_flag = 1u << 16;
             const uint32_t plane_a16 = (uint32_t)p.a_plane_bytes >> 4, plane_b16 = (uint32_t)p.b_plane_bytes >> 4;
             const uint32_t tile16 = (uint32_t)(p.TH * p.P * TC_ROW) >> 4;
-            int ia = 0, ib = 0, it = 0;
+            int sa = 0, sb = 0, it = 0;
+            uint32_t pha = 0, phb = 0;
             long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t_commit = 0, t0 = TC_CLK(), tq;
             for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
                 const int set = it & 1;
@@ -378,20 +382,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                 t_acc += TC_CLK() - tq;
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(set * acc_stride);
-                for (int kb = 0; kb < p.KBn; ++kb, ++ia) {
-                    const int sa = ia % p.SA;
+                for (int kb = 0; kb < p.KBn; ++kb) {
                     tq = TC_CLK();
-                    mbar_wait(fullA + 8 * sa, (ia / p.SA) & 1);
+                    mbar_wait(fullA + 8 * sa, pha);
                     tc_fence_after();
                     t_a += TC_CLK() - tq;
                     const uint32_t a16 = (((sA + sa * a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
-                    for (int tap = 0; tap < 9; ++tap, ++ib) {
-                        const int sb = ib % p.SB;
+                    uint32_t tap16 = 0;   // (ky * P + kx) rows of 64 bytes, in 16-byte units
+                    for (int tap = 0; tap < 9; ++tap) {
                         tq = TC_CLK();
-                        mbar_wait(fullB + 8 * sb, (ib / p.SB) & 1);
+                        mbar_wait(fullB + 8 * sb, phb);
                         t_b += TC_CLK() - tq;
                         tc_fence_after();
-                        const uint32_t tap16 = (uint32_t)(((tap / 3) * p.P + (tap % 3)) * TC_ROW) >> 4;
                         const uint32_t b16 = (((sB + sb * b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
                         const uint32_t acc0 = (kb | tap) ? 1u : 0u;
                         if (elect_one()) {
@@ -425,7 +427,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                             t_issue += ci1 - ci0; t_commit += TC_CLK() - ci1;
                         }
                         __syncwarp();
+                        tap16 += (tap == 2 || tap == 5) ? (uint32_t)((p.P - 2) * (TC_ROW >> 4)) : (uint32_t)(TC_ROW >> 4);
+                        if (++sb == p.SB) { sb = 0; phb ^= 1; }
                     }
+                    if (++sa == p.SA) { sa = 0; pha ^= 1; }
                 }
                 ++it;
             }
@@ -434,12 +439,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                 d[0] = TC_CLK() - t0; d[1] = t_acc; d[2] = t_a; d[3] = t_b; d[4] = it; d[14] = t_issue; d[15] = t_commit;
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 8 || (warp < 4 && p.egroups == 3)) {
         // ===== epilogue warps 8..15 =====
         const ConvArgs& a = p.ca;
-        const int q4 = warp & 3, half = (warp - 8) >> 2;
+        const int q4 = warp & 3, half = warp < 4 ? 2 : (warp - 8) >> 2;   // `half` = column group 0..2
         const int m = q4 * 32 + lane;
-        const int etid = (warp - 8) * 32 + lane;
+        const int etid = half * 128 + q4 * 32 + lane;                      // 0..383
         const int hh = m / p.P, ww = m - hh * p.P;
         const uint32_t accEmpty_leader = map_to_cta(accEmpty, 0);
         const float inv = p.inv_scale;
@@ -455,7 +460,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                 // loads of item i+1 are in flight while item i is computed, and those of the FIRST item are issued
                 // before the wait for the accumulator, so their latency hides behind the MMAs.
                 const int R = a.N >> 2;
-                const int n_chunks = ncols > half * 16 ? (ncols - half * 16 + 31) >> 5 : 0;
+                const int n_chunks = ncols > half * 16 ? (ncols - half * 16 + 16 * p.egroups - 1) / (16 * p.egroups) : 0;
                 const int n_items = r.active ? p.NT * n_chunks : 0;
                 int nt = 0, nc0 = half * 16;
                 bool nvalid = false;
@@ -464,7 +469,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
 #pragma unroll
                 for (int q = 0; q < 4; ++q) pq[q] = cold;
                 auto fetch = [&](int i) {
-                    nt = i / n_chunks; nc0 = half * 16 + 32 * (i - nt * n_chunks);
+                    nt = i / n_chunks; nc0 = half * 16 + 16 * p.egroups * (i - nt * n_chunks);
                     const int y = r.y0 + nt * p.TH + hh, x = r.x0 + ww;
                     nvalid = hh < p.TH && ww < p.TW && y < p.H && x < p.W;
                     npix = nvalid ? ((long long)b * p.H + y) * p.W + x : 0;
@@ -529,7 +534,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                 const uint32_t tcol = lane_addr + (uint32_t)(t * tile_cols);
                 if (a.epi == EPI_CONVP || a.epi == EPI_RAW) {
                     const int nP = a.nP ? a.nP : a.N;
-                    for (int c0 = half * 16; c0 < ncols; c0 += 32) {
+                    for (int c0 = half * 16; c0 < ncols; c0 += 16 * p.egroups) {
                         float v[16];
                         tmem_ld16(tcol + c0, v);
                         if (!valid) continue;
@@ -555,7 +560,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                         }
                     }
                 } else {  // EPI_CONVA: relu -> staging tile -> 2x2 max-pool -> error units at half resolution
-                    for (int c0 = half * 16; c0 < ncols; c0 += 32) {
+                    for (int c0 = half * 16; c0 < ncols; c0 += 16 * p.egroups) {
                         float v[16];
                         tmem_ld16(tcol + c0, v);
 #pragma unroll
@@ -564,17 +569,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                             stage[m * p.stage_ld + c0 + i] = o > 0.f ? o : 0.f;
                         }
                     }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"r"(128 * p.egroups) : "memory");
                     const int Hp = p.H >> 1, Wp = p.W >> 1, tw2 = p.TW >> 1, th2 = p.TH >> 1;
                     const int items = th2 * tw2 * ncols;
-                    for (int base = 0; base < items; base += 4 * 256) {
+                    for (int base = 0; base < items; base += 4 * 128 * p.egroups) {
                         float mx[4], pv[4];
                         long long ppos[4];
                         int nn[4];
                         bool okk[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {   // loads first: four independent global reads in flight
-                            const int idx = base + u * 256 + etid;
+                            const int idx = base + u * 128 * p.egroups + etid;
                             okk[u] = idx < items;
                             const int n = idx % ncols, pp = idx / ncols;
                             const int ph = pp / tw2, pw = pp - ph * tw2;
@@ -595,7 +600,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                             view_store(a.dstE, ppos[u], a.N + nn[u], en > 0.f ? en : 0.f);
                         }
                     }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"r"(128 * p.egroups) : "memory");
                 }
             }
             tc_fence_before();
@@ -859,6 +864,7 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     p.KBn = w.KBn; p.Ncta = w.Ncta; p.N = w.Npad;
     p.a_plane_bytes = g.a_plane; p.b_plane_bytes = g.b_plane; p.b_stage_bytes = g.b_stage; p.a_box_bytes = TC_ROW * g.P * box_rows;
     p.SA = g.SA; p.SB = g.SB; p.tmem_cols = g.tmem_cols;
+    p.egroups = w.Ncta >= 96 ? 3 : 2;
     p.staging_bytes = g.staging; p.stage_ld = g.stage_ld;
     p.inv_scale = 1.0f / (EIG_ACT_SCALE * w.wscale);
     p.ca = a;
