@@ -42,93 +42,173 @@ struct L0Args {
 enum { L0_TW = 32, L0_TH = 8 };
 
 // ---------------------------------------------------------------------------------------------- ConvA1
-// CTA = 32x8 full-resolution pixels of one genome = 16x4 pooled pixels; thread = one pooled pixel x CPT channels.
+// Persistent: each CTA keeps the ConvA1 weights in shared memory and walks work items = (32x8 pixel tile, genome),
+// item = blockIdx.x, blockIdx.x + gridDim.x, ...  The x / P0 halo of the NEXT item is fetched into registers while the
+// current one is computed (double-buffered E0 tile).  thread = one pooled pixel x CPT output channels.
+enum { L0_PF = 4 };   // prefetch registers per thread per tensor: 340 halo positions x C0 channels / blockDim <= 4
 template <int CPT>
-__global__ void __launch_bounds__(256) l0_conva1_kernel(L0Args a) {
+__global__ void __launch_bounds__(256) l0_conva1_kernel(L0Args a, int n_items) {
     constexpr int SW = L0_TW + 2, SH = L0_TH + 2;
     EIG_DYN_SMEM(smem);
-    float* sE = reinterpret_cast<float*>(smem);                 // [2*C0][SH][SW]
-    float* sW = sE + 2 * a.C0 * SH * SW;                        // [9][2*C0][C1pad]
-    const int tiles_x = (a.W + L0_TW - 1) / L0_TW;
-    const int x0 = (blockIdx.x % tiles_x) * L0_TW, y0 = (blockIdx.x / tiles_x) * L0_TH;
-    const int b = blockIdx.y;
     const int cin = 2 * a.C0;
-    const long long img = (long long)b * a.H * a.W;
-    for (int i = threadIdx.x; i < SH * SW; i += blockDim.x) {
-        const int cy = i / SW, cx = i - cy * SW;
-        const int gy = y0 + cy - 1, gx = x0 + cx - 1;
-        const bool in = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
-        for (int c = 0; c < a.C0; ++c) {
+    const int e_sz = cin * SH * SW;
+    float* sE = reinterpret_cast<float*>(smem);                 // [2 buffers][2*C0][SH][SW]
+    float* sW = sE + 2 * e_sz;                                  // [9][2*C0][C1pad]
+    float* sOut = sW + 9 * cin * a.C1pad;                       // [64 pooled pixels][C1pad + 1]
+    const int ldo = a.C1pad + 1;   // odd pitch: the 64 pooled pixels of a warp pair hit different banks
+    const int tiles_x = (a.W + L0_TW - 1) / L0_TW;
+    const int tiles = tiles_x * ((a.H + L0_TH - 1) / L0_TH);
+    const int n_halo = SH * SW * a.C0;                          // (position, channel) pairs of one halo tile
+    for (int i = threadIdx.x; i < 9 * cin * a.C1pad; i += blockDim.x) sW[i] = a.wA[i];
+
+    float pf_x[L0_PF], pf_p[L0_PF];
+    auto fetch = [&](int item) {   // halo of `item` -> registers (zeros outside the image)
+        const int b = item / tiles, tile = item - b * tiles;
+        const int x0 = (tile % tiles_x) * L0_TW, y0 = (tile / tiles_x) * L0_TH;
+        const long long img = (long long)b * a.H * a.W;
+#pragma unroll
+        for (int k = 0; k < L0_PF; ++k) {
+            const int i = threadIdx.x + k * blockDim.x;
+            pf_x[k] = 0.f; pf_p[k] = 0.f;
+            if (i < n_halo) {
+                const int c = i % a.C0, pos = i / a.C0;
+                const int cy = pos / SW, cx = pos - cy * SW;
+                const int gy = y0 + cy - 1, gx = x0 + cx - 1;
+                if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+                    const long long idx = (img + (long long)gy * a.W + gx) * a.C0 + c;
+                    pf_x[k] = a.x[idx]; pf_p[k] = a.P0[idx];
+                }
+            }
+        }
+    };
+    auto stash = [&](float* dst) {  // registers -> E0 = [relu(x - P0), relu(P0 - x)] tile in shared memory
+#pragma unroll
+        for (int k = 0; k < L0_PF; ++k) {
+            const int i = threadIdx.x + k * blockDim.x;
+            if (i < n_halo) {
+                const int c = i % a.C0, pos = i / a.C0;
+                float ep = __fsub_rn(pf_x[k], pf_p[k]), en = __fsub_rn(pf_p[k], pf_x[k]);
+                ep = ep > 0.f ? ep : 0.f; en = en > 0.f ? en : 0.f;
+                dst[c * SH * SW + pos] = ep;
+                dst[(a.C0 + c) * SH * SW + pos] = en;
+            }
+        }
+    };
+    // small test networks run fewer threads than the halo needs registers for: they stage without the prefetch
+    const bool pf_ok = n_halo <= L0_PF * (int)blockDim.x;
+    auto stage_direct = [&](int it2, float* dst) {
+        const int b = it2 / tiles, tile = it2 - b * tiles;
+        const int x0 = (tile % tiles_x) * L0_TW, y0 = (tile / tiles_x) * L0_TH;
+        const long long img = (long long)b * a.H * a.W;
+        for (int i = threadIdx.x; i < n_halo; i += blockDim.x) {
+            const int c = i % a.C0, pos = i / a.C0;
+            const int cy = pos / SW, cx = pos - cy * SW;
+            const int gy = y0 + cy - 1, gx = x0 + cx - 1;
             float ep = 0.f, en = 0.f;
-            if (in) {
+            if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
                 const long long idx = (img + (long long)gy * a.W + gx) * a.C0 + c;
                 const float xv = a.x[idx], pv = a.P0[idx];
                 ep = __fsub_rn(xv, pv); en = __fsub_rn(pv, xv);
                 ep = ep > 0.f ? ep : 0.f; en = en > 0.f ? en : 0.f;
             }
-            sE[(c * SH + cy) * SW + cx] = ep;
-            sE[((a.C0 + c) * SH + cy) * SW + cx] = en;
+            dst[c * SH * SW + pos] = ep;
+            dst[(a.C0 + c) * SH * SW + pos] = en;
         }
+    };
+    int item = blockIdx.x, cur = 0;
+    if (item < n_items) {
+        if (pf_ok) { fetch(item); stash(sE); }
+        else stage_direct(item, sE);
     }
-    for (int i = threadIdx.x; i < 9 * cin * a.C1pad; i += blockDim.x) sW[i] = a.wA[i];
     __syncthreads();
 
     const int pp = threadIdx.x & 63, grp = threadIdx.x >> 6;    // pooled pixel in the tile, channel group
     const int px = pp & 15, py = pp >> 4;
     const int n0 = grp * CPT;
-    float acc[4][CPT];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int n = 0; n < CPT; ++n) acc[j][n] = 0.f;
-    for (int c = 0; c < cin; ++c) {
-        float in[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) in[r][q] = sE[(c * SH + 2 * py + r) * SW + 2 * px + q];
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const float* wrow = sW + ((ky * 3 + kx) * cin + c) * a.C1pad + n0;
-                float wv[CPT];
-#pragma unroll
-                for (int n = 0; n < CPT; n += 4) {
-                    const float4 q = *reinterpret_cast<const float4*>(wrow + n);
-                    wv[n] = q.x; wv[n + 1] = q.y; wv[n + 2] = q.z; wv[n + 3] = q.w;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int n = 0; n < CPT; ++n)
-                        acc[j][n] = __fmaf_rn(in[(j >> 1) + ky][(j & 1) + kx], wv[n], acc[j][n]);
-            }
-    }
-    // pooled, biased, rectified A1 -> shared memory [64 pooled pixels][C1pad], then the error units are written with
-    // consecutive threads on consecutive channels of one pixel (coalesced rows of the layer-1 concat buffer)
-    float* sOut = sW + 9 * cin * a.C1pad;
-    const int ldo = a.C1pad + 1;   // odd pitch: the 64 pooled pixels of a warp pair hit different banks
-#pragma unroll
-    for (int n = 0; n < CPT; ++n) {
-        if (n0 + n >= a.C1) continue;
-        const float bn = a.bA[n0 + n];
-        float m = fmaxf(fmaxf(__fadd_rn(acc[0][n], bn), __fadd_rn(acc[1][n], bn)),
-                        fmaxf(__fadd_rn(acc[2][n], bn), __fadd_rn(acc[3][n], bn)));
-        sOut[pp * ldo + n0 + n] = fmaxf(m, 0.f);  // relu commutes with max
-    }
-    __syncthreads();
     const int Hp = a.H >> 1, Wp = a.W >> 1;
     const int c2 = 2 * a.C1;
-    for (int i = threadIdx.x; i < 64 * c2; i += blockDim.x) {
-        const int q = i / c2, ch = i - q * c2;
-        const int gpy = (y0 >> 1) + (q >> 4), gpx = (x0 >> 1) + (q & 15);
-        if (gpy >= Hp || gpx >= Wp) continue;
-        const long long ppos = ((long long)b * Hp + gpy) * Wp + gpx;
-        const int n = ch < a.C1 ? ch : ch - a.C1;
-        const float m = sOut[q * ldo + n], pv = a.P1[ppos * a.C1 + n];
-        const float e = ch < a.C1 ? __fsub_rn(m, pv) : __fsub_rn(pv, m);
-        view_store(a.dstE1, ppos, ch, e > 0.f ? e : 0.f);
+    for (; item < n_items; item += gridDim.x) {
+        const int nxt = item + gridDim.x;
+        if (pf_ok && nxt < n_items) fetch(nxt);                 // global loads in flight during the FMAs below
+        const float* sEc = sE + cur * e_sz;
+        float acc[4][CPT];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int n = 0; n < CPT; ++n) acc[j][n] = 0.f;
+        for (int c = 0; c < cin; ++c) {
+            float in[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) in[r][q] = sEc[(c * SH + 2 * py + r) * SW + 2 * px + q];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float* wrow = sW + ((ky * 3 + kx) * cin + c) * a.C1pad + n0;
+                    float wv[CPT];
+#pragma unroll
+                    for (int n = 0; n < CPT; n += 4) {
+                        const float4 q = *reinterpret_cast<const float4*>(wrow + n);
+                        wv[n] = q.x; wv[n + 1] = q.y; wv[n + 2] = q.z; wv[n + 3] = q.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int n = 0; n < CPT; ++n)
+                            acc[j][n] = __fmaf_rn(in[(j >> 1) + ky][(j & 1) + kx], wv[n], acc[j][n]);
+                }
+        }
+        // pooled, biased, rectified A1 -> shared memory, then the error units are written with consecutive threads on
+        // consecutive channels of one pixel (coalesced rows of the layer-1 concat buffer)
+#pragma unroll
+        for (int n = 0; n < CPT; ++n) {
+            if (n0 + n >= a.C1) continue;
+            const float bn = a.bA[n0 + n];
+            float m = fmaxf(fmaxf(__fadd_rn(acc[0][n], bn), __fadd_rn(acc[1][n], bn)),
+                            fmaxf(__fadd_rn(acc[2][n], bn), __fadd_rn(acc[3][n], bn)));
+            sOut[pp * ldo + n0 + n] = fmaxf(m, 0.f);  // relu commutes with max
+        }
+        __syncthreads();
+        {
+            const int b = item / tiles, tile = item - b * tiles;
+            const int x0 = (tile % tiles_x) * L0_TW, y0 = (tile / tiles_x) * L0_TH;
+            // batches of 8: the P1 loads of a batch are all in flight before the first store
+            for (int i0 = threadIdx.x; i0 < 64 * c2; i0 += 8 * blockDim.x) {
+                float pv[8], m[8];
+                long long ppos[8];
+                int chn[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * blockDim.x;
+                    ppos[u] = -1;
+                    if (i < 64 * c2) {
+                        const int q = i / c2, ch = i - q * c2;
+                        const int gpy = (y0 >> 1) + (q >> 4), gpx = (x0 >> 1) + (q & 15);
+                        if (gpy < Hp && gpx < Wp) {
+                            ppos[u] = ((long long)b * Hp + gpy) * Wp + gpx;
+                            const int n = ch < a.C1 ? ch : ch - a.C1;
+                            chn[u] = ch;
+                            m[u] = sOut[q * ldo + n];
+                            pv[u] = a.P1[ppos[u] * a.C1 + n];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (ppos[u] < 0) continue;
+                    const float e = chn[u] < a.C1 ? __fsub_rn(m[u], pv[u]) : __fsub_rn(pv[u], m[u]);
+                    view_store(a.dstE1, ppos[u], chn[u], e > 0.f ? e : 0.f);
+                }
+            }
+        }
+        if (nxt < n_items) {
+            if (pf_ok) stash(sE + (cur ^ 1) * e_sz);
+            else stage_direct(nxt, sE + (cur ^ 1) * e_sz);
+        }
+        __syncthreads();
+        cur ^= 1;
     }
 }
 

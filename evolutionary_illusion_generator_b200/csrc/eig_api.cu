@@ -1,6 +1,7 @@
 // libeig.so: context, weight repacking, stage orchestration and the C ABI (include/eig.h).
 // Host-side C++ only orchestrates; every number on the hot path is produced by the CUDA kernels in
 // render.cuh / conv_simt.cuh / conv_tc.cuh / flow.cuh / score.cuh.  There is no CPU fallback.
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -413,11 +414,23 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
     const int l0_tiles = ((c->w + L0_TW - 1) / L0_TW) * ((c->h + L0_TH - 1) / L0_TH);
     {   // E0 -> ConvA1 -> pool -> E1 (layer-1 concat buffer)
         const int c1pad = l0.C1pad;
-        const size_t smem = ((size_t)2 * l0.C0 * (L0_TH + 2) * (L0_TW + 2) + (size_t)9 * 2 * l0.C0 * c1pad + (size_t)64 * (c1pad + 1) + 16) * sizeof(float);
-        if (c1pad <= 4) { auto k = l0_conva1_kernel<4>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(64), smem, s, l0); }
-        else if (c1pad <= 16) { auto k = l0_conva1_kernel<8>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(64 * ((c1pad + 7) / 8)), smem, s, l0); }
-        else if (c1pad <= 48) { auto k = l0_conva1_kernel<12>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(64 * ((c1pad + 11) / 12)), smem, s, l0); }
-        else { auto k = l0_conva1_kernel<16>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(64 * ((c1pad + 15) / 16)), smem, s, l0); }
+        const size_t smem = ((size_t)2 * 2 * l0.C0 * (L0_TH + 2) * (L0_TW + 2) + (size_t)9 * 2 * l0.C0 * c1pad + (size_t)64 * (c1pad + 1) + 16) * sizeof(float);
+        const int n_items = l0_tiles * B;
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+        // persistent grid: a few CTAs per SM (the register file allows 2 of the 256-thread variant), at most one per item
+        // persistent grid: as many CTAs as can be resident (occupancy query per variant), at most one per item
+        auto grid_of = [&](const void* fn, int threads) {
+            int per_sm = 1;
+#ifndef EIG_EMU
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+#endif
+            return dim3((unsigned)std::min(n_items, nsm * per_sm));
+        };
+        if (c1pad <= 4) { auto k = l0_conva1_kernel<4>; LAUNCH_K(CLS_L0, k, grid_of((const void*)k, 64), dim3(64), smem, s, l0, n_items); }
+        else if (c1pad <= 16) { const int th = 64 * ((c1pad + 7) / 8); auto k = l0_conva1_kernel<8>; LAUNCH_K(CLS_L0, k, grid_of((const void*)k, th), dim3(th), smem, s, l0, n_items); }
+        else if (c1pad <= 48) { const int th = 64 * ((c1pad + 11) / 12); auto k = l0_conva1_kernel<12>; LAUNCH_K(CLS_L0, k, grid_of((const void*)k, th), dim3(th), smem, s, l0, n_items); }
+        else { const int th = 64 * ((c1pad + 15) / 16); auto k = l0_conva1_kernel<16>; LAUNCH_K(CLS_L0, k, grid_of((const void*)k, th), dim3(th), smem, s, l0, n_items); }
         CKL();
     }
     for (int n = 2; n < 4; ++n) {  // ConvA_n: E_{n-1} (res n-1) -> pool -> E_n
