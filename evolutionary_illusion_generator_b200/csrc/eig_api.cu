@@ -107,6 +107,11 @@ struct eig_ctx {
     void* d_blob = nullptr; size_t d_blob_cap = 0; long long* d_off = nullptr;
     void* h_pin = nullptr; size_t h_pin_cap = 0;
     cudaStream_t stream = 0;
+    // ConvP_2 / ConvP_3 are off the critical path of a PredNet step: they run on a side stream, ordered by events
+    cudaStream_t side = 0;
+    cudaEvent_t ev_lstm[4] = {nullptr, nullptr, nullptr, nullptr}, ev_p[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool p_pending[4] = {false, false, false, false};
+    bool overlap = true;
     std::vector<void*> allocs;
 };
 
@@ -170,6 +175,16 @@ extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, co
     CK(dalloc(c, &c->vectors, B * FLOW_MAX_CORNERS * 4)); CK(dalloc(c, &c->nvec, B));
     CK(dalloc(c, &c->fitness, B)); CK(dalloc(c, &c->d_off, B + 1));
     CK(dalloc(c, &c->xmat, (size_t)w * h)); CK(dalloc(c, &c->ymat, (size_t)w * h));
+#ifndef EIG_EMU
+    CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    for (int n = 2; n < 4; ++n) {
+        CK(cudaEventCreateWithFlags(&c->ev_lstm[n], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_p[n], cudaEventDisableTiming));
+    }
+    if (const char* e = getenv("EIG_NO_OVERLAP")) c->overlap = atoi(e) == 0;
+#else
+    c->overlap = false;
+#endif
     *out = c;
     return EIG_OK;
 }
@@ -180,6 +195,10 @@ extern "C" void eig_destroy(eig_ctx* c) {
     cudaDeviceSynchronize();
 #ifndef EIG_EMU
     for (int n = 0; n < 4; ++n) { tc_free(c->lw[n].tcA); tc_free(c->lw[n].tcP); tc_free(c->lw[n].tcL); }
+#endif
+#ifndef EIG_EMU
+    for (int n = 2; n < 4; ++n) { if (c->ev_lstm[n]) cudaEventDestroy(c->ev_lstm[n]); if (c->ev_p[n]) cudaEventDestroy(c->ev_p[n]); }
+    if (c->side) cudaStreamDestroy(c->side);
 #endif
     for (void* p : c->allocs) cudaFree(p);
     if (c->d_blob) cudaFree(c->d_blob);
@@ -409,6 +428,7 @@ static L0Args l0_args(eig_ctx* c, const float* x, int B, int cur, int nxt) {
 static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s) {
     const int cur = t & 1, nxt = cur ^ 1;
     const bool tc = c->conv_mode == EIG_CONV_TC;
+    const bool side_ok = c->overlap && !g_prof.on;   // the per-class profiler times launches on one stream
     int rc;
     const L0Args l0 = l0_args(c, x, B, cur, nxt);
     const int l0_tiles = ((c->w + L0_TW - 1) / L0_TW) * ((c->h + L0_TH - 1) / L0_TH);
@@ -434,6 +454,9 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         CKL();
     }
     for (int n = 2; n < 4; ++n) {  // ConvA_n: E_{n-1} (res n-1) -> pool -> E_n
+#ifndef EIG_EMU
+        if (c->p_pending[n]) { CK(cudaStreamWaitEvent(s, c->ev_p[n], 0)); c->p_pending[n] = false; }   // its epilogue reads P_n
+#endif
         ConvArgs a;
         memset(&a, 0, sizeof a);
         a.in_hi = c->X[n - 1][cur]; a.in_lo = lo_plane(c, n - 1, c->X[n - 1][cur]);
@@ -447,7 +470,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }
-    auto conv_p = [&](int n) -> int {   // ConvP_n: R_n -> P_n (layer 1 also emits Z for ConvLSTM0)
+    auto conv_p = [&](int n, cudaStream_t s) -> int {   // ConvP_n: R_n -> P_n (layer 1 also emits Z for ConvLSTM0)
         ConvArgs a;
         memset(&a, 0, sizeof a);
         const int hoff = 2 * c->ch[n] + (n < 3 ? c->ch[n + 1] : 0);
@@ -476,11 +499,21 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         // R_n up-sampled x2 into the concat buffer of layer n-1 (layer 0 gets R_1 through Z instead)
         if (n >= 2) a.dstUp = mkview(c->X[n - 1][cur], lo_plane(c, n - 1, c->X[n - 1][cur]), c->ctot[n - 1], 2 * c->ch[n - 1], c->ch[n]);
 #ifndef EIG_EMU
-        if (tc && c->lw[n].tcL.ok && tc_view_ok(a)) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); continue; }
+        if (tc && c->lw[n].tcL.ok && tc_view_ok(a)) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); }
+        else
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
+#ifndef EIG_EMU
+        if (side_ok && n >= 2) {   // ConvP_n only needs h_n: it overlaps ConvLSTM_{n-1} .. ConvP_0 of this step
+            CK(cudaEventRecord(c->ev_lstm[n], s));
+            CK(cudaStreamWaitEvent(c->side, c->ev_lstm[n], 0));
+            if ((rc = conv_p(n, c->side))) return rc;
+            CK(cudaEventRecord(c->ev_p[n], c->side));
+            c->p_pending[n] = true;
+        }
+#endif
     }
-    if ((rc = conv_p(1))) return rc;   // P_1 and Z (half-resolution partial sums of ConvLSTM0's R1 taps)
+    if ((rc = conv_p(1, s))) return rc;   // P_1 and Z (half-resolution partial sums of ConvLSTM0's R1 taps)
     {   // ConvLSTM_0 on [E0 | up(R1) | h0] (R1 taps via Z), then ConvP_0 -> P0 (this step's prediction)
         if (c->ch[0] == 1) { auto k = l0_lstm_kernel<1>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(128), 0, s, l0); }
         else { auto k = l0_lstm_kernel<3>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(128), 0, s, l0); }
@@ -490,8 +523,19 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         else { auto k = l0_convp_kernel<3>; LAUNCH_K(CLS_L0, k, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, l0); }
         CKL();
     }
+    if (!side_ok)
+        for (int n = 2; n < 4; ++n)
+            if ((rc = conv_p(n, s))) return rc;
+    return EIG_OK;
+}
+
+// the main stream waits for the side-stream ConvP launches still in flight (before anything overwrites / reads P_2, P_3)
+static int join_side(eig_ctx* c, cudaStream_t s) {
+#ifndef EIG_EMU
     for (int n = 2; n < 4; ++n)
-        if ((rc = conv_p(n))) return rc;
+        if (c->p_pending[n]) { CK(cudaStreamWaitEvent(s, c->ev_p[n], 0)); c->p_pending[n] = false; }
+#endif
+    (void)c; (void)s;
     return EIG_OK;
 }
 
@@ -513,6 +557,7 @@ static int prednet_reset(eig_ctx* c, int B, cudaStream_t s) {
 static int prednet_sequence(eig_ctx* c, const float* d_x, int B, int n_in, int n_ext, unsigned char* frames_out,
                             unsigned char* const* gray_dst, cudaStream_t s) {
     int rc;
+    if ((rc = join_side(c, s))) return rc;   // a previous sequence may still have ConvP launches on the side stream
     if ((rc = prednet_reset(c, B, s))) return rc;
     const long long npix = (long long)B * c->h * c->w;
     for (int t = 0; t < n_in + n_ext; ++t) {
@@ -530,7 +575,7 @@ static int prednet_sequence(eig_ctx* c, const float* d_x, int B, int n_in, int n
             }
         }
     }
-    return EIG_OK;
+    return join_side(c, s);
 }
 
 static int check_ready(eig_ctx* c, int n, bool need_w, bool need_grid) {

@@ -265,6 +265,34 @@ def test_full_size_properties_c2(gpu_engine_factory):
     assert (full > 0).mean() > 0.5
 
 
+@pytest.mark.parametrize("name,preset,structure,w,h", [("C4", "bands", 0, 320, 240), ("C5", "free", 2, 512, 512)])
+def test_largest_baseline_configs(gpu_engine_factory, name, preset, structure, w, h):
+    """BASELINE configs[3] / configs[4] (320x240 Bands, 512x512 Free, colour, 3-level LK pyramid): the tensor-core path
+    against the exact-fp32 SIMT path on 3 genomes, and against the CPU oracle on the first one."""
+    ch, c, n = (3, 48, 96, 192), 3, 3
+    wts = W.synthetic_predictor_weights(w, h, ch, seed=0)
+    cfg, pop, progs = _programs(preset, c, list(range(n)))
+    fits = {}
+    for mode in ("simt", "tc"):
+        eng = gpu_engine_factory(w, h, ch, n)
+        eng.set_conv_mode(_lib.CONV_TC if mode == "tc" else _lib.CONV_SIMT)
+        eng.set_grid(structure)
+        eng.load_weights(wts)
+        fits[mode] = eng.evaluate(progs, structure)
+        assert np.array_equal(fits[mode], eng.evaluate(progs, structure))          # deterministic
+        if mode == "tc":
+            dbg = eng.debug_buffers(n)
+    gc = cfg.genome_config
+    ref, extra = OPL.evaluate_population(pop[:1], gc.input_keys, gc.output_keys, structure, wts, w, h, ch, c, keep=True)
+    print("%s fitness simt %s tc %s oracle[0] %s nvec %s" % (name, fits["simt"], fits["tc"], ref, list(dbg["nvec"])))
+    assert np.array_equal(dbg["image"][0], extra[0]["image"])                        # render byte-exact at full size
+
+    def close(a, b):
+        return (a == b) or abs(a - b) <= 1e-3 * max(abs(b), 1e-12) or (np.isnan(a) and np.isnan(b))
+    assert close(fits["simt"][0], ref[0])
+    assert sum(close(a, b) for a, b in zip(fits["tc"], fits["simt"])) >= n - 1
+
+
 def test_tcgen05_conv_self_check():
     """tests/gpu/tc_check (built by csrc/build.sh): the tcgen05 conv against a float64 CPU convolution and, epilogue by
     epilogue, against the exact-fp32 SIMT kernel on identical inputs."""
