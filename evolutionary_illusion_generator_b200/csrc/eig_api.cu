@@ -655,7 +655,7 @@ static int flow_from_gray(eig_ctx* c, int B, cudaStream_t s) {
     LAUNCH_K(CLS_FLOW, lk_track_kernel, dim3((B * FLOW_MAX_CORNERS + LK_WARPS_PER_BLOCK - 1) / LK_WARPS_PER_BLOCK),
                dim3(32 * LK_WARPS_PER_BLOCK), 0, s, la);
     CKL();
-    LAUNCH_K(CLS_FLOW, collect_vectors_kernel, dim3((B + 63) / 64), dim3(64), 0, s, (const float*)c->corners, (const int*)c->ncorners,
+    LAUNCH_K(CLS_FLOW, collect_vectors_kernel, dim3((B + 3) / 4), dim3(128), 0, s, (const float*)c->corners, (const int*)c->ncorners,
                (const float*)c->next_pts, (const unsigned char*)c->status, c->vectors, c->nvec, B);
     CKL();
     return EIG_OK;

@@ -419,23 +419,29 @@ __global__ void __launch_bounds__(32 * LK_WARPS_PER_BLOCK) lk_track_kernel(LkArg
     }
 }
 
-// rows [x0, y0, x1-x0, y1-y0] (fp32) for corners with status 1, in corner order (optical_flow.py:73-82)
+// rows [x0, y0, x1-x0, y1-y0] (fp32) for corners with status 1, in corner order (optical_flow.py:73-82).
+// One warp per genome: ballot + popcount compaction keeps the corner order.
 __global__ void collect_vectors_kernel(const float* corners, const int* ncorners, const float* next_pts,
                                        const unsigned char* status, float* vectors, int* nvec, int B) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b >= B) return;
-    int n = 0;
     const int nc = ncorners[b];
-    for (int k = 0; k < nc; ++k) {
+    int n = 0;
+    for (int k0 = 0; k0 < nc; k0 += 32) {
+        const int k = k0 + lane;
         const long long i = (long long)b * FLOW_MAX_CORNERS + k;
-        if (!status[i]) continue;
-        float* v = vectors + ((long long)b * FLOW_MAX_CORNERS + n) * 4;
-        v[0] = corners[i * 2]; v[1] = corners[i * 2 + 1];
-        v[2] = __fsub_rn(next_pts[i * 2], corners[i * 2]);
-        v[3] = __fsub_rn(next_pts[i * 2 + 1], corners[i * 2 + 1]);
-        ++n;
+        const bool keep = k < nc && status[i] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            float* v = vectors + ((long long)b * FLOW_MAX_CORNERS + n + __popc(m & ((1u << lane) - 1u))) * 4;
+            v[0] = corners[i * 2]; v[1] = corners[i * 2 + 1];
+            v[2] = __fsub_rn(next_pts[i * 2], corners[i * 2]);
+            v[3] = __fsub_rn(next_pts[i * 2 + 1], corners[i * 2 + 1]);
+        }
+        n += __popc(m);
     }
-    nvec[b] = n;
+    if (lane == 0) nvec[b] = n;
 }
 
 }  // namespace eig

@@ -18,7 +18,7 @@ def _load_image(image_path, c_dim, w, h):
     from PIL import Image
     im = Image.open(image_path)
     im = im.convert("RGB") if c_dim == 3 else im.convert("L")
-    a = np.asarray(im)
+    a = np.array(im)
     if a.shape[0] != h or a.shape[1] != w:
         raise ValueError("image is %dx%d, the model expects %dx%d" % (a.shape[1], a.shape[0], w, h))
     return np.ascontiguousarray(a.reshape(h, w, c_dim))

@@ -7,7 +7,8 @@ Same names, argument meaning and side effects on `genome.fitness` as the referen
   get_fitnesses_neat             generate_illusion.py:478-673   -> sets genome.fitness for every genome
   neat_illusion / CLI            generate_illusion.py:676-771   (needs neat-python, which is untouched)
 Differences, all listed in SURVEY.md "defects": no Colab import, no PNG hand-offs between stages (files are
-written only for the best genome), N=1 populations work, Bands planes are reshaped to (h,w), colour uses
+written only for the best genome: best.png, best_black_bg.png, best_flow.png, enhanced.png), N=1 populations
+work, Bands planes are reshaped to (h,w), colour uses
 outputs 0..2 of 6-output configs, the dead 22nd PredNet forward is not computed.
 """
 import argparse
@@ -17,7 +18,7 @@ import numpy as np
 
 from . import engine as engine_mod, genome as G, runtime
 from ._lib import PAIR_POPULATION
-from .grid import StructureType, create_grid  # noqa: F401  (re-exported, reference names)
+from .grid import StructureType, create_grid, enhanced_image_grid  # noqa: F401  (re-exported, reference names)
 
 REPEAT = 20  # generate_illusion.py:482
 
@@ -62,23 +63,49 @@ def get_fitnesses_neat(structure, population, model_name, config, w, h, channels
             best_score, best_i = genome.fitness, i
     print("scores", [[i, float(f)] for i, f in enumerate(fit)])
     if export_best and population:
-        _export_best(eng, population[best_i][1], config, c_dim, gradient, best_dir)
+        _export_best(eng, population[best_i][1], config, c_dim, gradient, best_dir, structure)
     print("best", best_score, best_i)
     return None
 
 
-def _export_best(eng, genome, config, c_dim, gradient, best_dir):
-    """best.png / best_black_bg.png (generate_illusion.py:650-663).  The 800x800 `enhanced.png` mosaic
-    (664-671) is a per-generation cosmetic outside the hot path and is not produced."""
+ENHANCED_SIZE = 800  # generate_illusion.py:665-666
+_render_engines = {}
+
+
+def _render_engine(w, h, c_dim):
+    """Render-only engine (tiny PredNet channels: only the CPPN kernel is used) for the enhanced mosaic."""
+    key = (w, h, c_dim)
+    if key not in _render_engines:
+        _render_engines[key] = engine_mod.Engine(w, h, (c_dim, 4, 4, 4), 1)
+    return _render_engines[key]
+
+
+def _to_pil(arr, c_dim):
     from PIL import Image
+    return Image.fromarray(arr) if c_dim > 1 else Image.fromarray(arr[:, :, 0], "L")
+
+
+def _export_best(eng, genome, config, c_dim, gradient, best_dir, structure=None):
+    """The per-generation files of generate_illusion.py:650-671 for the best genome, without the PNG hand-offs:
+    best.png, best_black_bg.png, best_flow.png (extension frame #1 with the flow vectors drawn,
+    optical_flow.py:10-18,84-86) and enhanced.png (800x800 circle mosaic, lines 664-671; the grid is cached)."""
+    from .optical_flow import draw_tracks
     os.makedirs(best_dir, exist_ok=True)
     prog = G.flatten_genome(genome, config, n_outputs=_used_outputs(c_dim))
     mode = engine_mod.render_mode_for(c_dim, gradient)
     for name, bg in (("best.png", 1.0), ("best_black_bg.png", 0.0)):
         img, _ = eng.render([prog], mode=mode, bg=bg)
-        arr = img[0].cpu().numpy()
-        im = Image.fromarray(arr) if c_dim > 1 else Image.fromarray(arr[:, :, 0], "L")
-        im.save(os.path.join(best_dir, name), "PNG")
+        _to_pil(img[0].cpu().numpy(), c_dim).save(os.path.join(best_dir, name), "PNG")
+    if structure is not None:
+        eng.evaluate([prog], int(structure), mode, PAIR_POPULATION)      # one genome: frames + vectors of the winner
+        dbg = eng.debug_buffers(1)
+        vec = dbg["vectors"][0, :int(dbg["nvec"][0])]
+        frame = dbg["frames"][1, 0]                                      # extension #1 = the image lucas_kanade draws on
+        draw_tracks(_to_pil(frame, c_dim).convert("RGB"), vec).save(os.path.join(best_dir, "best_flow.png"), "PNG")
+        e_eng = _render_engine(ENHANCED_SIZE, ENHANCED_SIZE, c_dim)
+        e_eng.set_grid(grid=enhanced_image_grid(ENHANCED_SIZE, ENHANCED_SIZE, structure))
+        img, _ = e_eng.render([prog], mode=mode, bg=1.0)
+        _to_pil(img[0].cpu().numpy(), c_dim).save(os.path.join(best_dir, "enhanced.png"), "PNG")
 
 
 def neat_illusion(output_dir, model_name, config_path, structure, w, h, channels, c_dim=3, checkpoint=None,

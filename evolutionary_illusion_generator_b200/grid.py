@@ -53,12 +53,15 @@ def polar_cells(x, y, max_radius, direction=1, structure=StructureType.Circles):
         r = np.where(hit, rv, r)
         ring = np.where(hit, n - i - 1, ring)
         assigned |= hit
-    theta = _theta(x, y)
-    theta = np.where(ring % 2 == 1, theta + math.pi / 4.0, theta)
-    if structure == StructureType.Circles:
-        theta = theta % (math.pi / 6.0)
-    if direction < 0:
-        theta = (math.pi / 6.0) - theta
+    if structure in (StructureType.Circles, StructureType.CirclesFree):
+        theta = _theta(x, y)
+        theta = np.where(ring % 2 == 1, theta + math.pi / 4.0, theta)
+        if structure == StructureType.Circles:
+            theta = theta % (math.pi / 6.0)
+        if direction < 0:
+            theta = (math.pi / 6.0) - theta
+    else:   # fill_circle leaves theta at 0 for Bands / Free (generate_illusion.py:66-104)
+        theta = np.zeros(x.shape)
     white = (r > 0.9) | (r < 0.1)
     r_out = np.where(white, -1.0, r / 0.8)
     theta = np.where(white, 0.0, theta)
@@ -111,3 +114,46 @@ def create_grid(structure, x_res=32, y_res=32, scaling=1.0):
                 y_mat = np.where(r_total < h / 2, th, 0.0)
     _cache[key] = (np.ascontiguousarray(x_mat, np.float64), np.ascontiguousarray(y_mat, np.float64))
     return create_grid(structure, x_res, y_res, scaling)
+
+
+_enh_cache = {}
+
+
+def enhanced_image_grid(x_res, y_res, structure):
+    """The 3x3 + 2x2 circle mosaic of the per-generation `enhanced.png` export
+    (/root/reference/generate_illusion.py:121-193), vectorised and cached (it is genome-independent; the reference
+    spends ~10 s per generation in its scalar loops).  Circles alternate direction with their index."""
+    key = (int(x_res), int(y_res), int(structure))
+    if key not in _enh_cache:
+        st = StructureType(int(structure))
+        c_rows = c_cols = 3
+        y_step, x_step = int(y_res / c_cols), int(x_res / c_cols)
+        x_mat = np.ones((y_res, x_res)) * -1
+        y_mat = np.ones((y_res, x_res)) * -1
+        yy, xx = np.meshgrid(np.arange(y_step), np.arange(x_step), indexing="ij")
+        for row in range(c_rows):
+            for col in range(c_cols):
+                index = row * c_cols + col
+                direction = -1 if index % 2 == 0 else 1
+                real_x, real_y = col * x_step + xx, row * y_step + yy
+                x = real_x - (x_step * col + x_step / 2)
+                y = real_y - (y_step * row + y_step / 2)
+                r, theta = polar_cells(x, y, y_step, direction, st)
+                x_mat[real_y, real_x] = r
+                y_mat[real_y, real_x] = theta
+        sub = c_rows - 1
+        for row in range(sub):
+            for col in range(sub):
+                index = c_rows * c_cols + row * sub + col
+                direction = -1 if index % 2 == 0 else 1
+                real_x = col * x_step + xx + int(x_step / 2)
+                real_y = row * y_step + yy + int(y_step / 2)
+                x = real_x - (x_step * col + x_step)
+                y = real_y - (y_step * row + x_step)      # sic: the reference uses x_step for the y centre (line 147)
+                hit = np.sqrt(x * x + y * y) < x_step / 2
+                r, theta = polar_cells(x, y, y_step, direction, st)
+                x_mat[real_y[hit], real_x[hit]] = r[hit]
+                y_mat[real_y[hit], real_x[hit]] = theta[hit]
+        _enh_cache[key] = (x_mat, y_mat)
+    g = _enh_cache[key]
+    return {"x_mat": g[0].copy(), "y_mat": g[1].copy()}

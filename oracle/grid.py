@@ -111,3 +111,48 @@ def create_grid(structure, w, h, scaling=10.0):
                 y_mat[yy, xx] = theta
         return {"x_mat": x_mat, "y_mat": y_mat}
     raise ValueError("unknown structure %r" % (structure,))
+
+
+def enhanced_image_grid(x_res, y_res, structure):
+    """Scalar restatement of `enhanced_image_grid` (/root/reference/generate_illusion.py:121-193): 3x3 circles plus a
+    2x2 overlay, directions alternating with the circle index."""
+    c_rows = c_cols = 3
+    y_step, x_step = int(y_res / c_cols), int(x_res / c_cols)
+    sub_rows = sub_cols = c_rows - 1
+    centers = [None] * (c_rows * c_cols + sub_rows * sub_cols)
+    for y in range(c_rows):
+        for x in range(c_cols):
+            centers[y * c_cols + x] = [x_step * x + x_step / 2, y_step * y + y_step / 2]
+    for y in range(sub_rows):
+        for x in range(sub_cols):
+            centers[c_rows * c_cols + y * sub_cols + x] = [x_step * x + x_step, y_step * y + x_step]
+    y_mat = np.ones((y_res, x_res)) * -1
+    x_mat = np.ones((y_res, x_res)) * -1
+    for row in range(c_rows):
+        for col in range(c_cols):
+            index = row * c_cols + col
+            direction = -1 if index % 2 == 0 else 1
+            for xx in range(x_step):
+                real_x = col * x_step + xx
+                x = real_x - centers[index][0]
+                for yy in range(y_step):
+                    real_y = row * y_step + yy
+                    y = real_y - centers[index][1]
+                    r, theta = polar_cell(x, y, y_step, direction, structure)
+                    x_mat[real_y, real_x] = r
+                    y_mat[real_y, real_x] = theta
+    for row in range(sub_rows):
+        for col in range(sub_cols):
+            index = c_rows * c_cols + row * sub_rows + col
+            direction = -1 if index % 2 == 0 else 1
+            for xx in range(x_step):
+                real_x = (col * x_step + xx) + int(x_step / 2)
+                x = real_x - centers[index][0]
+                for yy in range(y_step):
+                    real_y = (row * y_step + yy) + int(y_step / 2)
+                    y = real_y - centers[index][1]
+                    if np.sqrt(x * x + y * y) < x_step / 2:
+                        r, theta = polar_cell(x, y, y_step, direction, structure)
+                        x_mat[real_y, real_x] = r
+                        y_mat[real_y, real_x] = theta
+    return {"x_mat": x_mat, "y_mat": y_mat}

@@ -138,6 +138,18 @@ def make_flow_and_pipeline():
     print("pipeline.npz, flow_cv2.npz written")
 
 
+def make_enhanced_digest(ns):
+    """sha256 of the planes the reference's own `enhanced_image_grid` returns (generate_illusion.py:121-193)."""
+    import hashlib
+    out = {}
+    for w, h, st in ((800, 800, 1), (800, 800, 0), (300, 240, 3)):
+        g = ns.gi.enhanced_image_grid(w, h, ns.gi.StructureType(st))
+        out["%dx%dx%d" % (w, h, st)] = [hashlib.sha256(np.ascontiguousarray(g["x_mat"], np.float64).tobytes()).hexdigest(),
+                                         hashlib.sha256(np.ascontiguousarray(g["y_mat"], np.float64).tobytes()).hexdigest()]
+    json.dump(out, open(os.path.join(HERE, "enhanced_grid_digest.json"), "w"), indent=1)
+    print("enhanced_grid_digest.json:", list(out))
+
+
 def make_pipeline_predictor():
     """Same as the pipeline cases above but with `synthetic_predictor_weights` (P0 tracks the frame, flow of a
     few hundredths of a pixel, non-zero fitness for most genomes): oracle only, /root/reference not needed."""
@@ -167,9 +179,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "predictor":
         make_pipeline_predictor()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "enhanced":
+        make_enhanced_digest(ref_harness.load())
+        sys.exit(0)
     ns = ref_harness.load()
     make_render(ns)
     make_scoring(ns)
     make_cppn_cases()
+    make_enhanced_digest(ns)
     make_flow_and_pipeline()
     make_pipeline_predictor()

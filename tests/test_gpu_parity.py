@@ -293,6 +293,53 @@ def test_largest_baseline_configs(gpu_engine_factory, name, preset, structure, w
     assert sum(close(a, b) for a, b in zip(fits["tc"], fits["simt"])) >= n - 1
 
 
+def test_reference_call_surface(tmp_path):
+    """The drop-in modules with the reference's names and arguments: get_fitnesses_neat (generate_illusion.py:478-673),
+    get_vectors / calculate_fitness (fitness_calculator.py:468-548), lucas_kanade (optical_flow.py:40-89)."""
+    from PIL import Image
+    from evolutionary_illusion_generator_b200 import fitness_calculator as FC, generate_illusion as GI, optical_flow as OFL
+    w, h, ch, n = 64, 64, (1, 4, 8, 8), 4
+    wts = W.synthetic_predictor_weights(w, h, ch, seed=3)
+    model = str(tmp_path / "prednet.npz")
+    W.save_npz(model, wts)
+    cfg, pop, _ = _programs("circles_bw", 1, list(range(n)))
+    population = [(100 + i, g) for i, g in enumerate(pop)]
+    best_dir = str(tmp_path / "best")
+    assert GI.get_fitnesses_neat(GI.StructureType.Free, population, model, cfg, w, h, ch, c_dim=1, best_dir=best_dir) is None
+    gc = cfg.genome_config
+    ref, extra = OPL.evaluate_population(pop, gc.input_keys, gc.output_keys, 2, wts, w, h, ch, 1, keep=True)
+    got = np.array([g.fitness for _, g in population])
+    assert all(isinstance(g.fitness, float) for _, g in population)
+    assert np.allclose(got, ref, rtol=1e-3, atol=1e-9, equal_nan=True), (got, ref)
+    for name, size in (("best.png", (w, h)), ("best_black_bg.png", (w, h)), ("best_flow.png", (w, h)), ("enhanced.png", (800, 800))):
+        assert Image.open(os.path.join(best_dir, name)).size == size, name
+    best, best_i = 0, 0
+    for i, f in enumerate(ref):           # generate_illusion.py:625-628: `>=` keeps the last of equal scores, NaN never wins
+        if f >= best:
+            best, best_i = f, i
+    assert np.array_equal(np.asarray(Image.open(os.path.join(best_dir, "best.png"))), extra[best_i]["image"])
+    # single-image rating path: input image vs extension #2
+    img_path = str(tmp_path / "img.png")
+    Image.fromarray(extra[0]["image"], "L").save(img_path)
+    vec = FC.get_vectors(img_path, model, ch, w, h)
+    want_vec = OF.lucas_kanade_np(extra[0]["image"], extra[0]["frames"][2])
+    if len(want_vec) == 0:
+        assert len(vec) == 1 and vec[0] is None
+    else:
+        assert np.allclose(np.asarray(vec), want_vec, atol=2e-3)
+        f = FC.calculate_fitness(GI.StructureType.Free, vec, img_path, w, h)
+        assert np.isclose(f, OS.fitness_from_vectors(2, want_vec, w, h), rtol=1e-3, atol=1e-9, equal_nan=True)
+    assert FC.calculate_fitness(GI.StructureType.Circles, [None], img_path, w, h) == 0.0
+    # file-based lucas_kanade: overlay + csv written, vectors identical to the oracle's
+    f1, f2 = str(tmp_path / "a.png"), str(tmp_path / "b.png")
+    Image.fromarray(extra[1]["frames"][0], "L").save(f1)
+    Image.fromarray(extra[1]["frames"][1], "L").save(f2)
+    res = OFL.lucas_kanade(f1, f2, output_path=str(tmp_path / "flow"), verbose=0)
+    want = OF.lucas_kanade_np(extra[1]["frames"][0], extra[1]["frames"][1])
+    assert np.array_equal(np.asarray(res["vectors"], np.float32).reshape(-1, 4), want.reshape(-1, 4))
+    assert os.path.isfile(str(tmp_path / "flow" / "a.png")) and os.path.isfile(str(tmp_path / "flow" / "csv" / "a.csv"))
+
+
 def test_tcgen05_conv_self_check():
     """tests/gpu/tc_check (built by csrc/build.sh): the tcgen05 conv against a float64 CPU convolution and, epilogue by
     epilogue, against the exact-fp32 SIMT kernel on identical inputs."""

@@ -21,6 +21,24 @@ def test_grid_matches_oracle_all_structures():
             assert np.array_equal(a["x_mat"], b["x_mat"]) and np.array_equal(a["y_mat"], b["y_mat"])
 
 
+def test_enhanced_grid_matches_oracle_and_reference_digest():
+    """`enhanced_image_grid` (generate_illusion.py:121-193): vectorised product version == scalar oracle
+    on small mosaics of every structure, and == the reference at 800x800 through the digest recorded by
+    tests/golden/make_golden.py from the reference's own function."""
+    import hashlib
+    import json
+    from conftest import GOLDEN
+    for st, w, h in ((1, 96, 96), (3, 90, 120), (0, 60, 60), (2, 75, 75)):
+        a, b = PG.enhanced_image_grid(w, h, st), OG.enhanced_image_grid(w, h, st)
+        assert np.array_equal(a["x_mat"], b["x_mat"]) and np.array_equal(a["y_mat"], b["y_mat"]), (st, w, h)
+    want = json.load(open(os.path.join(GOLDEN, "enhanced_grid_digest.json")))
+    for key, dig in want.items():
+        w, h, st = [int(v) for v in key.split("x")]
+        g = PG.enhanced_image_grid(w, h, st)
+        assert hashlib.sha256(g["x_mat"].tobytes()).hexdigest() == dig[0], key
+        assert hashlib.sha256(g["y_mat"].tobytes()).hexdigest() == dig[1], key
+
+
 def test_flattener_matches_oracle_on_evolved_genomes():
     w, h = 48, 40
     for preset, c_dim, structure in (("circles_bw", 1, 1), ("circles", 3, 1), ("free", 3, 2)):

@@ -28,6 +28,13 @@ def test_grids_match_reference(ns):
                 assert np.array_equal(np.asarray(ref["y_mat"]).reshape(h, w), impl["y_mat"])
 
 
+def test_enhanced_grid_matches_reference(ns):
+    for s, w, h in ((1, 120, 120), (3, 90, 120), (0, 60, 60), (2, 75, 75)):
+        ref = ns.gi.enhanced_image_grid(w, h, ns.gi.StructureType(s))
+        for impl in (OG.enhanced_image_grid(w, h, s), PG.enhanced_image_grid(w, h, s)):
+            assert np.array_equal(ref["x_mat"], impl["x_mat"]) and np.array_equal(ref["y_mat"], impl["y_mat"])
+
+
 def test_render_matches_reference_on_fresh_genomes(ns):
     w, h = 64, 64
     grid = ns.gi.create_grid(ns.gi.StructureType.Circles, w, h, 10)
