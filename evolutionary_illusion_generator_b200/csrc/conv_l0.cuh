@@ -61,36 +61,38 @@ __global__ void __launch_bounds__(256) l0_conva1_kernel(L0Args a, int n_items) {
     const int n_halo = SH * SW * a.C0;                          // (position, channel) pairs of one halo tile
     for (int i = threadIdx.x; i < 9 * cin * a.C1pad; i += blockDim.x) sW[i] = a.wA[i];
 
+    // the halo slots a thread prefetches are the same for every item: decode them once
     float pf_x[L0_PF], pf_p[L0_PF];
+    int pf_cy[L0_PF], pf_cx[L0_PF], pf_dst[L0_PF], pf_src[L0_PF];   // halo row / column, smem offset, global offset
+#pragma unroll
+    for (int k = 0; k < L0_PF; ++k) {
+        const int i = threadIdx.x + k * blockDim.x;
+        const int c = i % a.C0, pos = i / a.C0;
+        pf_cy[k] = i < n_halo ? pos / SW : -100000;          // an impossible row: never inside the image
+        pf_cx[k] = pos % SW;
+        pf_dst[k] = c * SH * SW + pos;
+        pf_src[k] = ((pf_cy[k] - 1) * a.W + (pf_cx[k] - 1)) * a.C0 + c;
+    }
     auto fetch = [&](int item) {   // halo of `item` -> registers (zeros outside the image)
         const int b = item / tiles, tile = item - b * tiles;
         const int x0 = (tile % tiles_x) * L0_TW, y0 = (tile / tiles_x) * L0_TH;
-        const long long img = (long long)b * a.H * a.W;
+        const long long base = (((long long)b * a.H + y0) * a.W + x0) * a.C0;
 #pragma unroll
         for (int k = 0; k < L0_PF; ++k) {
-            const int i = threadIdx.x + k * blockDim.x;
-            pf_x[k] = 0.f; pf_p[k] = 0.f;
-            if (i < n_halo) {
-                const int c = i % a.C0, pos = i / a.C0;
-                const int cy = pos / SW, cx = pos - cy * SW;
-                const int gy = y0 + cy - 1, gx = x0 + cx - 1;
-                if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-                    const long long idx = (img + (long long)gy * a.W + gx) * a.C0 + c;
-                    pf_x[k] = a.x[idx]; pf_p[k] = a.P0[idx];
-                }
-            }
+            const int gy = y0 + pf_cy[k] - 1, gx = x0 + pf_cx[k] - 1;
+            const bool in = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+            pf_x[k] = in ? a.x[base + pf_src[k]] : 0.f;
+            pf_p[k] = in ? a.P0[base + pf_src[k]] : 0.f;
         }
     };
     auto stash = [&](float* dst) {  // registers -> E0 = [relu(x - P0), relu(P0 - x)] tile in shared memory
 #pragma unroll
         for (int k = 0; k < L0_PF; ++k) {
-            const int i = threadIdx.x + k * blockDim.x;
-            if (i < n_halo) {
-                const int c = i % a.C0, pos = i / a.C0;
+            if (pf_cy[k] >= 0) {
                 float ep = __fsub_rn(pf_x[k], pf_p[k]), en = __fsub_rn(pf_p[k], pf_x[k]);
                 ep = ep > 0.f ? ep : 0.f; en = en > 0.f ? en : 0.f;
-                dst[c * SH * SW + pos] = ep;
-                dst[(a.C0 + c) * SH * SW + pos] = en;
+                dst[pf_dst[k]] = ep;
+                dst[a.C0 * SH * SW + pf_dst[k]] = en;
             }
         }
     };
@@ -174,26 +176,30 @@ __global__ void __launch_bounds__(256) l0_conva1_kernel(L0Args a, int n_items) {
         {
             const int b = item / tiles, tile = item - b * tiles;
             const int x0 = (tile % tiles_x) * L0_TW, y0 = (tile / tiles_x) * L0_TH;
-            // batches of 8: the P1 loads of a batch are all in flight before the first store
-            for (int i0 = threadIdx.x; i0 < 64 * c2; i0 += 8 * blockDim.x) {
+            // element i = (pooled pixel q, channel ch of [E+ | E-]) with i = thread, thread + blockDim, ...: (q, ch) advance
+            // by a fixed step, so the walk needs no division; batches of 8 keep the P1 loads in flight before the stores
+            const int dq = (int)blockDim.x / c2, dch = (int)blockDim.x - dq * c2;
+            int q = (int)threadIdx.x / c2, ch = (int)threadIdx.x - q * c2;
+            const long long prow = ((long long)b * Hp + (y0 >> 1)) * Wp + (x0 >> 1);
+            while (q < 64) {
                 float pv[8], m[8];
                 long long ppos[8];
                 int chn[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int i = i0 + u * blockDim.x;
                     ppos[u] = -1;
-                    if (i < 64 * c2) {
-                        const int q = i / c2, ch = i - q * c2;
+                    if (q < 64) {
                         const int gpy = (y0 >> 1) + (q >> 4), gpx = (x0 >> 1) + (q & 15);
                         if (gpy < Hp && gpx < Wp) {
-                            ppos[u] = ((long long)b * Hp + gpy) * Wp + gpx;
+                            ppos[u] = prow + (long long)(q >> 4) * Wp + (q & 15);
                             const int n = ch < a.C1 ? ch : ch - a.C1;
                             chn[u] = ch;
                             m[u] = sOut[q * ldo + n];
                             pv[u] = a.P1[ppos[u] * a.C1 + n];
                         }
                     }
+                    q += dq; ch += dch;
+                    if (ch >= c2) { ch -= c2; ++q; }
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
