@@ -23,7 +23,7 @@ enum { EPI_CONVP = 0, EPI_CONVA = 1, EPI_LSTM = 2 };
 struct ConvArgs {
     // input view (B, H, W, Cin) inside a buffer with `in_pitch` floats per pixel
     const float* in_hi;
-    const float* in_lo;  // nullable
+    const float* in_lo;  // nullable: non-null = split-fp16 storage, in_hi / in_lo are the two fp16 planes (common.cuh View)
     int in_pitch, in_coff, Cin;
     int B, H, W;
     const float* wgt;   // [9][Cin][Npad], Npad = N rounded up to a multiple of 4

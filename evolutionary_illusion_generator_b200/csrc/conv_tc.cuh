@@ -639,7 +639,7 @@ struct TcState {
     std::string reason, last_error;
     int force_nt = 0;  // EIG_TC_NT: cap on MMA tiles per CTA region
     long long* dbg = nullptr;  // device buffer for the per-role cycle counters (tests only)
-    int last_grid = 0, last_csize = 2, last_nt = 0, last_sa = 0, last_sb = 0;
+    int last_grid = 0, last_nt = 0, last_sa = 0, last_sb = 0;
     int n_sm = 148, max_pairs = 0;
     std::map<int, bool> smem_attr_set;   // cudaFuncSetAttribute is per device
     std::map<std::tuple<const void*, int, int, int, int, int, int, int>, CUtensorMap> amaps;
@@ -673,10 +673,7 @@ inline bool tc_available() {
 }
 inline std::string tc_unavailable_reason() { return tc_state().reason; }
 inline std::string tc_last_error() { return tc_state().last_error; }
-inline void tc_set_kb(int) {}           // kept for tests/gpu/tc_check: the K block is fixed at 32 channels now
 inline void tc_set_max_nt(int nt) { tc_state().force_nt = nt; }
-inline void tc_set_merged(bool) {}
-inline void tc_set_max_cluster(int) {}  // the cluster is always the CTA pair
 
 inline void tc_free(TcWeights& w) {
     if (w.d) cudaFree(w.d);
