@@ -41,6 +41,28 @@ struct L0Args {
 
 enum { L0_TW = 32, L0_TH = 8 };
 
+// ---------------------------------------------------------------------------------------------- E0 for the tensor cores
+// E0 = [relu(x - P0), relu(P0 - x)] as an 8-channel split-fp16 tensor (channels 2*C0 .. 7 zero): the input of ConvA1 when
+// it runs on the tcgen05 kernel (wide first layers, C1 >= 32).  hi / lo: [B*H*W][8] fp16 planes.
+__global__ void __launch_bounds__(256) l0_e0_kernel(const float* x, const float* P0, h16* hi, h16* lo, long long npix, int C0) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    h16 h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { h[i] = 0; l[i] = 0; }
+    for (int c = 0; c < C0; ++c) {
+        const float xv = x[p * C0 + c], pv = P0[p * C0 + c];
+        const float ep = __fsub_rn(xv, pv), en = __fsub_rn(pv, xv);
+        split16(ep > 0.f ? ep : 0.f, &h[c], &l[c]);
+        split16(en > 0.f ? en : 0.f, &h[C0 + c], &l[C0 + c]);
+    }
+    uint4 uh, ul;
+    uh.x = h[0] | ((unsigned)h[1] << 16); uh.y = h[2] | ((unsigned)h[3] << 16); uh.z = h[4] | ((unsigned)h[5] << 16); uh.w = h[6] | ((unsigned)h[7] << 16);
+    ul.x = l[0] | ((unsigned)l[1] << 16); ul.y = l[2] | ((unsigned)l[3] << 16); ul.z = l[4] | ((unsigned)l[5] << 16); ul.w = l[6] | ((unsigned)l[7] << 16);
+    reinterpret_cast<uint4*>(hi)[p] = uh;
+    reinterpret_cast<uint4*>(lo)[p] = ul;
+}
+
 // ---------------------------------------------------------------------------------------------- ConvA1
 // Persistent: each CTA keeps the ConvA1 weights in shared memory and walks work items = (32x8 pixel tile, genome),
 // item = blockIdx.x, blockIdx.x + gridDim.x, ...  The x / P0 halo of the NEXT item is fetched into registers while the

@@ -47,6 +47,7 @@ enum { TC_THREADS = 512, TC_SMEM_LIMIT = 227 * 1024, TC_KB = 32, TC_ROW = 64, TC
 struct TcWeights {
     __half* d = nullptr;  // [2 planes][9 taps][KBn][Npad][32] fp16 (hi plane, then lo plane), scaled by wscale
     int cin = 0, N = 0, Npad = 0, KBn = 0, Ncta = 0, gz = 1;
+    int ksteps = 2;       // 16-channel MMA k-steps per 32-channel block: 1 when the whole input has <= 16 channels
     float wscale = 1.f;   // power of two
     CUtensorMap map;      // weight-tile box: Ncta/2 rows (each CTA of the pair stages its half)
     bool ok = false;
@@ -61,6 +62,7 @@ struct TcParams {
     int a_plane_bytes, b_plane_bytes, b_stage_bytes, a_box_bytes;
     int SA, SB;
     int tmem_cols;
+    int ksteps;                   // 1 or 2 (see TcWeights)
     int egroups;                  // epilogue column groups: 2 (warps 8-15) or 3 (+ warps 0-3, for wide accumulators)
     int staging_bytes, stage_ld;  // ConvA pooling tile: 128 rows x stage_ld floats
     float inv_scale;              // 1 / (activation scale * weight scale), exact power of two
@@ -123,6 +125,12 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t cta) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// "accumulator drained": orders only the epilogue's TMEM reads (tcgen05.wait::ld + tcgen05.fence::before_thread_sync)
+// before the MMAs that overwrite the set - a release would also wait for every global store of the warp (measured:
+// the ERRBAR in front of it was the largest single stall of the epilogue warps)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
@@ -204,7 +212,18 @@ __device__ __forceinline__ float lstm_cell_v(float gi, float gf, float gc, float
     return __fmul_rn(o, tanhf(cn));
 }
 
-__device__ __forceinline__ void view_store4(const View& v, long long pix, int c, const float* val) {
+// 4 values -> the two 8-byte words of their split-fp16 form (packed conversions: two values per cvt)
+__device__ __forceinline__ void split4_pack(const float* val, uint2* uh, uint2* ul) {
+    const float x0 = val[0] * EIG_ACT_SCALE, x1 = val[1] * EIG_ACT_SCALE, x2 = val[2] * EIG_ACT_SCALE, x3 = val[3] * EIG_ACT_SCALE;
+    const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(__fsub_rn(x0, f01.x), __fsub_rn(x1, f01.y));
+    const __half2 l23 = __floats2half2_rn(__fsub_rn(x2, f23.x), __fsub_rn(x3, f23.y));
+    uh->x = *reinterpret_cast<const uint32_t*>(&h01); uh->y = *reinterpret_cast<const uint32_t*>(&h23);
+    ul->x = *reinterpret_cast<const uint32_t*>(&l01); ul->y = *reinterpret_cast<const uint32_t*>(&l23);
+}
+// store 4 consecutive channels; uh / ul = split4_pack(val) (computed once when the same values go to several views)
+__device__ __forceinline__ void view_store4_pre(const View& v, long long pix, int c, const float* val, const uint2& uh, const uint2& ul) {
     const long long idx = pix * v.pitch + v.coff + c;
     if ((v.pitch | v.coff) & 3) {  // not vector aligned
 #pragma unroll
@@ -212,17 +231,16 @@ __device__ __forceinline__ void view_store4(const View& v, long long pix, int c,
         return;
     }
     if (v.lo) {   // split-fp16 planes: 4 halves = 8 bytes per plane
-        h16 h[4], l[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) split16(val[i], &h[i], &l[i]);
-        uint2 uh, ul;
-        uh.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16); uh.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
-        ul.x = (uint32_t)l[0] | ((uint32_t)l[1] << 16); ul.y = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
         *reinterpret_cast<uint2*>(reinterpret_cast<h16*>(v.hi) + idx) = uh;
         *reinterpret_cast<uint2*>(reinterpret_cast<h16*>(v.lo) + idx) = ul;
         return;
     }
     *reinterpret_cast<float4*>(v.hi + idx) = make_float4(val[0], val[1], val[2], val[3]);
+}
+__device__ __forceinline__ void view_store4(const View& v, long long pix, int c, const float* val) {
+    uint2 uh = make_uint2(0u, 0u), ul = uh;
+    if (v.lo) split4_pack(val, &uh, &ul);
+    view_store4_pre(v, pix, c, val, uh, ul);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -295,6 +313,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
     const uint32_t fullB = emptyA + 8 * p.SA, emptyB = fullB + 8 * p.SB;
     const uint32_t accFull = emptyB + 8 * p.SB, accEmpty = accFull + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pipe_bytes + p.staging_bytes + 8 * (2 * p.SA + 2 * p.SB + 4));
+    float* sBias = reinterpret_cast<float*>(smem + pipe_bytes + p.staging_bytes + 8 * (2 * p.SA + 2 * p.SB + 4) + 16);   // [N] bias, read by every epilogue tile
+    for (int i = threadIdx.x; i < p.ca.N; i += TC_THREADS) sBias[i] = p.ca.bias[i];
 
     if (warp == 4 && lane == 0) {
         for (int i = 0; i < p.SA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
@@ -414,9 +434,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                                         tc_mma_f16_pair<0>(d, dal0, desc_hi | bh0, idesc, acc0);
                                         tc_mma_f16_pair<1>(d, dah0, desc_hi | bl0, idesc, 1u);
                                         tc_mma_f16_pair<3>(d, dah0, desc_hi | bh0, idesc, 1u);
-                                        tc_mma_f16_pair<0>(d, dal1, desc_hi | bh1, idesc, 1u);
-                                        tc_mma_f16_pair<1>(d, dah1, desc_hi | bl1, idesc, 1u);
-                                        tc_mma_f16_pair<3>(d, dah1, desc_hi | bh1, idesc, 1u);
+                                        if (p.ksteps == 2) {
+                                            tc_mma_f16_pair<0>(d, dal1, desc_hi | bh1, idesc, 1u);
+                                            tc_mma_f16_pair<1>(d, dah1, desc_hi | bl1, idesc, 1u);
+                                            tc_mma_f16_pair<3>(d, dah1, desc_hi | bh1, idesc, 1u);
+                                        }
                                     }
                                 }
                             }
@@ -501,25 +523,109 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                     float cn[4], hn[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float4 bq = *reinterpret_cast<const float4*>(a.bias + n0 + c0 + q * 4);
+                        const float4 bq = *reinterpret_cast<const float4*>(sBias + n0 + c0 + q * 4);
                         hn[q] = lstm_cell_v(__fmul_rn(v[q * 4], inv), __fmul_rn(v[q * 4 + 1], inv), __fmul_rn(v[q * 4 + 2], inv),
                                             __fmul_rn(v[q * 4 + 3], inv), bq, pcur[q], co[q], &cn[q]);
                     }
                     *reinterpret_cast<float4*>(a.cstate + pix * R + r0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                    view_store4(a.dstH, pix, r0, hn);
+                    uint2 uh = make_uint2(0u, 0u), ul = uh;    // h goes to up to five places: split it once
+                    if (a.dstH.lo || a.dstUp.lo) split4_pack(hn, &uh, &ul);
+                    view_store4_pre(a.dstH, pix, r0, hn, uh, ul);
                     if (a.dstUp.hi) {
                         const int W2 = p.W * 2;
                         const int y = r.y0 + t * p.TH + hh, x = r.x0 + ww;
                         const long long ub = ((long long)b * p.H * 2 + y * 2) * W2 + x * 2;
-                        view_store4(a.dstUp, ub, r0, hn);
-                        view_store4(a.dstUp, ub + 1, r0, hn);
-                        view_store4(a.dstUp, ub + W2, r0, hn);
-                        view_store4(a.dstUp, ub + W2 + 1, r0, hn);
+                        view_store4_pre(a.dstUp, ub, r0, hn, uh, ul);
+                        view_store4_pre(a.dstUp, ub + 1, r0, hn, uh, ul);
+                        view_store4_pre(a.dstUp, ub + W2, r0, hn, uh, ul);
+                        view_store4_pre(a.dstUp, ub + W2 + 1, r0, hn, uh, ul);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(accEmpty_leader + 8 * set);
+                if (lane == 0) mbar_arrive_cluster_relaxed(accEmpty_leader + 8 * set);
+                ++it;
+                continue;
+            }
+            if (a.epi == EPI_CONVA) {
+                // relu -> staging tile -> 2x2 max-pool -> error units at half resolution, in groups of 4 channels: float4
+                // staging stores (pitch = 4 mod 32 floats: conflict-free per quarter warp), float4 pooling reads, float4 P
+                // loads, vector stores.  The P loads run one tile ahead (those of the first tile are issued before the
+                // wait for the accumulator), so their latency hides behind the MMAs / the previous tile.
+                const int Hp = p.H >> 1, Wp = p.W >> 1, tw2 = p.TW >> 1, th2 = p.TH >> 1;
+                const int n4 = ncols >> 2;
+                const int items = th2 * tw2 * n4;
+                const int ethreads = 128 * p.egroups;
+                struct Item { float4 pv; long long ppos; int nn, soff; bool ok; };
+                Item cur[2], nxt[2];
+                auto locate = [&](Item* it2, int t, int base) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int idx = base + u * ethreads + etid;
+                        bool ok = r.active && idx < items;
+                        const int q = idx % n4, pp = idx / n4;
+                        const int ph = pp / tw2, pw = pp - ph * tw2;
+                        const int py = ((r.y0 + t * p.TH) >> 1) + ph, px = (r.x0 >> 1) + pw;
+                        ok = ok && py < Hp && px < Wp;
+                        it2[u].ok = ok;
+                        it2[u].nn = n0 + q * 4;
+                        it2[u].ppos = ok ? ((long long)b * Hp + py) * Wp + px : 0;
+                        it2[u].soff = (ok ? (2 * ph) * p.P + 2 * pw : 0) * p.stage_ld + q * 4;
+                        it2[u].pv = ok ? *reinterpret_cast<const float4*>(a.P + it2[u].ppos * a.N + it2[u].nn) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                };
+                auto pool_store = [&](const Item* it2) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (!it2[u].ok) continue;
+                        const float* s0 = stage + it2[u].soff;
+                        const float4 s00 = *reinterpret_cast<const float4*>(s0), s01 = *reinterpret_cast<const float4*>(s0 + p.stage_ld);
+                        const float4 s10 = *reinterpret_cast<const float4*>(s0 + p.P * p.stage_ld), s11 = *reinterpret_cast<const float4*>(s0 + (p.P + 1) * p.stage_ld);
+                        const float mx[4] = {fmaxf(fmaxf(s00.x, s01.x), fmaxf(s10.x, s11.x)), fmaxf(fmaxf(s00.y, s01.y), fmaxf(s10.y, s11.y)),
+                                             fmaxf(fmaxf(s00.z, s01.z), fmaxf(s10.z, s11.z)), fmaxf(fmaxf(s00.w, s01.w), fmaxf(s10.w, s11.w))};
+                        const float pq[4] = {it2[u].pv.x, it2[u].pv.y, it2[u].pv.z, it2[u].pv.w};
+                        float ep[4], en[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { ep[i] = fmaxf(__fsub_rn(mx[i], pq[i]), 0.f); en[i] = fmaxf(__fsub_rn(pq[i], mx[i]), 0.f); }
+                        view_store4(a.dstE, it2[u].ppos, it2[u].nn, ep);
+                        view_store4(a.dstE, it2[u].ppos, a.N + it2[u].nn, en);
+                    }
+                };
+                locate(nxt, 0, 0);
+                eq = TC_CLK();
+                mbar_wait(accFull + 8 * set, (it >> 1) & 1);
+                e_wait += TC_CLK() - eq;
+                tc_fence_after();
+                for (int t = 0; r.active && t < p.NT; ++t) {
+                    cur[0] = nxt[0]; cur[1] = nxt[1];
+                    if (t + 1 < p.NT) locate(nxt, t + 1, 0);
+                    const uint32_t tcol = lane_addr + (uint32_t)(t * tile_cols);
+                    for (int c0 = half * 16; c0 < ncols; c0 += 16 * p.egroups) {
+                        float v[16];
+                        tmem_ld16(tcol + c0, v);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 bq = *reinterpret_cast<const float4*>(sBias + n0 + c0 + q * 4);
+                            float4 o;
+                            o.x = fmaxf(__fadd_rn(__fmul_rn(v[q * 4], inv), bq.x), 0.f);
+                            o.y = fmaxf(__fadd_rn(__fmul_rn(v[q * 4 + 1], inv), bq.y), 0.f);
+                            o.z = fmaxf(__fadd_rn(__fmul_rn(v[q * 4 + 2], inv), bq.z), 0.f);
+                            o.w = fmaxf(__fadd_rn(__fmul_rn(v[q * 4 + 3], inv), bq.w), 0.f);
+                            *reinterpret_cast<float4*>(stage + m * p.stage_ld + c0 + q * 4) = o;
+                        }
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"r"(ethreads) : "memory");
+                    pool_store(cur);
+                    for (int base = 2 * ethreads; base < items; base += 2 * ethreads) {   // tiles with more items than threads
+                        Item more[2];
+                        locate(more, t, base);
+                        pool_store(more);
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"r"(ethreads) : "memory");
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_relaxed(accEmpty_leader + 8 * set);
                 ++it;
                 continue;
             }
@@ -546,7 +652,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                                     make_float4(__fmul_rn(v[q * 4], inv), __fmul_rn(v[q * 4 + 1], inv), __fmul_rn(v[q * 4 + 2], inv), __fmul_rn(v[q * 4 + 3], inv));
                                 continue;
                             }
-                            const float4 bq = *reinterpret_cast<const float4*>(a.bias + n0 + c0 + q * 4);
+                            const float4 bq = *reinterpret_cast<const float4*>(sBias + n0 + c0 + q * 4);
                             float o[4] = {__fadd_rn(__fmul_rn(v[q * 4], inv), bq.x), __fadd_rn(__fmul_rn(v[q * 4 + 1], inv), bq.y),
                                           __fadd_rn(__fmul_rn(v[q * 4 + 2], inv), bq.z), __fadd_rn(__fmul_rn(v[q * 4 + 3], inv), bq.w)};
                             if (a.epi == EPI_CONVP) {
@@ -559,53 +665,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                             *reinterpret_cast<float4*>(a.outP + pix * nP + col) = make_float4(o[0], o[1], o[2], o[3]);
                         }
                     }
-                } else {  // EPI_CONVA: relu -> staging tile -> 2x2 max-pool -> error units at half resolution
-                    for (int c0 = half * 16; c0 < ncols; c0 += 16 * p.egroups) {
-                        float v[16];
-                        tmem_ld16(tcol + c0, v);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float o = __fadd_rn(__fmul_rn(v[i], inv), a.bias[n0 + c0 + i]);
-                            stage[m * p.stage_ld + c0 + i] = o > 0.f ? o : 0.f;
-                        }
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"r"(128 * p.egroups) : "memory");
-                    const int Hp = p.H >> 1, Wp = p.W >> 1, tw2 = p.TW >> 1, th2 = p.TH >> 1;
-                    const int items = th2 * tw2 * ncols;
-                    for (int base = 0; base < items; base += 4 * 128 * p.egroups) {
-                        float mx[4], pv[4];
-                        long long ppos[4];
-                        int nn[4];
-                        bool okk[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {   // loads first: four independent global reads in flight
-                            const int idx = base + u * 128 * p.egroups + etid;
-                            okk[u] = idx < items;
-                            const int n = idx % ncols, pp = idx / ncols;
-                            const int ph = pp / tw2, pw = pp - ph * tw2;
-                            const int py = ((r.y0 + t * p.TH) >> 1) + ph, px = (r.x0 >> 1) + pw;
-                            okk[u] = okk[u] && py < Hp && px < Wp;
-                            nn[u] = n0 + n;
-                            ppos[u] = okk[u] ? ((long long)b * Hp + py) * Wp + px : 0;
-                            pv[u] = okk[u] ? a.P[ppos[u] * a.N + nn[u]] : 0.f;
-                            const int m00 = okk[u] ? (2 * ph) * p.P + 2 * pw : 0;
-                            const float* s0 = stage + m00 * p.stage_ld + n;
-                            mx[u] = fmaxf(fmaxf(s0[0], s0[p.stage_ld]), fmaxf(s0[p.P * p.stage_ld], s0[(p.P + 1) * p.stage_ld]));
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (!okk[u]) continue;
-                            const float ep = __fsub_rn(mx[u], pv[u]), en = __fsub_rn(pv[u], mx[u]);
-                            view_store(a.dstE, ppos[u], nn[u], ep > 0.f ? ep : 0.f);
-                            view_store(a.dstE, ppos[u], a.N + nn[u], en > 0.f ? en : 0.f);
-                        }
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"r"(128 * p.egroups) : "memory");
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(accEmpty_leader + 8 * set);
+            if (lane == 0) mbar_arrive_cluster_relaxed(accEmpty_leader + 8 * set);
             ++it;
         }
         if (DBG && p.dbg && warp == 8 && lane == 0) {
@@ -690,6 +754,7 @@ inline int tc_pack(TcWeights& w, const float* wv, int cin, int N, int npad, int 
     tc_free(w);
     if (N % 16 || cin % 4) return 0;  // not a tensor-core shape: w.ok stays false, the caller keeps the SIMT kernel
     w.cin = cin; w.N = N; w.KBn = (cin + TC_KB - 1) / TC_KB;
+    w.ksteps = cin <= 16 ? 1 : 2;
     w.Npad = tc_round_up(N, 32);      // each CTA of the pair stages Ncta/2 rows, a multiple of 16
     w.gz = (w.Npad + max_ncta - 1) / max_ncta;
     while (w.Npad % w.gz || (w.Npad / w.gz) % 32) ++w.gz;
@@ -753,7 +818,7 @@ inline bool tc_geometry(int B, int H, int W, int Ncta, int gz, bool pooled, int 
     g.b_plane = (Ncta / 2) * TC_ROW;
     g.b_stage = 2 * g.b_plane;
     const int tile_cols = Ncta;
-    g.stage_ld = Ncta + 1;
+    g.stage_ld = Ncta + 4;   // 4 mod 32 floats: float4 rows, conflict-free staging stores
     g.staging = pooled ? tc_round_up(128 * g.stage_ld * 4, 1024) : 0;
     int nt_cap = 256 / tile_cols;  // two accumulator sets of NT * tile_cols columns in the 512 TMEM columns
     if (nt_cap > row_tiles) nt_cap = row_tiles;
@@ -770,7 +835,7 @@ inline bool tc_geometry(int B, int H, int W, int Ncta, int gz, bool pooled, int 
         const int a_plane = tc_round_up(rows * TC_ROW, 1024);
         int SA = 4, SB = 0;
         for (; SA >= 2; --SA) {   // up to four activation stages while the weight ring still gets >= 4
-            const long long left = (long long)TC_SMEM_LIMIT - 4096 - g.staging - (long long)SA * 2 * a_plane;
+            const long long left = (long long)TC_SMEM_LIMIT - 8192 - g.staging - (long long)SA * 2 * a_plane;
             SB = left > 0 ? (int)(left / g.b_stage) : 0;
             if (SB > 10) SB = 10;
             if (SB >= (SA >= 3 ? 4 : 2)) break;
@@ -783,7 +848,7 @@ inline bool tc_geometry(int B, int H, int W, int Ncta, int gz, bool pooled, int 
         int cols = 32;
         while (cols < 2 * NT * tile_cols) cols <<= 1;
         c.tmem_cols = cols;
-        c.smem = (size_t)SA * 2 * a_plane + (size_t)SB * g.b_stage + g.staging + 8 * (2 * SA + 2 * SB + 4) + 16 + 1024;
+        c.smem = (size_t)SA * 2 * a_plane + (size_t)SB * g.b_stage + g.staging + 8 * (2 * SA + 2 * SB + 4) + 16 + 3072 + 1024;   // + bias [<= 768]
         const int groups = ((c.regions + 1) / 2) * gz;
         const int rounds = (groups + n_pairs - 1) / n_pairs;
         const double eff = (double)c.regions * gz / ((double)rounds * n_pairs * 2);
@@ -805,6 +870,7 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     if (!w.ok) { s.last_error = "tc_conv: weights not packed"; return -1; }
     if (!a.in_lo) { s.last_error = "tc_conv: the input view must be in split-fp16 storage (in_lo = lo plane)"; return -1; }
     if (a.Cin != w.cin || a.N != w.N) { s.last_error = "tc_conv: shape mismatch with packed weights"; return -1; }
+    if (a.N > 768) { s.last_error = "tc_conv: more than 768 output channels (bias staging)"; return -1; }
     if ((a.in_coff & 7) || (a.in_pitch & 7)) { s.last_error = "tc_conv: view not 16-byte aligned"; return -1; }
     const bool pooled = a.epi == EPI_CONVA;
     if (pooled && ((a.H | a.W) & 1)) { s.last_error = "tc_conv: pooled conv needs even H, W"; return -1; }
@@ -861,7 +927,8 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     p.KBn = w.KBn; p.Ncta = w.Ncta; p.N = w.Npad;
     p.a_plane_bytes = g.a_plane; p.b_plane_bytes = g.b_plane; p.b_stage_bytes = g.b_stage; p.a_box_bytes = TC_ROW * g.P * box_rows;
     p.SA = g.SA; p.SB = g.SB; p.tmem_cols = g.tmem_cols;
-    p.egroups = w.Ncta >= 96 ? 3 : 2;
+    p.egroups = (w.Ncta >= 96 || (pooled && w.Ncta >= 48)) ? 3 : 2;
+    p.ksteps = w.ksteps;
     p.staging_bytes = g.staging; p.stage_ld = g.stage_ld;
     p.inv_scale = 1.0f / (EIG_ACT_SCALE * w.wscale);
     p.ca = a;

@@ -90,6 +90,8 @@ struct eig_ctx {
     float* cst[4] = {nullptr};       // cell state [B][H][W][R]
     float* h0[2] = {nullptr, nullptr};  // layer-0 hidden state [B][h][w][C0], double-buffered over time steps
     float* P[4] = {nullptr};         // predictions [B][H][W][C]
+    h16* E0s = nullptr;              // [2 planes][B][h][w][8] split-fp16 E0, input of ConvA1 on the tensor cores (conv_l0.cuh)
+    bool conva1_tc = false;          // ConvA1 runs on the tcgen05 kernel (set at weight load: C1 >= 32)
     float* Z = nullptr;              // [B][H/2][W/2][16*C0] partial sums of ConvLSTM0's up-sampled-R1 taps (conv_l0.cuh)
     int npz = 0;                     // columns of the layer-1 ConvP+Z convolution: C1 + 16*C0
     float* x_in = nullptr;           // [B][h][w][c]
@@ -155,6 +157,7 @@ extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, co
     const size_t npx = B * w * h;
     c->npz = c->ch[1] + 16 * c->ch[0];
     CK(dalloc(c, &c->Z, B * c->H[1] * c->W[1] * 16 * c->ch[0]));
+    CK(dalloc(c, &c->E0s, 2 * npx * 8));
     CK(dalloc(c, &c->x_in, npx * c_dim));
     CK(dalloc(c, &c->img, npx * c_dim));
     CK(dalloc(c, &c->frames, 3 * npx * c_dim));
@@ -319,6 +322,15 @@ extern "C" int eig_load_weights(eig_ctx* c, int nt, const char* const* names, co
             CK(upload(c, &L.convA, wv)); CK(upload(c, &L.convA_b, bv));
 #ifndef EIG_EMU
             if (n >= 2 && (rc = tc_pack(L.tcA, wv.data(), cin, C, npad, 128))) return fail(EIG_E_CUDA, "tc_pack ConvA: " + tc_last_error());
+            if (n == 1) {   // ConvA1 over the 8-channel split-fp16 E0 tensor (channels >= 2*C0 are zero)
+                std::vector<float> w8((size_t)9 * 8 * npad, 0.f);
+                for (int tap = 0; tap < 9; ++tap)
+                    for (int ci = 0; ci < cin; ++ci)
+                        for (int k = 0; k < npad; ++k) w8[((size_t)tap * 8 + ci) * npad + k] = wv[((size_t)tap * cin + ci) * npad + k];
+                if ((rc = tc_pack(L.tcA, w8.data(), 8, C, npad, 128))) return fail(EIG_E_CUDA, "tc_pack ConvA1: " + tc_last_error());
+                c->conva1_tc = L.tcA.ok && C >= 32;
+                if (const char* e = getenv("EIG_CONVA1_TC")) c->conva1_tc = L.tcA.ok && atoi(e) != 0;
+            }
 #endif
         }
         {
@@ -432,6 +444,24 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
     int rc;
     const L0Args l0 = l0_args(c, x, B, cur, nxt);
     const int l0_tiles = ((c->w + L0_TW - 1) / L0_TW) * ((c->h + L0_TH - 1) / L0_TH);
+#ifndef EIG_EMU
+    if (tc && c->conva1_tc) {   // E0 -> split-fp16 tensor, then ConvA1 + pool + E1 on the tcgen05 kernel
+        const long long npix = (long long)B * c->h * c->w;
+        h16* e_lo = c->E0s + (size_t)c->cap * c->h * c->w * 8;
+        LAUNCH_K(CLS_L0, l0_e0_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, x, (const float*)c->P[0], c->E0s, e_lo, npix, c->ch[0]);
+        CKL();
+        ConvArgs a;
+        memset(&a, 0, sizeof a);
+        a.in_hi = reinterpret_cast<const float*>(c->E0s); a.in_lo = reinterpret_cast<const float*>(e_lo);
+        a.in_pitch = 8; a.in_coff = 0; a.Cin = 8;
+        a.B = B; a.H = c->h; a.W = c->w;
+        a.wgt = nullptr; a.bias = c->lw[1].convA_b; a.N = c->ch[1]; a.Npad = (c->ch[1] + 3) & ~3;
+        a.epi = EPI_CONVA; a.P = c->P[1];
+        a.dstE = mkview(c->X[1][cur], lo_plane(c, 1, c->X[1][cur]), c->ctot[1], 0, 2 * c->ch[1]);
+        prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[1].tcA, a, s); prof_post(s); EIG_COUNT_LAUNCH();
+        if (rc) return fail(EIG_E_CUDA, "tc_conv ConvA1: " + tc_last_error());
+    } else
+#endif
     {   // E0 -> ConvA1 -> pool -> E1 (layer-1 concat buffer)
         const int c1pad = l0.C1pad;
         const size_t smem = ((size_t)2 * 2 * l0.C0 * (L0_TH + 2) * (L0_TW + 2) + (size_t)9 * 2 * l0.C0 * c1pad + (size_t)64 * (c1pad + 1) + 16) * sizeof(float);

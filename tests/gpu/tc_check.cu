@@ -267,6 +267,8 @@ static int timing_main() {
             time_shape("ConvP2", 32, 30, 40, 160, 128, 32, 32, EPI_CONVP, max_nt);
             time_shape("ConvP3", 32, 15, 20, 192, 128, 64, 64, EPI_CONVP, max_nt);
             time_shape("LSTM1x4", 128, 60, 80, 80, 0, 80, 64, EPI_LSTM, max_nt);
+            time_shape("A1gray", 32, 120, 160, 8, 0, 8, 16, EPI_CONVA, max_nt);
+            time_shape("A1col", 128, 120, 160, 8, 0, 8, 48, EPI_CONVA, max_nt);
         }
     }
     return 0;
