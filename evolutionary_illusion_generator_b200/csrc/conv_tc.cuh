@@ -191,6 +191,22 @@ __device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc,
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
+// issue only: the 16 destination registers may be read after tmem_ld_wait() - lets the next chunk's TMEM read fly while
+// the current chunk is computed (the LDTM -> first use latency was the top stall of the epilogue warps)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// the registers are in/out operands of the wait so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(
@@ -506,6 +522,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                 mbar_wait(accFull + 8 * set, (it >> 1) & 1);
                 e_wait += TC_CLK() - eq;
                 tc_fence_after();
+                uint32_t racc[16];                       // accumulator chunk of the NEXT item, in flight
+                if (n_items > 0) tmem_ld16_issue(lane_addr + (uint32_t)(nt * tile_cols) + nc0, racc);
                 for (int i = 0; i < n_items; ++i) {
                     const int t = nt, c0 = nc0;
                     const bool valid = nvalid;
@@ -516,7 +534,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                     for (int q = 0; q < 4; ++q) pcur[q] = pq[q];
                     if (i + 1 < n_items) fetch(i + 1);
                     float v[16];
-                    tmem_ld16(lane_addr + (uint32_t)(t * tile_cols) + c0, v);
+                    tmem_ld_wait(racc);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(racc[k]);
+                    if (i + 1 < n_items) tmem_ld16_issue(lane_addr + (uint32_t)(nt * tile_cols) + nc0, racc);   // nt / nc0 are item i+1's now
                     if (!valid) continue;
                     const int r0 = (n0 + c0) >> 2;
                     const float co[4] = {ccur.x, ccur.y, ccur.z, ccur.w};
