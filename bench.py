@@ -48,6 +48,8 @@ def tc_kernel_macs(ch):
     total += 9 * (2 * c2 + c3 + c2) * 4 * c2 / 16.0 + 9 * (2 * c3 + c3) * 4 * c3 / 64.0   # ConvLSTM2, ConvLSTM3
     total += 9 * c1 * c1 / 4.0 + 9 * c2 * c2 / 16.0 + 9 * c3 * c3 / 64.0          # ConvP1..3
     total += 9 * c1 * 4 * c0                                                      # R1 taps of ConvLSTM0
+    if c1 >= 32:
+        total += 9 * 2 * c0 * c1                                                  # ConvA1 (on tcgen05 for wide first layers)
     return total
 USEFUL_STEPS = 21  # 20 static frames + 1 self-fed (the reference's 22nd forward is never read)
 METRIC = "NEAT genome fitness evals/sec (CPPN+PredNet+flow) @160x120"
