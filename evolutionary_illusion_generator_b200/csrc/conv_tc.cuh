@@ -47,7 +47,7 @@ enum { TC_THREADS = 512, TC_SMEM_LIMIT = 227 * 1024, TC_KB = 32, TC_ROW = 64, TC
 struct TcWeights {
     __half* d = nullptr;  // [2 planes][9 taps][KBn][Npad][32] fp16 (hi plane, then lo plane), scaled by wscale
     int cin = 0, N = 0, Npad = 0, KBn = 0, Ncta = 0, gz = 1;
-    int ksteps = 2;       // 16-channel MMA k-steps per 32-channel block: 1 when the whole input has <= 16 channels
+    int ksteps = 2;       // 16-channel MMA k-steps of the LAST 32-channel block: 1 when it holds <= 16 real channels
     float wscale = 1.f;   // power of two
     CUtensorMap map;      // weight-tile box: Ncta/2 rows (each CTA of the pair stages its half)
     bool ok = false;
@@ -62,7 +62,7 @@ struct TcParams {
     int a_plane_bytes, b_plane_bytes, b_stage_bytes, a_box_bytes;
     int SA, SB;
     int tmem_cols;
-    int ksteps;                   // 1 or 2 (see TcWeights)
+    int ksteps;                   // k-steps of the last K block (see TcWeights); all other blocks have 2
     int egroups;                  // epilogue column groups: 2 (warps 8-15) or 3 (+ warps 0-3, for wide accumulators)
     int staging_bytes, stage_ld;  // ConvA pooling tile: 128 rows x stage_ld floats
     float inv_scale;              // 1 / (activation scale * weight scale), exact power of two
@@ -424,6 +424,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                     tc_fence_after();
                     t_a += TC_CLK() - tq;
                     const uint32_t a16 = (((sA + sa * a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
+                    const bool two_ksteps = kb + 1 < p.KBn || p.ksteps == 2;   // a half-empty last block skips its zero k-step
                     uint32_t tap16 = 0;   // (ky * P + kx) rows of 64 bytes, in 16-byte units
                     for (int tap = 0; tap < 9; ++tap) {
                         tq = TC_CLK();
@@ -450,7 +451,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                                         tc_mma_f16_pair<0>(d, dal0, desc_hi | bh0, idesc, acc0);
                                         tc_mma_f16_pair<1>(d, dah0, desc_hi | bl0, idesc, 1u);
                                         tc_mma_f16_pair<3>(d, dah0, desc_hi | bh0, idesc, 1u);
-                                        if (p.ksteps == 2) {
+                                        if (two_ksteps) {
                                             tc_mma_f16_pair<0>(d, dal1, desc_hi | bh1, idesc, 1u);
                                             tc_mma_f16_pair<1>(d, dah1, desc_hi | bl1, idesc, 1u);
                                             tc_mma_f16_pair<3>(d, dah1, desc_hi | bh1, idesc, 1u);
@@ -775,7 +776,7 @@ inline int tc_pack(TcWeights& w, const float* wv, int cin, int N, int npad, int 
     tc_free(w);
     if (N % 16 || cin % 4) return 0;  // not a tensor-core shape: w.ok stays false, the caller keeps the SIMT kernel
     w.cin = cin; w.N = N; w.KBn = (cin + TC_KB - 1) / TC_KB;
-    w.ksteps = cin <= 16 ? 1 : 2;
+    w.ksteps = (cin % TC_KB != 0 && cin % TC_KB <= 16) ? 1 : 2;
     w.Npad = tc_round_up(N, 32);      // each CTA of the pair stages Ncta/2 rows, a multiple of 16
     w.gz = (w.Npad + max_ncta - 1) / max_ncta;
     while (w.Npad % w.gz || (w.Npad / w.gz) % 32) ++w.gz;

@@ -293,6 +293,26 @@ def test_largest_baseline_configs(gpu_engine_factory, name, preset, structure, w
     assert sum(close(a, b) for a, b in zip(fits["tc"], fits["simt"])) >= n - 1
 
 
+def test_tensor_core_path_is_the_one_that_runs(gpu_engine_factory):
+    """In tensor-core mode every layer-1..3 convolution of the BASELINE networks is a tcgen05 launch (no silent fall back
+    to the SIMT kernel): counted with the library's per-class launch instrumentation."""
+    import ctypes as C
+    for ch, c, preset in (((1, 16, 32, 64), 1, "circles_bw"), ((3, 48, 96, 192), 3, "circles")):
+        eng = gpu_engine_factory(160, 120, ch, 4)
+        eng.set_conv_mode(_lib.CONV_TC)
+        eng.set_grid(1)
+        eng.load_weights(W.synthetic_predictor_weights(160, 120, ch, seed=0))
+        _, _, progs = _programs(preset, c, [0, 1, 2])
+        ms, cnt = (C.c_double * 8)(), (C.c_int64 * 8)()
+        eng.lib.check(eng.lib.eig_profile_begin(eng.ctx))
+        eng.evaluate(progs, 1)
+        eng.lib.check(eng.lib.eig_profile_end(eng.ctx, ms, cnt))
+        n_tc, n_simt = int(cnt[2]), int(cnt[1])
+        print("channels %s: %d tcgen05 conv launches, %d SIMT conv launches" % (ch, n_tc, n_simt))
+        assert n_simt == 0
+        assert n_tc == 21 * (9 if ch[1] >= 32 else 8)     # A2 A3 L3 L2 L1 P1+Z P2 P3 (+ ConvA1 for wide first layers)
+
+
 def test_reference_call_surface(tmp_path):
     """The drop-in modules with the reference's names and arguments: get_fitnesses_neat (generate_illusion.py:478-673),
     get_vectors / calculate_fitness (fitness_calculator.py:468-548), lucas_kanade (optical_flow.py:40-89)."""
