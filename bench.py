@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py - genome fitness evaluations per second on N B200s (BASELINE.json metric).
+"""bench.py - genome fitness evaluations per second on N B200s (BASELINE.json metric).  `--workload c4|c5`: the per-GPU shares of the 320x240 / 512x512 configs (not 160x120; informational).
 
 One "step" = one pass of the hot path (CPPN render -> PredNet 20+1 steps -> Shi-Tomasi/LK flow -> score) over
 one synthetic population shard per GPU.  Default workload = BASELINE.json configs[1] ("c2": pop 32,
@@ -33,7 +33,11 @@ WORKLOADS = {
     # name: (preset, c_dim, channels, w, h, structure, pop per GPU, MACs per layer-0 pixel per PredNet step)
     "c2": ("circles_bw", 1, (1, 16, 32, 64), 160, 120, 1, 32, 37269),
     "c3": ("circles", 3, (3, 48, 96, 192), 160, 120, 1, 128, 335421),
+    # per-GPU shares of BASELINE configs[3] / configs[4] on 8 GPUs (pop 256 -> 32, pop 1024 -> 128): stress / roofline
+    "c4": ("bands", 3, (3, 48, 96, 192), 320, 240, 0, 32, 335421),
+    "c5": ("free", 3, (3, 48, 96, 192), 512, 512, 2, 128, 335421),
 }
+STRUCTURE_NAMES = {0: "Bands", 1: "Circles", 2: "Free", 3: "CirclesFree"}
 
 
 def tc_kernel_macs(ch):
@@ -295,7 +299,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": args.workload, "pop_per_gpu": pop, "global_pop": world * pop,
                            "resolution": "%dx%d" % (w, h), "channels": list(ch), "neat_config": preset,
-                           "structure": "Circles", "prednet_steps": USEFUL_STEPS, "conv": args.conv,
+                           "structure": STRUCTURE_NAMES[structure], "prednet_steps": USEFUL_STEPS, "conv": args.conv,
                            "weights": "synthetic_predictor_weights seed 0 (LeCun-normal, layer 0 shaped as an error integrator)", "l2": "flushed between steps (256 MiB memset, untimed)",
                            "parallelism": "genome-sharded dp%d + 1 all-gather/step" % world},
                 "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": int(blob.nbytes + offsets.nbytes),
