@@ -179,7 +179,13 @@ extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, co
     CK(dalloc(c, &c->fitness, B)); CK(dalloc(c, &c->d_off, B + 1));
     CK(dalloc(c, &c->xmat, (size_t)w * h)); CK(dalloc(c, &c->ymat, (size_t)w * h));
 #ifndef EIG_EMU
-    CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    {   // the host entry point runs on its own high-priority stream; the side stream (ConvP_2/3, off the critical path)
+        // gets the lowest priority so that its CTAs only take SMs the critical-path kernels leave idle
+        int least = 0, greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, greatest));
+        CK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, least));
+    }
     for (int n = 2; n < 4; ++n) {
         CK(cudaEventCreateWithFlags(&c->ev_lstm[n], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_p[n], cudaEventDisableTiming));
@@ -202,6 +208,7 @@ extern "C" void eig_destroy(eig_ctx* c) {
 #ifndef EIG_EMU
     for (int n = 2; n < 4; ++n) { if (c->ev_lstm[n]) cudaEventDestroy(c->ev_lstm[n]); if (c->ev_p[n]) cudaEventDestroy(c->ev_p[n]); }
     if (c->side) cudaStreamDestroy(c->side);
+    if (c->stream) cudaStreamDestroy(c->stream);
 #endif
     for (void* p : c->allocs) cudaFree(p);
     if (c->d_blob) cudaFree(c->d_blob);

@@ -47,6 +47,9 @@ class Engine:
         self.ctx = ctx
         self._grid_key = None
         self.structure = None
+        # whole-path evaluations run on a high-priority stream: the library puts ConvP_2/3 on a lowest-priority side
+        # stream, and the block scheduler then gives the critical-path kernels the SMs first
+        self._hp_stream = torch.cuda.Stream(device=self.tdev, priority=-1) if self.tdev.type == "cuda" else None
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -162,9 +165,17 @@ class Engine:
         d_blob, d_off, n, max_slots, max_blob = resident
         if out is None:
             out = torch.empty((n,), dtype=torch.float64, device=self.tdev)
+        if self._hp_stream is None:
+            self.lib.check(self.lib.eig_eval(self.ctx, d_blob.data_ptr(), d_off.data_ptr(), n, max_slots, max_blob,
+                                             int(structure), int(render_mode), int(pair_mode), out.data_ptr(),
+                                             self._stream()))
+            return out
+        cur = torch.cuda.current_stream(self.tdev)
+        self._hp_stream.wait_stream(cur)                 # inputs / `out` may have been produced on the caller's stream
         self.lib.check(self.lib.eig_eval(self.ctx, d_blob.data_ptr(), d_off.data_ptr(), n, max_slots, max_blob,
                                          int(structure), int(render_mode), int(pair_mode), out.data_ptr(),
-                                         self._stream()))
+                                         C.c_void_p(self._hp_stream.cuda_stream)))
+        cur.wait_stream(self._hp_stream)                 # the caller's stream sees the fitness vector in order
         return out
 
     def evaluate_host(self, blob, offsets, max_slots, structure, render_mode=RENDER_GRADIENT,

@@ -53,7 +53,7 @@ def lucas_kanade(file1, file2, output_path="./", vector_scale=60, circle_size=2,
     from PIL import Image
     im1, im2 = Image.open(file1), Image.open(file2)
     mode = "RGB" if (im1.mode != "L" or im2.mode != "L") else "L"
-    a, b = np.asarray(im1.convert(mode)), np.asarray(im2.convert(mode))
+    a, b = np.array(im1.convert(mode)), np.array(im2.convert(mode))
     data = lucas_kanade_arrays(a, b, engine=engine)
     image = None
     os.makedirs(os.path.join(output_path, "csv"), exist_ok=True)   # optical_flow.py:45-46 (always)
