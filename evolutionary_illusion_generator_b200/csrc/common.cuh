@@ -89,6 +89,24 @@ __device__ __forceinline__ void view_store(const View& v, long long pix, int c, 
     else v.hi[idx] = val;
 }
 
+// four consecutive channels (c a multiple of 4); falls back to scalar stores when the view is not vector aligned
+__device__ __forceinline__ void view_store_vec4(const View& v, long long pix, int c, const float* val) {
+    const long long idx = pix * v.pitch + v.coff + c;
+    if ((v.pitch | v.coff | c) & 3) {
+        for (int i = 0; i < 4; ++i) view_store(v, pix, c + i, val[i]);
+    } else if (v.lo) {
+        h16 h[4], l[4];
+        for (int i = 0; i < 4; ++i) split16(val[i], &h[i], &l[i]);
+        uint2 uh, ul;
+        uh.x = (unsigned)h[0] | ((unsigned)h[1] << 16); uh.y = (unsigned)h[2] | ((unsigned)h[3] << 16);
+        ul.x = (unsigned)l[0] | ((unsigned)l[1] << 16); ul.y = (unsigned)l[2] | ((unsigned)l[3] << 16);
+        *reinterpret_cast<uint2*>(reinterpret_cast<h16*>(v.hi) + idx) = uh;
+        *reinterpret_cast<uint2*>(reinterpret_cast<h16*>(v.lo) + idx) = ul;
+    } else {
+        *reinterpret_cast<float4*>(v.hi + idx) = make_float4(val[0], val[1], val[2], val[3]);
+    }
+}
+
 __device__ __forceinline__ float view_load(const float* hi, const float* lo, long long idx) {
     if (lo) return join16(reinterpret_cast<const h16*>(hi)[idx], reinterpret_cast<const h16*>(lo)[idx]);
     return hi[idx];

@@ -198,36 +198,63 @@ __global__ void __launch_bounds__(256) l0_conva1_kernel(L0Args a, int n_items) {
         {
             const int b = item / tiles, tile = item - b * tiles;
             const int x0 = (tile % tiles_x) * L0_TW, y0 = (tile / tiles_x) * L0_TH;
-            // element i = (pooled pixel q, channel ch of [E+ | E-]) with i = thread, thread + blockDim, ...: (q, ch) advance
-            // by a fixed step, so the walk needs no division; batches of 8 keep the P1 loads in flight before the stores
-            const int dq = (int)blockDim.x / c2, dch = (int)blockDim.x - dq * c2;
-            int q = (int)threadIdx.x / c2, ch = (int)threadIdx.x - q * c2;
             const long long prow = ((long long)b * Hp + (y0 >> 1)) * Wp + (x0 >> 1);
-            while (q < 64) {
-                float pv[8], m[8];
-                long long ppos[8];
-                int chn[8];
+            if ((a.C1 & 3) == 0) {
+                // item = (pooled pixel q, group of 4 channels): one float4 P1 load, two vector stores (E+ and E-); the
+                // walk advances (q, g) by a fixed step, so it needs no division; 4 items per batch keep the loads in flight
+                const int g4 = a.C1 >> 2;
+                const int dq = (int)blockDim.x / g4, dg = (int)blockDim.x - dq * g4;
+                int q = (int)threadIdx.x / g4, g = (int)threadIdx.x - q * g4;
+                while (q < 64) {
+                    float4 pv[4];
+                    float m[4][4];
+                    long long ppos[4];
+                    int ch0[4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    ppos[u] = -1;
-                    if (q < 64) {
-                        const int gpy = (y0 >> 1) + (q >> 4), gpx = (x0 >> 1) + (q & 15);
-                        if (gpy < Hp && gpx < Wp) {
-                            ppos[u] = prow + (long long)(q >> 4) * Wp + (q & 15);
-                            const int n = ch < a.C1 ? ch : ch - a.C1;
-                            chn[u] = ch;
-                            m[u] = sOut[q * ldo + n];
-                            pv[u] = a.P1[ppos[u] * a.C1 + n];
+                    for (int u = 0; u < 4; ++u) {
+                        ppos[u] = -1;
+                        if (q < 64) {
+                            const int gpy = (y0 >> 1) + (q >> 4), gpx = (x0 >> 1) + (q & 15);
+                            if (gpy < Hp && gpx < Wp) {
+                                ppos[u] = prow + (long long)(q >> 4) * Wp + (q & 15);
+                                ch0[u] = 4 * g;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) m[u][k] = sOut[q * ldo + 4 * g + k];
+                                pv[u] = *reinterpret_cast<const float4*>(a.P1 + ppos[u] * a.C1 + 4 * g);
+                            }
                         }
+                        q += dq; g += dg;
+                        if (g >= g4) { g -= g4; ++q; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (ppos[u] < 0) continue;
+                        const float p4[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w};
+                        float ep[4], en[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float d1 = __fsub_rn(m[u][k], p4[k]), d2 = __fsub_rn(p4[k], m[u][k]);
+                            ep[k] = d1 > 0.f ? d1 : 0.f; en[k] = d2 > 0.f ? d2 : 0.f;
+                        }
+                        view_store_vec4(a.dstE1, ppos[u], ch0[u], ep);
+                        view_store_vec4(a.dstE1, ppos[u], a.C1 + ch0[u], en);
+                    }
+                }
+            } else {
+                // scalar walk for channel counts that are not a multiple of 4 (small test networks)
+                const int dq = (int)blockDim.x / c2, dch = (int)blockDim.x - dq * c2;
+                int q = (int)threadIdx.x / c2, ch = (int)threadIdx.x - q * c2;
+                while (q < 64) {
+                    const int gpy = (y0 >> 1) + (q >> 4), gpx = (x0 >> 1) + (q & 15);
+                    if (gpy < Hp && gpx < Wp) {
+                        const long long ppos = prow + (long long)(q >> 4) * Wp + (q & 15);
+                        const int n = ch < a.C1 ? ch : ch - a.C1;
+                        const float m = sOut[q * ldo + n], pv = a.P1[ppos * a.C1 + n];
+                        const float e = ch < a.C1 ? __fsub_rn(m, pv) : __fsub_rn(pv, m);
+                        view_store(a.dstE1, ppos, ch, e > 0.f ? e : 0.f);
                     }
                     q += dq; ch += dch;
                     if (ch >= c2) { ch -= c2; ++q; }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (ppos[u] < 0) continue;
-                    const float e = chn[u] < a.C1 ? __fsub_rn(m[u], pv[u]) : __fsub_rn(pv[u], m[u]);
-                    view_store(a.dstE1, ppos[u], chn[u], e > 0.f ? e : 0.f);
                 }
             }
         }
