@@ -332,6 +332,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
     float* sBias = reinterpret_cast<float*>(smem + pipe_bytes + p.staging_bytes + 8 * (2 * p.SA + 2 * p.SB + 4) + 16);   // [N] bias, read by every epilogue tile
     for (int i = threadIdx.x; i < p.ca.N; i += TC_THREADS) sBias[i] = p.ca.bias[i];
 
+    if (warp == 6 && lane == 0) {   // hide the descriptor fetch of the first TMA loads behind the barrier / TMEM set-up
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&mAh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&mAl) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&mB) : "memory");
+    }
     if (warp == 4 && lane == 0) {
         for (int i = 0; i < p.SA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
         for (int i = 0; i < p.SB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
