@@ -293,6 +293,30 @@ def test_largest_baseline_configs(gpu_engine_factory, name, preset, structure, w
     assert sum(close(a, b) for a, b in zip(fits["tc"], fits["simt"])) >= n - 1
 
 
+@pytest.mark.parametrize("c", [1, 3])
+def test_every_structure_and_render_mode_end_to_end(gpu_engine_factory, c):
+    """All four StructureType grids x gradient on / off (gray: np.round path, colour: palette path,
+    generate_illusion.py:404-458) through the whole path on small frames, against the CPU oracle."""
+    w, h, ch, n = 80, 64, (c, 4, 8, 8), 3     # Bands needs w % 10 == 0 (generate_illusion.py:222-227)
+    preset = "circles_bw" if c == 1 else "circles"
+    wts = W.synthetic_predictor_weights(w, h, ch, seed=5)
+    cfg, pop, progs = _programs(preset, c, [3, 4, 5], evolved=True)
+    gc = cfg.genome_config
+    eng = gpu_engine_factory(w, h, ch, n)
+    eng.load_weights(wts)
+    for structure in range(4):
+        eng.set_grid(structure)
+        for gradient in (1, 0):
+            mode = E.render_mode_for(c, gradient)
+            fit = eng.evaluate(progs, structure, render_mode=mode)
+            dbg = eng.debug_buffers(n)
+            ref, extra = OPL.evaluate_population(pop, gc.input_keys, gc.output_keys, structure, wts, w, h, ch, c,
+                                                 gradient=gradient, keep=True)
+            for i in range(n):
+                assert np.array_equal(_sq(dbg["image"][i], c), extra[i]["image"]), (structure, gradient, i)
+            assert np.allclose(fit, ref, rtol=1e-3, atol=1e-9, equal_nan=True), (structure, gradient, fit, ref)
+
+
 def test_tensor_core_path_is_the_one_that_runs(gpu_engine_factory):
     """In tensor-core mode every layer-1..3 convolution of the BASELINE networks is a tcgen05 launch (no silent fall back
     to the SIMT kernel): counted with the library's per-class launch instrumentation."""
