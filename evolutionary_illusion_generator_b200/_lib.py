@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeig.so")
 
-EIG_OK, EIG_E_INVALID, EIG_E_CUDA, EIG_E_STATE, EIG_E_CAPACITY, EIG_E_NODEVICE = 0, -1, -2, -3, -4, -5
+EIG_OK, EIG_E_INVALID, EIG_E_CUDA, EIG_E_STATE, EIG_E_CAPACITY, EIG_E_NODEVICE, EIG_E_RANGE = 0, -1, -2, -3, -4, -5, -6
 CONV_SIMT, CONV_TC = 0, 1
 PAIR_POPULATION, PAIR_SINGLE_IMAGE = 0, 1
 

@@ -75,8 +75,24 @@ __host__ __device__ __forceinline__ h16 f2h(float f) { return __half_as_ushort(_
 __host__ __device__ __forceinline__ float h2f(h16 h) { return __half2float(__ushort_as_half(h)); }
 #endif
 
+// Split-fp16 storage covers |v| < 65504 / 16 = 4094.  PredNet activations are O(1); a weight file that drives them out of
+// range (or to NaN) raises this flag instead of silently producing inf - inf: the scoring kernel hands it to the host
+// with the fitness vector and eig_eval_host fails with EIG_E_RANGE (use conv_mode SIMT for such a model).
+#ifdef EIG_EMU
+static int g_eig_range_flag = 0;
+#define EIG_NOTE_RANGE(x) do { if (!(fabsf(x) <= 65504.f)) g_eig_range_flag = 1; } while (0)
+#else
+__device__ int g_eig_range_flag = 0;
+#ifdef __CUDA_ARCH__
+#define EIG_NOTE_RANGE(x) do { if (!(fabsf(x) <= 65504.f)) g_eig_range_flag = 1; } while (0)
+#else
+#define EIG_NOTE_RANGE(x) do { } while (0)
+#endif
+#endif
+
 __host__ __device__ __forceinline__ void split16(float v, h16* h, h16* l) {
     const float x = v * EIG_ACT_SCALE;        // exact (power of two)
+    EIG_NOTE_RANGE(x);
     const h16 hh = f2h(x);
     *h = hh;
     *l = f2h(x - h2f(hh));                    // the difference is exact in fp32

@@ -231,6 +231,7 @@ __device__ __forceinline__ float lstm_cell_v(float gi, float gf, float gc, float
 // 4 values -> the two 8-byte words of their split-fp16 form (packed conversions: two values per cvt)
 __device__ __forceinline__ void split4_pack(const float* val, uint2* uh, uint2* ul) {
     const float x0 = val[0] * EIG_ACT_SCALE, x1 = val[1] * EIG_ACT_SCALE, x2 = val[2] * EIG_ACT_SCALE, x3 = val[3] * EIG_ACT_SCALE;
+    EIG_NOTE_RANGE(fmaxf(fmaxf(fabsf(x0), fabsf(x1)), fmaxf(fabsf(x2), fabsf(x3))) + (x0 + x1 + x2 + x3) * 0.f);   // the sum term carries a NaN
     const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
     const __half2 l01 = __floats2half2_rn(__fsub_rn(x0, f01.x), __fsub_rn(x1, f01.y));

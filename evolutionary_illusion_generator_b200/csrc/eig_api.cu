@@ -176,7 +176,7 @@ extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, co
     CK(dalloc(c, &c->corners, B * FLOW_MAX_CORNERS * 2)); CK(dalloc(c, &c->ncorners, B));
     CK(dalloc(c, &c->next_pts, B * FLOW_MAX_CORNERS * 2)); CK(dalloc(c, &c->status, B * FLOW_MAX_CORNERS));
     CK(dalloc(c, &c->vectors, B * FLOW_MAX_CORNERS * 4)); CK(dalloc(c, &c->nvec, B));
-    CK(dalloc(c, &c->fitness, B)); CK(dalloc(c, &c->d_off, B + 1));
+    CK(dalloc(c, &c->fitness, B + 1)); CK(dalloc(c, &c->d_off, B + 1));   // fitness[B] = status slot
     CK(dalloc(c, &c->xmat, (size_t)w * h)); CK(dalloc(c, &c->ymat, (size_t)w * h));
 #ifndef EIG_EMU
     {   // the host entry point runs on its own high-priority stream; the side stream (ConvP_2/3, off the critical path)
@@ -720,6 +720,7 @@ extern "C" int eig_flow(eig_ctx* c, const uint8_t* d_img1, const uint8_t* d_img2
 static int score_launch(eig_ctx* c, const float* vec, const int* nvec, int n, int structure, double* fit, cudaStream_t s) {
     if (structure < 0 || structure > 3) return fail(EIG_E_INVALID, "unknown structure id");
     ScoreArgs sa; sa.vectors = vec; sa.nvec = nvec; sa.fitness = fit; sa.B = n; sa.structure = structure; sa.w = c->w; sa.h = c->h;
+    sa.status = fit == c->fitness ? c->fitness + c->cap : nullptr;   // only the host entry point collects the range flag
     LAUNCH_K(CLS_SCORE, score_kernel, dim3(n), dim3(32), 0, s, sa);
     CKL();
     return EIG_OK;
@@ -779,8 +780,13 @@ extern "C" int eig_eval_host(eig_ctx* c, const void* h_blob, const int64_t* h_of
     if ((rc = eig_eval(c, c->d_blob, (const int64_t*)c->d_off, n, max_slots, max_blob, structure, render_mode, pair_mode,
                        c->fitness, (void*)(intptr_t)s)))
         return rc;
+    double status = 0.0;
     CK(cudaMemcpyAsync(h_fitness, c->fitness, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&status, c->fitness + c->cap, sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (status != 0.0)
+        return fail(EIG_E_RANGE, "an activation left the split-fp16 range (|v| >= 4094) or became NaN in tensor-core mode; "
+                                 "this weight file needs conv_mode EIG_CONV_SIMT");
     return EIG_OK;
 }
 

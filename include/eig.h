@@ -25,7 +25,8 @@ enum {
     EIG_E_CUDA = -2,      /* CUDA runtime / driver error */
     EIG_E_STATE = -3,     /* weights or grid not loaded yet */
     EIG_E_CAPACITY = -4,  /* population larger than max_genomes, genome too large for shared memory */
-    EIG_E_NODEVICE = -5   /* no CUDA device: there is no CPU fallback */
+    EIG_E_NODEVICE = -5,  /* no CUDA device: there is no CPU fallback */
+    EIG_E_RANGE = -6      /* tensor-core mode: an activation left the split-fp16 range (|v| >= 4094) or became NaN */
 };
 
 /* structure ids = StructureType, generate_illusion.py:25-29 */

@@ -317,6 +317,28 @@ def test_every_structure_and_render_mode_end_to_end(gpu_engine_factory, c):
             assert np.allclose(fit, ref, rtol=1e-3, atol=1e-9, equal_nan=True), (structure, gradient, fit, ref)
 
 
+def test_out_of_range_activations_fail_loudly_in_tensor_core_mode(gpu_engine_factory):
+    """Split-fp16 storage covers |activation| < 4094: a weight file that leaves the range must produce EIG_E_RANGE from the
+    host entry point (not silent infinities); the exact-fp32 SIMT mode still evaluates it."""
+    w, h, ch = 64, 64, (1, 16, 32, 64)
+    wts = W.synthetic_predictor_weights(w, h, ch, seed=0)
+    wts = dict(wts)
+    wts["predictor/ConvA2/W"] = wts["predictor/ConvA2/W"] * np.float32(3e5)
+    _, _, progs = _programs("circles_bw", 1, [0, 1])
+    eng = gpu_engine_factory(w, h, ch, 2)
+    eng.set_grid(1)
+    eng.load_weights(wts)
+    eng.set_conv_mode(_lib.CONV_TC)
+    with pytest.raises(_lib.EigError) as ei:
+        eng.evaluate(progs, 1)
+    assert ei.value.code == _lib.EIG_E_RANGE
+    eng.set_conv_mode(_lib.CONV_SIMT)
+    assert eng.evaluate(progs, 1).shape == (2,)
+    eng.load_weights(W.synthetic_predictor_weights(w, h, ch, seed=0))      # the flag does not stick
+    eng.set_conv_mode(_lib.CONV_TC)
+    assert np.all(np.isfinite(eng.evaluate(progs, 1)))
+
+
 def test_tensor_core_path_is_the_one_that_runs(gpu_engine_factory):
     """In tensor-core mode every layer-1..3 convolution of the BASELINE networks is a tcgen05 launch (no silent fall back
     to the SIMT kernel): counted with the library's per-class launch instrumentation."""
