@@ -348,10 +348,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
+    // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as every CTA of this one has
+    // passed this point (its CTAs still need our SMs to free up), and everything above - barrier init, TMEM allocation,
+    // descriptor prefetch, bias staging (weights are constants) - overlaps the tail of the kernel in front of us.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / pair TMA / multicast commit
     tc_fence_after();
+    // all reads of activations / state and all writes happen after the predecessor grid has completed and flushed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int tile_cols = p.Ncta;   // TMEM columns of one MMA tile
     const int acc_stride = p.NT * tile_cols;
@@ -733,6 +739,7 @@ struct TcState {
     long long* dbg = nullptr;  // device buffer for the per-role cycle counters (tests only)
     int last_grid = 0, last_nt = 0, last_sa = 0, last_sb = 0;
     int n_sm = 148, max_pairs = 0;
+    bool pdl = true;   // EIG_TC_PDL=0 disables programmatic dependent launch
     std::map<int, bool> smem_attr_set;   // cudaFuncSetAttribute is per device
     std::map<std::tuple<const void*, int, int, int, int, int, int, int>, CUtensorMap> amaps;
 };
@@ -760,6 +767,7 @@ inline bool tc_available() {
         return false;
     }
     if (const char* e = getenv("EIG_TC_NT")) s.force_nt = atoi(e);
+    if (const char* e = getenv("EIG_TC_PDL")) s.pdl = atoi(e) != 0;
     s.available = true;
     return true;
 }
@@ -914,10 +922,12 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(TC_THREADS); cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see griddepcontrol.* in the kernel
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.blockDim = dim3(TC_THREADS); cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = s.pdl ? 2 : 1;
     if (s.max_pairs == 0) {   // how many CTA pairs can be resident at once
         int n = 0;
         cfg.gridDim = dim3(s.n_sm / 2 * 2);
