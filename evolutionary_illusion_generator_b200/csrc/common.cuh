@@ -8,6 +8,27 @@
 #include <cmath>
 #define EIG_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #define EIG_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+// Programmatic dependent launch (sm_90+): a kernel launched with EIG_LAUNCH_PDL may start while its predecessor in the
+// stream is still draining; it must execute EIG_PDL_WAIT() before it touches anything the predecessor reads or writes
+// (weights are constants and may be staged earlier), and it lets its own successor start early with EIG_PDL_TRIGGER().
+#define EIG_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define EIG_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+template <class... KArgs, class... Args>
+inline cudaError_t eig_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define EIG_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) eig_launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
+#else
+#define EIG_PDL_TRIGGER() do { } while (0)
+#define EIG_PDL_WAIT() do { } while (0)
+#define EIG_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) EIG_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__)
 #endif
 
 namespace eig {

@@ -45,6 +45,7 @@ enum { L0_TW = 32, L0_TH = 8 };
 // E0 = [relu(x - P0), relu(P0 - x)] as an 8-channel split-fp16 tensor (channels 2*C0 .. 7 zero): the input of ConvA1 when
 // it runs on the tcgen05 kernel (wide first layers, C1 >= 32).  hi / lo: [B*H*W][8] fp16 planes.
 __global__ void __launch_bounds__(256) l0_e0_kernel(const float* x, const float* P0, h16* hi, h16* lo, long long npix, int C0) {
+    EIG_PDL_WAIT();   // (no early trigger: multi-wave grid - a successor holding whole SMs would starve our later CTAs)
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npix) return;
     h16 h[8], l[8];
@@ -81,7 +82,9 @@ __global__ void __launch_bounds__(256) l0_conva1_kernel(L0Args a, int n_items) {
     const int tiles_x = (a.W + L0_TW - 1) / L0_TW;
     const int tiles = tiles_x * ((a.H + L0_TH - 1) / L0_TH);
     const int n_halo = SH * SW * a.C0;                          // (position, channel) pairs of one halo tile
-    for (int i = threadIdx.x; i < 9 * cin * a.C1pad; i += blockDim.x) sW[i] = a.wA[i];
+    EIG_PDL_TRIGGER();
+    for (int i = threadIdx.x; i < 9 * cin * a.C1pad; i += blockDim.x) sW[i] = a.wA[i];   // constants: before the wait
+    EIG_PDL_WAIT();
 
     // the halo slots a thread prefetches are the same for every item: decode them once
     float pf_x[L0_PF], pf_p[L0_PF];
@@ -284,6 +287,15 @@ __global__ void __launch_bounds__(128) l0_lstm_kernel(L0Args a) {
     const int b = blockIdx.y;
     const int ctot = 2 * C0 + a.C1 + C0;
     const long long img = (long long)b * a.H * a.W;
+    // (no early trigger here: the grid has more CTAs than fit at once, and a tcgen05 successor holding whole SMs would
+    // starve the later ones - measured slower)
+    for (int i = threadIdx.x; i < 9 * CIN * NG; i += blockDim.x) {   // weights are constants: staged before the wait
+        const int n = i % NG, r = i / NG;
+        const int k = r % CIN, tap = r / CIN;
+        const int c = k < 2 * C0 ? k : k + a.C1;   // skip the R1 channels of the full weight tensor
+        sWt[i] = a.wL[((long long)tap * ctot + c) * NG + n];
+    }
+    EIG_PDL_WAIT();
     for (int i = threadIdx.x; i < SH * SW * C0; i += blockDim.x) {
         const int c = i % C0, pp = i / C0;
         const int cy = pp / SW, cx = pp - cy * SW;
@@ -299,12 +311,6 @@ __global__ void __launch_bounds__(128) l0_lstm_kernel(L0Args a) {
         sIn[c][cy][cx] = ep;
         sIn[C0 + c][cy][cx] = en;
         sIn[2 * C0 + c][cy][cx] = hv;
-    }
-    for (int i = threadIdx.x; i < 9 * CIN * NG; i += blockDim.x) {
-        const int n = i % NG, r = i / NG;
-        const int k = r % CIN, tap = r / CIN;
-        const int c = k < 2 * C0 ? k : k + a.C1;   // skip the R1 channels of the full weight tensor
-        sWt[i] = a.wL[((long long)tap * ctot + c) * NG + n];
     }
     __syncthreads();
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // strip: columns 2*tx, 2*tx+1 of row ty
@@ -367,6 +373,7 @@ __global__ void __launch_bounds__(256) l0_convp_kernel(L0Args a) {
         sW[i] = a.wP[(long long)r * a.C0pad + n];
     }
     if (threadIdx.x < C0) sB[threadIdx.x] = a.bP[threadIdx.x];
+    EIG_PDL_WAIT();
     __syncthreads();
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long npix = (long long)a.B * a.H * a.W;

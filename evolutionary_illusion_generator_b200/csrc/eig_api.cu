@@ -68,6 +68,14 @@ static void prof_post(cudaStream_t s) {
         EIG_COUNT_LAUNCH();                                           \
     } while (0)
 
+#define LAUNCH_K_PDL(cls, kernel, grid, block, smem, s, ...)          \
+    do {                                                              \
+        prof_pre(cls, s);                                             \
+        EIG_LAUNCH_PDL(kernel, grid, block, smem, s, __VA_ARGS__);    \
+        prof_post(s);                                                 \
+        EIG_COUNT_LAUNCH();                                           \
+    } while (0)
+
 struct LayerW {            // repacked weights of one PredNet layer (device)
     float* convA = nullptr; float* convA_b = nullptr;   // [9][2C_{n-1}][Npad]
     float* convP = nullptr; float* convP_b = nullptr;   // [9][R_n][Npad]
@@ -455,7 +463,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
     if (tc && c->conva1_tc) {   // E0 -> split-fp16 tensor, then ConvA1 + pool + E1 on the tcgen05 kernel
         const long long npix = (long long)B * c->h * c->w;
         h16* e_lo = c->E0s + (size_t)c->cap * c->h * c->w * 8;
-        LAUNCH_K(CLS_L0, l0_e0_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, x, (const float*)c->P[0], c->E0s, e_lo, npix, c->ch[0]);
+        LAUNCH_K_PDL(CLS_L0, l0_e0_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, x, (const float*)c->P[0], c->E0s, e_lo, npix, c->ch[0]);
         CKL();
         ConvArgs a;
         memset(&a, 0, sizeof a);
@@ -484,10 +492,10 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
 #endif
             return dim3((unsigned)std::min(n_items, nsm * per_sm));
         };
-        if (c1pad <= 4) { auto k = l0_conva1_kernel<4>; LAUNCH_K(CLS_L0, k, grid_of((const void*)k, 64), dim3(64), smem, s, l0, n_items); }
-        else if (c1pad <= 16) { const int th = 64 * ((c1pad + 7) / 8); auto k = l0_conva1_kernel<8>; LAUNCH_K(CLS_L0, k, grid_of((const void*)k, th), dim3(th), smem, s, l0, n_items); }
-        else if (c1pad <= 48) { const int th = 64 * ((c1pad + 11) / 12); auto k = l0_conva1_kernel<12>; LAUNCH_K(CLS_L0, k, grid_of((const void*)k, th), dim3(th), smem, s, l0, n_items); }
-        else { const int th = 64 * ((c1pad + 15) / 16); auto k = l0_conva1_kernel<16>; LAUNCH_K(CLS_L0, k, grid_of((const void*)k, th), dim3(th), smem, s, l0, n_items); }
+        if (c1pad <= 4) { auto k = l0_conva1_kernel<4>; LAUNCH_K_PDL(CLS_L0, k, grid_of((const void*)k, 64), dim3(64), smem, s, l0, n_items); }
+        else if (c1pad <= 16) { const int th = 64 * ((c1pad + 7) / 8); auto k = l0_conva1_kernel<8>; LAUNCH_K_PDL(CLS_L0, k, grid_of((const void*)k, th), dim3(th), smem, s, l0, n_items); }
+        else if (c1pad <= 48) { const int th = 64 * ((c1pad + 11) / 12); auto k = l0_conva1_kernel<12>; LAUNCH_K_PDL(CLS_L0, k, grid_of((const void*)k, th), dim3(th), smem, s, l0, n_items); }
+        else { const int th = 64 * ((c1pad + 15) / 16); auto k = l0_conva1_kernel<16>; LAUNCH_K_PDL(CLS_L0, k, grid_of((const void*)k, th), dim3(th), smem, s, l0, n_items); }
         CKL();
     }
     for (int n = 2; n < 4; ++n) {  // ConvA_n: E_{n-1} (res n-1) -> pool -> E_n
@@ -552,12 +560,12 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
     }
     if ((rc = conv_p(1, s))) return rc;   // P_1 and Z (half-resolution partial sums of ConvLSTM0's R1 taps)
     {   // ConvLSTM_0 on [E0 | up(R1) | h0] (R1 taps via Z), then ConvP_0 -> P0 (this step's prediction)
-        if (c->ch[0] == 1) { auto k = l0_lstm_kernel<1>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(128), 0, s, l0); }
-        else { auto k = l0_lstm_kernel<3>; LAUNCH_K(CLS_L0, k, dim3(l0_tiles, B), dim3(128), 0, s, l0); }
+        if (c->ch[0] == 1) { auto k = l0_lstm_kernel<1>; LAUNCH_K_PDL(CLS_L0, k, dim3(l0_tiles, B), dim3(128), 0, s, l0); }
+        else { auto k = l0_lstm_kernel<3>; LAUNCH_K_PDL(CLS_L0, k, dim3(l0_tiles, B), dim3(128), 0, s, l0); }
         CKL();
         const long long npix = (long long)B * c->h * c->w;
-        if (c->ch[0] == 1) { auto k = l0_convp_kernel<1>; LAUNCH_K(CLS_L0, k, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, l0); }
-        else { auto k = l0_convp_kernel<3>; LAUNCH_K(CLS_L0, k, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, l0); }
+        if (c->ch[0] == 1) { auto k = l0_convp_kernel<1>; LAUNCH_K_PDL(CLS_L0, k, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, l0); }
+        else { auto k = l0_convp_kernel<3>; LAUNCH_K_PDL(CLS_L0, k, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, l0); }
         CKL();
     }
     if (!side_ok)
