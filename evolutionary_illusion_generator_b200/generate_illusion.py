@@ -47,7 +47,7 @@ def get_image_from_cppn(inputs, genome, c_dim, w, h, config, bg=1, gradient=1, e
 
 
 def get_fitnesses_neat(structure, population, model_name, config, w, h, channels,
-                       id=0, c_dim=3, best_dir=".", gradient=1, export_best=True):
+                       id=0, c_dim=3, best_dir=".", gradient=1, export_best=True, export_async=False):
     """population: [(genome_id, genome)].  On return every genome.fitness is a python float."""
     population = list(population)
     print("Calculating fitnesses of populations: ", len(population))
@@ -63,7 +63,7 @@ def get_fitnesses_neat(structure, population, model_name, config, w, h, channels
             best_score, best_i = genome.fitness, i
     print("scores", [[i, float(f)] for i, f in enumerate(fit)])
     if export_best and population:
-        _export_best(eng, population[best_i][1], config, c_dim, gradient, best_dir, structure)
+        _export_best(eng, population[best_i][1], config, c_dim, gradient, best_dir, structure, export_async)
     print("best", best_score, best_i)
     return None
 
@@ -72,11 +72,14 @@ ENHANCED_SIZE = 800  # generate_illusion.py:665-666
 _render_engines = {}
 
 
-def _render_engine(w, h, c_dim):
-    """Render-only engine (tiny PredNet channels: only the CPPN kernel is used) for the enhanced mosaic."""
-    key = (w, h, c_dim)
+def _render_engine(w, h, c_dim, structure):
+    """Render-only engine (tiny PredNet channels: only the CPPN kernel is used) for the enhanced mosaic; the mosaic's
+    grid planes are uploaded once per structure."""
+    key = (w, h, c_dim, int(structure))
     if key not in _render_engines:
-        _render_engines[key] = engine_mod.Engine(w, h, (c_dim, 4, 4, 4), 1)
+        eng = engine_mod.Engine(w, h, (c_dim, 4, 4, 4), 1)
+        eng.set_grid(grid=enhanced_image_grid(w, h, structure))
+        _render_engines[key] = eng
     return _render_engines[key]
 
 
@@ -85,27 +88,55 @@ def _to_pil(arr, c_dim):
     return Image.fromarray(arr) if c_dim > 1 else Image.fromarray(arr[:, :, 0], "L")
 
 
-def _export_best(eng, genome, config, c_dim, gradient, best_dir, structure=None):
+PNG_COMPRESS_LEVEL = 1   # zlib level of the exported PNGs: level 6 (PIL's default) costs ~0.2 s for the 800x800 mosaic
+_export_pool = None
+_export_pending = []
+
+
+def wait_for_exports():
+    """Block until every background file export (`export_async=True`) has been written."""
+    while _export_pending:
+        _export_pending.pop().result()
+
+
+def _write_pngs(jobs):
+    for image, path in jobs:
+        image.save(path, "PNG", compress_level=PNG_COMPRESS_LEVEL)
+
+
+def _export_best(eng, genome, config, c_dim, gradient, best_dir, structure=None, export_async=False):
     """The per-generation files of generate_illusion.py:650-671 for the best genome, without the PNG hand-offs:
     best.png, best_black_bg.png, best_flow.png (extension frame #1 with the flow vectors drawn,
-    optical_flow.py:10-18,84-86) and enhanced.png (800x800 circle mosaic, lines 664-671; the grid is cached)."""
+    optical_flow.py:10-18,84-86) and enhanced.png (800x800 circle mosaic, lines 664-671; the grid is cached).
+    The GPU work (three renders and one single-genome evaluation) takes a few milliseconds; PNG encoding is the
+    expensive part and can run on a background thread (`export_async`, see wait_for_exports)."""
+    global _export_pool
     from .optical_flow import draw_tracks
     os.makedirs(best_dir, exist_ok=True)
     prog = G.flatten_genome(genome, config, n_outputs=_used_outputs(c_dim))
     mode = engine_mod.render_mode_for(c_dim, gradient)
+    jobs = []
     for name, bg in (("best.png", 1.0), ("best_black_bg.png", 0.0)):
         img, _ = eng.render([prog], mode=mode, bg=bg)
-        _to_pil(img[0].cpu().numpy(), c_dim).save(os.path.join(best_dir, name), "PNG")
+        jobs.append((_to_pil(img[0].cpu().numpy(), c_dim), os.path.join(best_dir, name)))
     if structure is not None:
         eng.evaluate([prog], int(structure), mode, PAIR_POPULATION)      # one genome: frames + vectors of the winner
         dbg = eng.debug_buffers(1)
         vec = dbg["vectors"][0, :int(dbg["nvec"][0])]
         frame = dbg["frames"][1, 0]                                      # extension #1 = the image lucas_kanade draws on
-        draw_tracks(_to_pil(frame, c_dim).convert("RGB"), vec).save(os.path.join(best_dir, "best_flow.png"), "PNG")
-        e_eng = _render_engine(ENHANCED_SIZE, ENHANCED_SIZE, c_dim)
-        e_eng.set_grid(grid=enhanced_image_grid(ENHANCED_SIZE, ENHANCED_SIZE, structure))
+        jobs.append((draw_tracks(_to_pil(frame, c_dim).convert("RGB"), vec), os.path.join(best_dir, "best_flow.png")))
+        e_eng = _render_engine(ENHANCED_SIZE, ENHANCED_SIZE, c_dim, structure)
         img, _ = e_eng.render([prog], mode=mode, bg=1.0)
-        _to_pil(img[0].cpu().numpy(), c_dim).save(os.path.join(best_dir, "enhanced.png"), "PNG")
+        jobs.append((_to_pil(img[0].cpu().numpy(), c_dim), os.path.join(best_dir, "enhanced.png")))
+    if export_async:
+        if _export_pool is None:
+            import atexit
+            from concurrent.futures import ThreadPoolExecutor
+            _export_pool = ThreadPoolExecutor(max_workers=1)      # one writer: files of successive generations stay in order
+            atexit.register(wait_for_exports)
+        _export_pending.append(_export_pool.submit(_write_pngs, jobs))
+    else:
+        _write_pngs(jobs)
 
 
 def neat_illusion(output_dir, model_name, config_path, structure, w, h, channels, c_dim=3, checkpoint=None,

@@ -372,6 +372,11 @@ def test_reference_call_surface(tmp_path):
     population = [(100 + i, g) for i, g in enumerate(pop)]
     best_dir = str(tmp_path / "best")
     assert GI.get_fitnesses_neat(GI.StructureType.Free, population, model, cfg, w, h, ch, c_dim=1, best_dir=best_dir) is None
+    t0 = __import__("time").perf_counter()
+    GI.get_fitnesses_neat(GI.StructureType.Free, population, model, cfg, w, h, ch, c_dim=1, best_dir=best_dir, export_async=True)
+    t_async = __import__("time").perf_counter() - t0
+    GI.wait_for_exports()
+    print("get_fitnesses_neat with background export: %.1f ms" % (1e3 * t_async))
     gc = cfg.genome_config
     ref, extra = OPL.evaluate_population(pop, gc.input_keys, gc.output_keys, 2, wts, w, h, ch, 1, keep=True)
     got = np.array([g.fitness for _, g in population])
