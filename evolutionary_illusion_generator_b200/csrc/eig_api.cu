@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 #ifdef EIG_EMU
 #include "cuda_emu.h"
@@ -122,6 +123,11 @@ struct eig_ctx {
     cudaEvent_t ev_lstm[4] = {nullptr, nullptr, nullptr, nullptr}, ev_p[4] = {nullptr, nullptr, nullptr, nullptr};
     bool p_pending[4] = {false, false, false, false};
     bool overlap = true;
+    // CUDA graphs of everything after the render (PredNet sequence + flow + score), keyed by what the launches depend on;
+    // a key is run once un-captured (lazy initialisations), captured on its second use and replayed afterwards
+    struct GraphEntry { int seen = 0; long long launches = 0; void* exec = nullptr; };
+    std::map<std::tuple<int, int, int, int, const void*>, GraphEntry> graphs;
+    bool use_graphs = true;
     std::vector<void*> allocs;
 };
 
@@ -131,6 +137,14 @@ static cudaError_t dalloc(eig_ctx* c, T** p, size_t count) {
     cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
     if (e == cudaSuccess) { c->allocs.push_back(q); *p = (T*)q; }
     return e;
+}
+
+// captured graphs hold raw pointers to the weight buffers: a new weight file invalidates them
+static void drop_graphs(eig_ctx* c) {
+#ifndef EIG_EMU
+    for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy((cudaGraphExec_t)kv.second.exec);
+#endif
+    c->graphs.clear();
 }
 
 extern "C" const char* eig_last_error(void) { return g_err.c_str(); }
@@ -199,8 +213,10 @@ extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, co
         CK(cudaEventCreateWithFlags(&c->ev_p[n], cudaEventDisableTiming));
     }
     if (const char* e = getenv("EIG_NO_OVERLAP")) c->overlap = atoi(e) == 0;
+    if (const char* e = getenv("EIG_NO_GRAPH")) c->use_graphs = atoi(e) == 0;
 #else
     c->overlap = false;
+    c->use_graphs = false;
 #endif
     *out = c;
     return EIG_OK;
@@ -214,6 +230,7 @@ extern "C" void eig_destroy(eig_ctx* c) {
     for (int n = 0; n < 4; ++n) { tc_free(c->lw[n].tcA); tc_free(c->lw[n].tcP); tc_free(c->lw[n].tcL); }
 #endif
 #ifndef EIG_EMU
+    drop_graphs(c);
     for (int n = 2; n < 4; ++n) { if (c->ev_lstm[n]) cudaEventDestroy(c->ev_lstm[n]); if (c->ev_p[n]) cudaEventDestroy(c->ev_p[n]); }
     if (c->side) cudaStreamDestroy(c->side);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -308,6 +325,8 @@ void build_z_weights(std::vector<float>& dst, int npad, int C1, const std::vecto
 extern "C" int eig_load_weights(eig_ctx* c, int nt, const char* const* names, const float* const* ptrs, const int64_t* shapes) {
     if (!c || !names || !ptrs || !shapes || nt <= 0) return fail(EIG_E_INVALID, "eig_load_weights: null argument");
     CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());   // no evaluation may still be reading the old weights
+    drop_graphs(c);
     WMap m;
     for (int i = 0; i < nt; ++i) {
         std::string k = names[i];
@@ -742,14 +761,9 @@ extern "C" int eig_score(eig_ctx* c, const float* d_vectors, const int* d_nvec, 
     return score_launch(c, d_vectors, d_nvec, n, structure, d_fitness, TO_STREAM(stream));
 }
 
-extern "C" int eig_eval(eig_ctx* c, const void* d_blob, const int64_t* d_offsets, int n, int max_slots, int max_blob_bytes,
-                        int structure, int render_mode, int pair_mode, double* d_fitness, void* stream) {
+// everything after the render: frame protocol, flow, score (all launch arguments depend only on n, the modes and ctx buffers)
+static int eval_after_render(eig_ctx* c, int n, int structure, int pair_mode, double* d_fitness, cudaStream_t s) {
     int rc;
-    if ((rc = check_ready(c, n, true, true))) return rc;
-    if (!d_fitness) return fail(EIG_E_INVALID, "eig_eval: null fitness pointer");
-    if (pair_mode != EIG_PAIR_POPULATION && pair_mode != EIG_PAIR_SINGLE_IMAGE) return fail(EIG_E_INVALID, "unknown pair mode");
-    cudaStream_t s = TO_STREAM(stream);
-    if ((rc = eig_cppn_render(c, d_blob, d_offsets, n, max_slots, max_blob_bytes, render_mode, 1.0, c->img, c->x_in, stream))) return rc;
     const long long npix = (long long)n * c->h * c->w;
     unsigned char* g1 = c->gray[0];
     unsigned char* g2 = c->gray[0] + npix;
@@ -765,6 +779,48 @@ extern "C" int eig_eval(eig_ctx* c, const void* d_blob, const int64_t* d_offsets
     if ((rc = prednet_sequence(c, c->x_in, n, 20, n_ext, c->frames, gd, s))) return rc;
     if ((rc = flow_from_gray(c, n, s))) return rc;
     return score_launch(c, c->vectors, c->nvec, n, structure, d_fitness, s);
+}
+
+extern "C" int eig_eval(eig_ctx* c, const void* d_blob, const int64_t* d_offsets, int n, int max_slots, int max_blob_bytes,
+                        int structure, int render_mode, int pair_mode, double* d_fitness, void* stream) {
+    int rc;
+    if ((rc = check_ready(c, n, true, true))) return rc;
+    if (!d_fitness) return fail(EIG_E_INVALID, "eig_eval: null fitness pointer");
+    if (pair_mode != EIG_PAIR_POPULATION && pair_mode != EIG_PAIR_SINGLE_IMAGE) return fail(EIG_E_INVALID, "unknown pair mode");
+    cudaStream_t s = TO_STREAM(stream);
+    if ((rc = eig_cppn_render(c, d_blob, d_offsets, n, max_slots, max_blob_bytes, render_mode, 1.0, c->img, c->x_in, stream))) return rc;
+#ifndef EIG_EMU
+    if (c->use_graphs && !g_prof.on) {
+        auto key = std::make_tuple(n, structure, pair_mode, c->conv_mode, (const void*)d_fitness);
+        eig_ctx::GraphEntry& ge = c->graphs[key];
+        if (ge.exec) {
+            CK(cudaGraphLaunch((cudaGraphExec_t)ge.exec, s));
+            launch_counter().n += ge.launches;
+            return EIG_OK;
+        }
+        if (ge.seen++ >= 1) {   // second use of this key: capture, instantiate, replay from now on
+            const long long before = launch_counter().n;
+            if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                rc = eval_after_render(c, n, structure, pair_mode, d_fitness, s);
+                cudaGraph_t g = nullptr;
+                const cudaError_t ee = cudaStreamEndCapture(s, &g);
+                cudaGraphExec_t exec = nullptr;
+                if (rc == EIG_OK && ee == cudaSuccess && g && cudaGraphInstantiate(&exec, g, 0) == cudaSuccess) {
+                    cudaGraphDestroy(g);
+                    ge.exec = exec;
+                    ge.launches = launch_counter().n - before;
+                    CK(cudaGraphLaunch(exec, s));
+                    return EIG_OK;
+                }
+                if (g) cudaGraphDestroy(g);
+                cudaGetLastError();
+                launch_counter().n = before;
+            }
+            c->use_graphs = false;   // capture is not possible here (e.g. the caller's stream is already capturing): run directly
+        }
+    }
+#endif
+    return eval_after_render(c, n, structure, pair_mode, d_fitness, s);
 }
 
 extern "C" int eig_eval_host(eig_ctx* c, const void* h_blob, const int64_t* h_offsets, int n, int max_slots, int structure,

@@ -339,6 +339,33 @@ def test_out_of_range_activations_fail_loudly_in_tensor_core_mode(gpu_engine_fac
     assert np.all(np.isfinite(eng.evaluate(progs, 1)))
 
 
+def test_graph_replay_is_transparent(gpu_engine_factory):
+    """The library replays everything after the render from a CUDA graph from the third identical call on.  Direct run,
+    capture run and replays must give the same bits; a new weight file, another population size and another structure
+    must not see stale graphs."""
+    w, h, ch = 64, 64, (1, 16, 32, 64)
+    _, _, progs = _programs("circles_bw", 1, [0, 1, 2, 3])
+    w_a, w_b = W.synthetic_predictor_weights(w, h, ch, seed=1), W.synthetic_predictor_weights(w, h, ch, seed=2)
+    eng = gpu_engine_factory(w, h, ch, 4)
+    eng.set_conv_mode(_lib.CONV_TC)
+    eng.set_grid(1)
+    eng.load_weights(w_a)
+    runs = [eng.evaluate(progs, 1) for _ in range(4)]          # direct, capture, replay, replay
+    assert all(np.array_equal(runs[0], r) for r in runs[1:])
+    three = [eng.evaluate(progs[:3], 1) for _ in range(3)]     # other n: its own graph
+    assert all(np.array_equal(three[0], r) for r in three) and np.array_equal(three[0], runs[0][:3])
+    eng.load_weights(w_b)                                      # drops the graphs
+    b_runs = [eng.evaluate(progs, 1) for _ in range(3)]
+    fresh = gpu_engine_factory(w, h, ch, 4)
+    fresh.set_conv_mode(_lib.CONV_TC); fresh.set_grid(1); fresh.load_weights(w_b)
+    want_b = fresh.evaluate(progs, 1)
+    assert all(np.array_equal(want_b, r) for r in b_runs) and not np.array_equal(want_b, runs[0])
+    eng.set_grid(2)                                            # other structure: new grid planes + its own graph
+    free_runs = [eng.evaluate(progs, 2) for _ in range(3)]
+    fresh.set_grid(2)
+    assert all(np.array_equal(fresh.evaluate(progs, 2), r) for r in free_runs)
+
+
 def test_tensor_core_path_is_the_one_that_runs(gpu_engine_factory):
     """In tensor-core mode every layer-1..3 convolution of the BASELINE networks is a tcgen05 launch (no silent fall back
     to the SIMT kernel): counted with the library's per-class launch instrumentation."""
