@@ -282,6 +282,9 @@ def run_ours(args):
                     "frac_of_3pass_ceiling": 3.0 * achieved / peaks["tf"] if args.conv == "tc" else None,
                     "class_ms_per_step": cls_ms, "class_launches_per_step": cls_n,
                     "whole_path_gflop_per_genome": 2.0 * macs * w * h * USEFUL_STEPS / 1e9,
+                    "timing": "per-launch CUDA events of an instrumented pass of the same step (library launch instrumentation; "
+                              "graph replay, side-stream overlap and programmatic dependent launch are off in that pass, "
+                              "so the class times are upper bounds of their share of ms_per_step)",
                     "note": "achieved counts each algorithmic MAC once; fp32-grade accuracy needs 3 fp16 MMAs per MAC "
                             "(hi*hi + hi*lo + lo*hi), so 1/3 of the dense 16-bit peak is the ceiling of this kernel"}
         cpu = None
