@@ -704,7 +704,7 @@ static int flow_from_gray(eig_ctx* c, int B, cudaStream_t s) {
     CKL();
     CornerArgs ca; ca.eig = c->eigmap; ca.eig_max_key = c->eigmax; ca.cand = c->cand; ca.corners = c->corners;
     ca.ncorners = c->ncorners; ca.H = H; ca.W = W;
-    LAUNCH_K(CLS_FLOW, corner_select_kernel, dim3(B), dim3(256), 0, s, ca);
+    LAUNCH_K(CLS_FLOW, corner_select_kernel, dim3(B), dim3(1024), 0, s, ca);
     CKL();
     LkArgs la;
     memset(&la, 0, sizeof la);
@@ -716,8 +716,7 @@ static int flow_from_gray(eig_ctx* c, int B, cudaStream_t s) {
     }
     la.n_levels = c->n_levels; la.corners = c->corners; la.ncorners = c->ncorners; la.next_pts = c->next_pts;
     la.status = c->status; la.B = B;
-    LAUNCH_K(CLS_FLOW, lk_track_kernel, dim3((B * FLOW_MAX_CORNERS + LK_WARPS_PER_BLOCK - 1) / LK_WARPS_PER_BLOCK),
-               dim3(32 * LK_WARPS_PER_BLOCK), 0, s, la);
+    LAUNCH_K(CLS_FLOW, lk_track_kernel, dim3(B * FLOW_MAX_CORNERS), dim3(LK_THREADS), 0, s, la);
     CKL();
     LAUNCH_K(CLS_FLOW, collect_vectors_kernel, dim3((B + 3) / 4), dim3(128), 0, s, (const float*)c->corners, (const int*)c->ncorners,
                (const float*)c->next_pts, (const unsigned char*)c->status, c->vectors, c->nvec, B);

@@ -9,8 +9,8 @@
 //                        greedy 7-px spacing, at most 100 corners           (one CTA per image)
 //   pyr_down_kernel    : 5x5 [1 4 6 4 1] integer pyramid level               (both frames)
 //   scharr_kernel      : int16 Scharr derivatives of frame 1
-//   lk_track_kernel    : one WARP per corner; the 50x50 window sums (A11,A12,A22,b1,b2) are exact int64
-//                        sums reduced with warp shuffles; <= 10 Newton steps per level
+//   lk_track_kernel    : one 128-thread CTA per corner; the 50x50 window sums (A11,A12,A22,b1,b2) are exact int64
+//                        sums reduced with warp shuffles (+ one shared-memory exchange); <= 10 Newton steps per level
 //   collect_vectors_kernel: rows [x, y, dx, dy] of the tracked corners, in corner order
 #pragma once
 #include "common.cuh"
@@ -151,7 +151,7 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int 
     }
 }
 
-__global__ void __launch_bounds__(256) corner_select_kernel(CornerArgs a) {
+__global__ void __launch_bounds__(1024) corner_select_kernel(CornerArgs a) {
     constexpr int SMEM_KEYS = 2048;
     __shared__ unsigned long long sKeys[SMEM_KEYS];
     __shared__ int sCount;
@@ -297,26 +297,37 @@ __device__ __forceinline__ void lk_weights(float a, float b, int* w) {
     w[3] = 16384 - w[0] - w[1] - w[2];
 }
 
-#define LK_WARPS_PER_BLOCK 2
-__global__ void __launch_bounds__(32 * LK_WARPS_PER_BLOCK) lk_track_kernel(LkArgs a) {
-    constexpr int WIN = FLOW_WIN, NPX = WIN * WIN;
-    __shared__ short sI[LK_WARPS_PER_BLOCK][NPX];
-    __shared__ short sIx[LK_WARPS_PER_BLOCK][NPX];
-    __shared__ short sIy[LK_WARPS_PER_BLOCK][NPX];
+// One CTA of LK_THREADS threads per corner: the 50x50 window is spread over the CTA (exact int64 partial sums, so the
+// result does not depend on the partition), reduced with warp shuffles and one shared-memory exchange per sum.
+#define LK_THREADS 128
+__device__ __forceinline__ void lk_block_sum3(long long& a, long long& b, long long& c, long long (*sRed)[3]) {
+    a = warp_sum_ll(a); b = warp_sum_ll(b); c = warp_sum_ll(c);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pt = blockIdx.x * LK_WARPS_PER_BLOCK + warp;
+    __syncthreads();                       // the previous use of sRed is over
+    if (lane == 0) { sRed[warp][0] = a; sRed[warp][1] = b; sRed[warp][2] = c; }
+    __syncthreads();
+    a = 0; b = 0; c = 0;
+#pragma unroll
+    for (int w = 0; w < LK_THREADS / 32; ++w) { a += sRed[w][0]; b += sRed[w][1]; c += sRed[w][2]; }
+}
+
+__global__ void __launch_bounds__(LK_THREADS) lk_track_kernel(LkArgs a) {
+    constexpr int WIN = FLOW_WIN, NPX = WIN * WIN;
+    __shared__ short I[NPX];
+    __shared__ short Ix[NPX];
+    __shared__ short Iy[NPX];
+    __shared__ long long sRed[LK_THREADS / 32][3];
+    const int tid = threadIdx.x;
+    const int pt = blockIdx.x;
     const int b = pt / FLOW_MAX_CORNERS, k = pt % FLOW_MAX_CORNERS;
     if (b >= a.B) return;
-    if (k >= a.ncorners[b]) return;  // warp-uniform
+    if (k >= a.ncorners[b]) return;  // block-uniform
     const float px0 = a.corners[((long long)b * FLOW_MAX_CORNERS + k) * 2];
     const float py0 = a.corners[((long long)b * FLOW_MAX_CORNERS + k) * 2 + 1];
     const float half = 24.5f;
     const float flt_scale = 1.f / (1 << 20);
     float nx = 0.f, ny = 0.f;
     bool status = true;
-    short* I = sI[warp];
-    short* Ix = sIx[warp];
-    short* Iy = sIy[warp];
     for (int level = a.n_levels - 1; level >= 0; --level) {
         const int rows = a.lh[level], cols = a.lw[level];
         const unsigned char* im1 = a.img1[level] + (long long)b * rows * cols;
@@ -335,7 +346,8 @@ __global__ void __launch_bounds__(32 * LK_WARPS_PER_BLOCK) lk_track_kernel(LkArg
         int w[4];
         lk_weights(__fsub_rn(pxw, (float)ipx), __fsub_rn(pyw, (float)ipy), w);
         long long s11 = 0, s12 = 0, s22 = 0;
-        for (int i = lane; i < NPX; i += 32) {
+        __syncthreads();   // the window buffers of the previous level are no longer read
+        for (int i = tid; i < NPX; i += LK_THREADS) {
             const int wy = i / WIN, wx = i % WIN;
             const int gy = ipy + wy, gx = ipx + wx;
             // image: 50-px BORDER_REFLECT_101 frame around the level; derivatives: zero outside
@@ -355,8 +367,7 @@ __global__ void __launch_bounds__(32 * LK_WARPS_PER_BLOCK) lk_track_kernel(LkArg
             I[i] = (short)iv; Ix[i] = (short)ixv; Iy[i] = (short)iyv;
             s11 += (long long)ixv * ixv; s12 += (long long)ixv * iyv; s22 += (long long)iyv * iyv;
         }
-        s11 = warp_sum_ll(s11); s12 = warp_sum_ll(s12); s22 = warp_sum_ll(s22);
-        __syncwarp();
+        lk_block_sum3(s11, s12, s22, sRed);   // also makes the window visible to the whole CTA
         const float A11 = __fmul_rn(__ll2float_rn(s11), flt_scale);
         const float A12 = __fmul_rn(__ll2float_rn(s12), flt_scale);
         const float A22 = __fmul_rn(__ll2float_rn(s22), flt_scale);
@@ -380,8 +391,8 @@ __global__ void __launch_bounds__(32 * LK_WARPS_PER_BLOCK) lk_track_kernel(LkArg
                 break;
             }
             lk_weights(__fsub_rn(cx, (float)icx), __fsub_rn(cy, (float)icy), w);
-            long long sb1 = 0, sb2 = 0;
-            for (int i = lane; i < NPX; i += 32) {
+            long long sb1 = 0, sb2 = 0, unused = 0;
+            for (int i = tid; i < NPX; i += LK_THREADS) {
                 const int wy = i / WIN, wx = i % WIN;
                 const int y0r = reflect101(icy + wy, rows), y1r = reflect101(icy + wy + 1, rows);
                 const int x0r = reflect101(icx + wx, cols), x1r = reflect101(icx + wx + 1, cols);
@@ -391,7 +402,7 @@ __global__ void __launch_bounds__(32 * LK_WARPS_PER_BLOCK) lk_track_kernel(LkArg
                 sb1 += (long long)diff * Ix[i];
                 sb2 += (long long)diff * Iy[i];
             }
-            sb1 = warp_sum_ll(sb1); sb2 = warp_sum_ll(sb2);
+            lk_block_sum3(sb1, sb2, unused, sRed);
             const float b1 = __fmul_rn(__ll2float_rn(sb1), flt_scale);
             const float b2 = __fmul_rn(__ll2float_rn(sb2), flt_scale);
             const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
@@ -406,13 +417,12 @@ __global__ void __launch_bounds__(32 * LK_WARPS_PER_BLOCK) lk_track_kernel(LkArg
             }
             pdx = ddx; pdy = ddy;
         }
-        __syncwarp();
         if (level == 0 && status) {
             const int ifx = __float2int_rd(__fsub_rn(nx, half)), ify = __float2int_rd(__fsub_rn(ny, half));
             if (ifx < -WIN || ifx >= cols || ify < -WIN || ify >= rows) status = false;
         }
     }
-    if (lane == 0) {
+    if (tid == 0) {
         a.next_pts[((long long)b * FLOW_MAX_CORNERS + k) * 2] = nx;
         a.next_pts[((long long)b * FLOW_MAX_CORNERS + k) * 2 + 1] = ny;
         a.status[(long long)b * FLOW_MAX_CORNERS + k] = status ? 1 : 0;
