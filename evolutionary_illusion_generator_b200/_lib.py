@@ -31,6 +31,7 @@ SYMBOLS = [
     ("eig_score", _I, [_P, _P, _P, _I, _I, _P, _P]),
     ("eig_eval", _I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     ("eig_eval_host", _I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    ("eig_range_check", _I, [_P, _P]),
     ("eig_debug_buffers", _I, [_P] + [C.POINTER(_P)] * 6),
     ("eig_memcpy_d2h", _I, [_P, _P, C.c_int64]),
     ("eig_profile_begin", _I, [_P]),

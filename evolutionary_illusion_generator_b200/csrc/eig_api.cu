@@ -116,6 +116,7 @@ struct eig_ctx {
     double* fitness = nullptr;
     // host staging for eig_eval_host
     void* d_blob = nullptr; size_t d_blob_cap = 0; long long* d_off = nullptr;
+    size_t corner_smem = 0;   // bitmap of the greedy corner spacing: one bit per pixel
     void* h_pin = nullptr; size_t h_pin_cap = 0;
     cudaStream_t stream = 0;
     // ConvP_2 / ConvP_3 are off the critical path of a PredNet step: they run on a side stream, ordered by events
@@ -126,7 +127,7 @@ struct eig_ctx {
     // CUDA graphs of everything after the render (PredNet sequence + flow + score), keyed by what the launches depend on;
     // a key is run once un-captured (lazy initialisations), captured on its second use and replayed afterwards
     struct GraphEntry { int seen = 0; long long launches = 0; void* exec = nullptr; };
-    std::map<std::tuple<int, int, int, int, const void*>, GraphEntry> graphs;
+    std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
     bool use_graphs = true;
     std::vector<void*> allocs;
 };
@@ -198,9 +199,14 @@ extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, co
     CK(dalloc(c, &c->corners, B * FLOW_MAX_CORNERS * 2)); CK(dalloc(c, &c->ncorners, B));
     CK(dalloc(c, &c->next_pts, B * FLOW_MAX_CORNERS * 2)); CK(dalloc(c, &c->status, B * FLOW_MAX_CORNERS));
     CK(dalloc(c, &c->vectors, B * FLOW_MAX_CORNERS * 4)); CK(dalloc(c, &c->nvec, B));
-    CK(dalloc(c, &c->fitness, B + 1)); CK(dalloc(c, &c->d_off, B + 1));   // fitness[B] = status slot
+    CK(dalloc(c, &c->fitness, B + 1)); CK(dalloc(c, &c->d_off, B + 1));   // fitness[B] = status slot (sticky range flag)
+    CK(cudaMemset(c->fitness + B, 0, sizeof(double)));
     CK(dalloc(c, &c->xmat, (size_t)w * h)); CK(dalloc(c, &c->ymat, (size_t)w * h));
+    c->corner_smem = (((size_t)w * h + 31) / 32) * sizeof(unsigned);
+    if (c->corner_smem > 200 * 1024) return fail(EIG_E_CAPACITY, "eig_create: image too large for the corner-selection bitmap (w*h <= 1.6 Mpx)");
 #ifndef EIG_EMU
+    if (c->corner_smem + 17 * 1024 > 48 * 1024)
+        CK(cudaFuncSetAttribute(corner_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->corner_smem));
     {   // the host entry point runs on its own high-priority stream; the side stream (ConvP_2/3, off the critical path)
         // gets the lowest priority so that its CTAs only take SMs the critical-path kernels leave idle
         int least = 0, greatest = 0;
@@ -704,7 +710,7 @@ static int flow_from_gray(eig_ctx* c, int B, cudaStream_t s) {
     CKL();
     CornerArgs ca; ca.eig = c->eigmap; ca.eig_max_key = c->eigmax; ca.cand = c->cand; ca.corners = c->corners;
     ca.ncorners = c->ncorners; ca.H = H; ca.W = W;
-    LAUNCH_K(CLS_FLOW, corner_select_kernel, dim3(B), dim3(1024), 0, s, ca);
+    LAUNCH_K(CLS_FLOW, corner_select_kernel, dim3(B), dim3(1024), c->corner_smem, s, ca);
     CKL();
     LkArgs la;
     memset(&la, 0, sizeof la);
@@ -746,7 +752,7 @@ extern "C" int eig_flow(eig_ctx* c, const uint8_t* d_img1, const uint8_t* d_img2
 static int score_launch(eig_ctx* c, const float* vec, const int* nvec, int n, int structure, double* fit, cudaStream_t s) {
     if (structure < 0 || structure > 3) return fail(EIG_E_INVALID, "unknown structure id");
     ScoreArgs sa; sa.vectors = vec; sa.nvec = nvec; sa.fitness = fit; sa.B = n; sa.structure = structure; sa.w = c->w; sa.h = c->h;
-    sa.status = fit == c->fitness ? c->fitness + c->cap : nullptr;   // only the host entry point collects the range flag
+    sa.status = c->fitness + c->cap;   // sticky range flag of this context, read and cleared by eig_eval_host / eig_range_check
     LAUNCH_K(CLS_SCORE, score_kernel, dim3(n), dim3(32), 0, s, sa);
     CKL();
     return EIG_OK;
@@ -780,6 +786,13 @@ static int eval_after_render(eig_ctx* c, int n, int structure, int pair_mode, do
     return score_launch(c, c->vectors, c->nvec, n, structure, d_fitness, s);
 }
 
+// the evaluation writes the context's own fitness vector (so a captured graph does not depend on the caller's pointer)
+static int copy_fitness(eig_ctx* c, int n, double* d_fitness, cudaStream_t s) {
+    if (d_fitness != c->fitness)
+        CK(cudaMemcpyAsync(d_fitness, c->fitness, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+    return EIG_OK;
+}
+
 extern "C" int eig_eval(eig_ctx* c, const void* d_blob, const int64_t* d_offsets, int n, int max_slots, int max_blob_bytes,
                         int structure, int render_mode, int pair_mode, double* d_fitness, void* stream) {
     int rc;
@@ -790,17 +803,17 @@ extern "C" int eig_eval(eig_ctx* c, const void* d_blob, const int64_t* d_offsets
     if ((rc = eig_cppn_render(c, d_blob, d_offsets, n, max_slots, max_blob_bytes, render_mode, 1.0, c->img, c->x_in, stream))) return rc;
 #ifndef EIG_EMU
     if (c->use_graphs && !g_prof.on) {
-        auto key = std::make_tuple(n, structure, pair_mode, c->conv_mode, (const void*)d_fitness);
+        auto key = std::make_tuple(n, structure, pair_mode, c->conv_mode);
         eig_ctx::GraphEntry& ge = c->graphs[key];
         if (ge.exec) {
             CK(cudaGraphLaunch((cudaGraphExec_t)ge.exec, s));
             launch_counter().n += ge.launches;
-            return EIG_OK;
+            return copy_fitness(c, n, d_fitness, s);
         }
         if (ge.seen++ >= 1) {   // second use of this key: capture, instantiate, replay from now on
             const long long before = launch_counter().n;
             if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
-                rc = eval_after_render(c, n, structure, pair_mode, d_fitness, s);
+                rc = eval_after_render(c, n, structure, pair_mode, c->fitness, s);
                 cudaGraph_t g = nullptr;
                 const cudaError_t ee = cudaStreamEndCapture(s, &g);
                 cudaGraphExec_t exec = nullptr;
@@ -809,7 +822,7 @@ extern "C" int eig_eval(eig_ctx* c, const void* d_blob, const int64_t* d_offsets
                     ge.exec = exec;
                     ge.launches = launch_counter().n - before;
                     CK(cudaGraphLaunch(exec, s));
-                    return EIG_OK;
+                    return copy_fitness(c, n, d_fitness, s);
                 }
                 if (g) cudaGraphDestroy(g);
                 cudaGetLastError();
@@ -819,7 +832,22 @@ extern "C" int eig_eval(eig_ctx* c, const void* d_blob, const int64_t* d_offsets
         }
     }
 #endif
-    return eval_after_render(c, n, structure, pair_mode, d_fitness, s);
+    if ((rc = eval_after_render(c, n, structure, pair_mode, c->fitness, s))) return rc;
+    return copy_fitness(c, n, d_fitness, s);
+}
+
+extern "C" int eig_range_check(eig_ctx* c, void* stream) {
+    if (!c) return fail(EIG_E_INVALID, "null ctx");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = TO_STREAM(stream);
+    double status = 0.0;
+    CK(cudaMemcpyAsync(&status, c->fitness + c->cap, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemsetAsync(c->fitness + c->cap, 0, sizeof(double), s));
+    CK(cudaStreamSynchronize(s));
+    if (status != 0.0)
+        return fail(EIG_E_RANGE, "an activation left the split-fp16 range (|v| >= 4094) or became NaN in tensor-core mode; "
+                                 "this weight file needs conv_mode EIG_CONV_SIMT");
+    return EIG_OK;
 }
 
 extern "C" int eig_eval_host(eig_ctx* c, const void* h_blob, const int64_t* h_offsets, int n, int max_slots, int structure,
@@ -843,14 +871,8 @@ extern "C" int eig_eval_host(eig_ctx* c, const void* h_blob, const int64_t* h_of
     if ((rc = eig_eval(c, c->d_blob, (const int64_t*)c->d_off, n, max_slots, max_blob, structure, render_mode, pair_mode,
                        c->fitness, (void*)(intptr_t)s)))
         return rc;
-    double status = 0.0;
     CK(cudaMemcpyAsync(h_fitness, c->fitness, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&status, c->fitness + c->cap, sizeof(double), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    if (status != 0.0)
-        return fail(EIG_E_RANGE, "an activation left the split-fp16 range (|v| >= 4094) or became NaN in tensor-core mode; "
-                                 "this weight file needs conv_mode EIG_CONV_SIMT");
-    return EIG_OK;
+    return eig_range_check(c, (void*)(intptr_t)s);
 }
 
 extern "C" int eig_debug_buffers(eig_ctx* c, uint8_t** d_img, uint8_t** d_frames, float** d_vectors, int** d_nvec,

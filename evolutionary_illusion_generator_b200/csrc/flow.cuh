@@ -155,14 +155,12 @@ __global__ void __launch_bounds__(1024) corner_select_kernel(CornerArgs a) {
     constexpr int SMEM_KEYS = 2048;
     __shared__ unsigned long long sKeys[SMEM_KEYS];
     __shared__ int sCount;
-    __shared__ int sAccX[FLOW_MAX_CORNERS], sAccY[FLOW_MAX_CORNERS];
-    __shared__ int sNacc;
     const int b = blockIdx.x;
     const float* eig = a.eig + (long long)b * a.H * a.W;
     unsigned long long* cand = a.cand + (long long)b * a.H * a.W;
     const float maxv = float_from_order_key(a.eig_max_key[b]);
     const float thr = (float)((double)maxv * 0.3);
-    if (threadIdx.x == 0) { sCount = 0; sNacc = 0; }
+    if (threadIdx.x == 0) sCount = 0;
     __syncthreads();
     const int iw = a.W - 2, ih = a.H - 2;
     for (int i = threadIdx.x; i < iw * ih; i += blockDim.x) {
@@ -203,28 +201,49 @@ __global__ void __launch_bounds__(1024) corner_select_kernel(CornerArgs a) {
     if (count > 1) bitonic_sort_desc(keys, n_pow2);
     __syncthreads();
     const int total = count < n_pow2 ? count : n_pow2;
-    // greedy spacing, serial over the sorted list, parallel over the accepted corners (warp 0)
+    // Greedy spacing (accept a candidate when no accepted corner lies within squared distance 49), serial over the sorted
+    // list.  Warp 0 takes 32 candidates at a time: a shared bitmap holds every pixel closer than 7 px to an accepted
+    // corner, so "is this candidate blocked" is one bit test; inside a batch the surviving lanes are accepted in order,
+    // each acceptance marking its disc before the later lanes look again.
+    EIG_DYN_SMEM(smem_blocked);
+    unsigned* blocked = reinterpret_cast<unsigned*>(smem_blocked);
+    const int n_words = (a.H * a.W + 31) >> 5;
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) blocked[i] = 0u;
+    __syncthreads();
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         int nacc = 0;
-        for (int i = 0; i < total && nacc < FLOW_MAX_CORNERS; ++i) {
-            const unsigned addr = (unsigned)(keys[i] & 0xffffffffu);
-            const int y = addr / a.W, x = addr % a.W;
-            bool bad = false;
-            for (int k = lane; k < nacc; k += 32) {
-                const int dx = x - sAccX[k], dy = y - sAccY[k];
-                if (dx * dx + dy * dy < 49) bad = true;
+        for (int base = 0; base < total && nacc < FLOW_MAX_CORNERS; base += 32) {
+            const int i = base + lane;
+            bool live = i < total;
+            unsigned addr = 0;
+            if (live) {
+                addr = (unsigned)(keys[i] & 0xffffffffu);
+                live = !((blocked[addr >> 5] >> (addr & 31)) & 1u);
             }
-            const unsigned any_bad = __ballot_sync(0xffffffffu, bad);
-            if (!any_bad) {
+            unsigned m = __ballot_sync(0xffffffffu, live);
+            while (m && nacc < FLOW_MAX_CORNERS) {
+                const int l = __ffs((int)m) - 1;
+                const unsigned acc_addr = __shfl_sync(0xffffffffu, addr, l);
+                const int ay = (int)(acc_addr / (unsigned)a.W), ax = (int)(acc_addr % (unsigned)a.W);
                 if (lane == 0) {
-                    sAccX[nacc] = x; sAccY[nacc] = y;
-                    a.corners[((long long)b * FLOW_MAX_CORNERS + nacc) * 2] = (float)x;
-                    a.corners[((long long)b * FLOW_MAX_CORNERS + nacc) * 2 + 1] = (float)y;
+                    a.corners[((long long)b * FLOW_MAX_CORNERS + nacc) * 2] = (float)ax;
+                    a.corners[((long long)b * FLOW_MAX_CORNERS + nacc) * 2 + 1] = (float)ay;
                 }
                 ++nacc;
+                for (int t = lane; t < 13 * 13; t += 32) {        // dx, dy in [-6, 6]: dx*dx + dy*dy < 49
+                    const int dy = t / 13 - 6, dx = t % 13 - 6;
+                    const int y = ay + dy, x = ax + dx;
+                    if (dx * dx + dy * dy < 49 && y >= 0 && y < a.H && x >= 0 && x < a.W) {
+                        const unsigned p = (unsigned)(y * a.W + x);
+                        atomicOr(&blocked[p >> 5], 1u << (p & 31));
+                    }
+                }
+                __syncwarp();
+                if (lane <= l) live = false;
+                else if (live) live = !((blocked[addr >> 5] >> (addr & 31)) & 1u);
+                m = __ballot_sync(0xffffffffu, live);
             }
-            __syncwarp();
         }
         if (lane == 0) a.ncorners[b] = nacc;
     }

@@ -22,7 +22,7 @@ struct ScoreArgs {
     const float* vectors;  // [B][100][4]
     const int* nvec;       // [B]
     double* fitness;       // [B]
-    double* status;        // nullable: 1 slot, receives (and clears) the split-fp16 range flag of this evaluation
+    double* status;        // nullable: 1 sticky slot, set when the split-fp16 range flag was raised during this evaluation
     int B, structure, w, h;
 };
 
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(32) score_kernel(ScoreArgs a) {
     __shared__ float sang[MAXV];
     const int b = blockIdx.x, lane = threadIdx.x;
     if (b >= a.B) return;
-    if (b == 0 && lane == 0 && a.status) { *a.status = (double)g_eig_range_flag; g_eig_range_flag = 0; }
+    if (b == 0 && lane == 0 && a.status && g_eig_range_flag) { *a.status = 1.0; g_eig_range_flag = 0; }
     const int nraw = a.nvec[b];
     const float limit = a.structure == STRUCT_BANDS ? 0.15f : (a.structure == STRUCT_FREE ? 0.4f : 0.3f);
     // plausibility filter, order preserving compaction

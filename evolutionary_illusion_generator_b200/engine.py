@@ -50,6 +50,8 @@ class Engine:
         # whole-path evaluations run on a high-priority stream: the library puts ConvP_2/3 on a lowest-priority side
         # stream, and the block scheduler then gives the critical-path kernels the SMs first
         self._hp_stream = torch.cuda.Stream(device=self.tdev, priority=-1) if self.tdev.type == "cuda" else None
+        self._up_stream = torch.cuda.Stream(device=self.tdev) if self.tdev.type == "cuda" else None
+        self._fit_buf = None
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -177,6 +179,60 @@ class Engine:
                                          C.c_void_p(self._hp_stream.cuda_stream)))
         cur.wait_stream(self._hp_stream)                 # the caller's stream sees the fitness vector in order
         return out
+
+    def stream_chunk(self, n):
+        """Genomes per chunk of `evaluate_streamed`: large enough that a chunk still fills the GPU (a chunk below
+        ~2e8 layer-0-pixel x channel units is latency-bound: splitting C2's 32 gray genomes would only lengthen
+        the evaluation), at most 8 chunks."""
+        units = self.w * self.h * sum(self.channels)
+        chunk = -(-int(2e8) // units)
+        chunk = max(-(-chunk // 8) * 8, -(-n // 8))
+        return min(max(chunk, 1), max(n, 1))
+
+    def evaluate_streamed(self, items, flatten, structure, render_mode=RENDER_GRADIENT,
+                          pair_mode=_lib.PAIR_POPULATION, chunk=None):
+        """[(genome_id, genome)] -> device fp64 fitness tensor (a view of an engine-owned buffer), with the host-side
+        flattening of chunk k+1 overlapped with the GPU evaluation of chunk k (SURVEY.md §8 f row 4: flattening is
+        0.15-0.3 ms of Python per genome, a third of the GPU time of a generation when done up front).
+        `flatten(genome_id, genome) -> FlatProgram`.  Chunks are queued on the engine's evaluation stream in population
+        order; uploads go through pinned memory on a copy stream.  One synchronisation, at the end (range check)."""
+        n = len(items)
+        if n > self.max_genomes:
+            raise ValueError("population of %d exceeds the engine capacity %d" % (n, self.max_genomes))
+        if self._fit_buf is None:
+            self._fit_buf = torch.empty((self.max_genomes,), dtype=torch.float64, device=self.tdev)
+        out = self._fit_buf
+        if n == 0:
+            return out[:0]
+        chunk = self.stream_chunk(n) if chunk is None else max(1, int(chunk))
+        cuda = self.tdev.type == "cuda"
+        ev = self._hp_stream if cuda else None
+        if cuda:
+            ev.wait_stream(torch.cuda.current_stream(self.tdev))
+        keep = []
+        for c0 in range(0, n, chunk):
+            progs = [flatten(gid, g) for gid, g in items[c0:c0 + chunk]]
+            blob, offsets, max_slots = G.pack_population(progs)
+            max_blob = int(np.diff(offsets).max())
+            if cuda:
+                hb, ho = torch.from_numpy(blob).pin_memory(), torch.from_numpy(offsets).pin_memory()
+                with torch.cuda.stream(self._up_stream):
+                    db, do = hb.to(self.tdev, non_blocking=True), ho.to(self.tdev, non_blocking=True)
+                ev.wait_stream(self._up_stream)
+                keep.append((hb, ho, db, do))               # alive until the final synchronisation
+                stream = C.c_void_p(ev.cuda_stream)
+            else:
+                db, do = torch.from_numpy(blob), torch.from_numpy(offsets)
+                keep.append((db, do))
+                stream = C.c_void_p(0)
+            self.lib.check(self.lib.eig_eval(self.ctx, db.data_ptr(), do.data_ptr(), len(progs), max_slots, max_blob,
+                                             int(structure), int(render_mode), int(pair_mode),
+                                             out[c0:].data_ptr(), stream))
+        self.lib.check(self.lib.eig_range_check(self.ctx, C.c_void_p(ev.cuda_stream) if cuda else C.c_void_p(0)))
+        if cuda:
+            torch.cuda.current_stream(self.tdev).wait_stream(ev)
+        del keep
+        return out[:n]
 
     def evaluate_host(self, blob, offsets, max_slots, structure, render_mode=RENDER_GRADIENT,
                       pair_mode=_lib.PAIR_POPULATION, out=None):

@@ -21,6 +21,7 @@ from ._lib import PAIR_POPULATION
 from .grid import StructureType, create_grid, enhanced_image_grid  # noqa: F401  (re-exported, reference names)
 
 REPEAT = 20  # generate_illusion.py:482
+program_cache = G.ProgramCache()  # genome id -> flattened program; elites are re-submitted unchanged every generation
 
 
 def _used_outputs(c_dim):
@@ -53,9 +54,13 @@ def get_fitnesses_neat(structure, population, model_name, config, w, h, channels
     print("Calculating fitnesses of populations: ", len(population))
     eng = runtime.get_engine(w, h, channels, model_name, len(population))
     eng.set_grid(structure)
-    programs = [G.flatten_genome(g, config, n_outputs=_used_outputs(c_dim)) for _, g in population]
     mode = engine_mod.render_mode_for(c_dim, gradient)
-    fit = runtime.evaluate_population(eng, programs, int(structure), mode, PAIR_POPULATION)
+    n_out = _used_outputs(c_dim)
+    # each rank flattens its own shard, chunk by chunk, while the GPU evaluates the previous chunk; unchanged genomes
+    # (elites) come out of the program cache
+    fit = runtime.evaluate_genomes(eng, population, lambda gid, g: program_cache.get(gid, g, config, n_out),
+                                   int(structure), mode, PAIR_POPULATION)
+    program_cache.end_generation()
     best_score, best_i = 0, 0
     for i, (_, genome) in enumerate(population):
         genome.fitness = float(fit[i])
@@ -63,7 +68,7 @@ def get_fitnesses_neat(structure, population, model_name, config, w, h, channels
             best_score, best_i = genome.fitness, i
     print("scores", [[i, float(f)] for i, f in enumerate(fit)])
     if export_best and population:
-        _export_best(eng, population[best_i][1], config, c_dim, gradient, best_dir, structure, export_async)
+        _export_best(eng, population[best_i], config, c_dim, gradient, best_dir, structure, export_async)
     print("best", best_score, best_i)
     return None
 
@@ -104,7 +109,7 @@ def _write_pngs(jobs):
         image.save(path, "PNG", compress_level=PNG_COMPRESS_LEVEL)
 
 
-def _export_best(eng, genome, config, c_dim, gradient, best_dir, structure=None, export_async=False):
+def _export_best(eng, id_genome, config, c_dim, gradient, best_dir, structure=None, export_async=False):
     """The per-generation files of generate_illusion.py:650-671 for the best genome, without the PNG hand-offs:
     best.png, best_black_bg.png, best_flow.png (extension frame #1 with the flow vectors drawn,
     optical_flow.py:10-18,84-86) and enhanced.png (800x800 circle mosaic, lines 664-671; the grid is cached).
@@ -113,7 +118,7 @@ def _export_best(eng, genome, config, c_dim, gradient, best_dir, structure=None,
     global _export_pool
     from .optical_flow import draw_tracks
     os.makedirs(best_dir, exist_ok=True)
-    prog = G.flatten_genome(genome, config, n_outputs=_used_outputs(c_dim))
+    prog = program_cache.get(id_genome[0], id_genome[1], config, _used_outputs(c_dim))
     mode = engine_mod.render_mode_for(c_dim, gradient)
     jobs = []
     for name, bg in (("best.png", 1.0), ("best_black_bg.png", 0.0)):

@@ -221,6 +221,12 @@ class FlatProgram:
         return SLOT_NODE0 + len(self.nodes)
 
     def to_bytes(self):
+        if getattr(self, "_bytes", None) is not None:
+            return self._bytes
+        self._bytes = self._encode()
+        return self._bytes
+
+    def _encode(self):
         outs = list(self.out_slots)
         if len(outs) % 2:
             outs.append(0)
@@ -313,6 +319,58 @@ def flatten_genome(genome, config, n_outputs=None):
             v = emit(ACT_IDS["identity"], AGG_IDS["sum"], [(float(v[0].item()), SLOT_ONE)], 0.0, 1.0) | OUT_F32_CONST
         prog.out_slots.append(v)
     return prog
+
+
+def genome_fingerprint(genome):
+    """Hash of everything `flatten_genome` reads from a genome (connection keys / weights / enabled flags, node
+    attributes).  Two genomes with equal fingerprints flatten to the same program."""
+    conns = tuple((k, c.weight, c.enabled) for k, c in genome.connections.items())
+    nodes = tuple((k, n.bias, n.response, n.activation, n.aggregation) for k, n in genome.nodes.items())
+    return hash((conns, nodes))
+
+
+class ProgramCache:
+    """genome id -> FlatProgram (SURVEY.md §8 f row 4).  NEAT re-submits unchanged genomes (the elites of every
+    species, `DefaultReproduction.reproduce`) generation after generation; a hit costs one fingerprint of the genome
+    (~6x cheaper than flattening) and re-uses the packed bytes.  The fingerprint guards against a genome that was
+    mutated in place under the same id.  Entries not touched for `keep` generations are dropped."""
+
+    def __init__(self, keep=2):
+        self.keep = keep
+        self.generation = 0
+        self.hits = 0
+        self.misses = 0
+        self._entries = {}
+
+    def get(self, genome_id, genome, config, n_outputs=None):
+        gc = config.genome_config
+        key = (genome_id, n_outputs, tuple(gc.input_keys), tuple(gc.output_keys))
+        fp = genome_fingerprint(genome)
+        e = self._entries.get(key)
+        if e is not None and e[0] == fp:
+            e[2] = self.generation
+            self.hits += 1
+            return e[1]
+        prog = flatten_genome(genome, config, n_outputs=n_outputs)
+        prog.to_bytes()
+        self._entries[key] = [fp, prog, self.generation]
+        self.misses += 1
+        return prog
+
+    def flatten_population(self, population, config, n_outputs=None):
+        """[(genome_id, genome)] -> [FlatProgram]; counts as one generation for eviction."""
+        progs = [self.get(gid, g, config, n_outputs) for gid, g in population]
+        self.end_generation()
+        return progs
+
+    def end_generation(self):
+        self.generation += 1
+        dead = [k for k, e in self._entries.items() if e[2] < self.generation - self.keep]
+        for k in dead:
+            del self._entries[k]
+
+    def __len__(self):
+        return len(self._entries)
 
 
 def pack_population(programs):

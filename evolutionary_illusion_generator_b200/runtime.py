@@ -63,3 +63,21 @@ def evaluate_population(eng, programs, structure, render_mode=engine_mod.RENDER_
     else:
         local = torch.zeros((0,), dtype=torch.float64, device=eng.tdev)
     return gather_fitness(local, n, per, group).cpu().numpy()
+
+
+def evaluate_genomes(eng, population, flatten, structure, render_mode=engine_mod.RENDER_GRADIENT,
+                     pair_mode=_lib.PAIR_POPULATION, group=None, chunk=None):
+    """[(genome_id, genome)] for the WHOLE population (same list on every rank) -> numpy float64 fitness vector.
+    Each rank flattens only its own shard (`flatten(genome_id, genome) -> FlatProgram`, e.g. `ProgramCache.get`), chunk
+    by chunk, overlapped with the GPU evaluation of the previous chunk (`Engine.evaluate_streamed`); sharding and the
+    single all-gather are those of `evaluate_population`."""
+    population = list(population)
+    n = len(population)
+    if n == 0:
+        return np.zeros((0,), dtype=np.float64)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return eng.evaluate_streamed(population, flatten, structure, render_mode, pair_mode, chunk).cpu().numpy()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi, per = shard_bounds(n, rank, world)
+    local = eng.evaluate_streamed(population[lo:hi], flatten, structure, render_mode, pair_mode, chunk)
+    return gather_fitness(local, n, per, group).cpu().numpy()

@@ -91,6 +91,11 @@ int eig_eval(eig_ctx* ctx, const void* d_blob, const int64_t* d_offsets, int n, 
 int eig_eval_host(eig_ctx* ctx, const void* h_blob, const int64_t* h_offsets, int n, int max_slots,
                   int structure, int render_mode, int pair_mode, double* h_fitness);
 
+/* Resident-path companion of eig_eval_host's range report: synchronises `stream`, returns EIG_E_RANGE if any eig_eval
+ * since the last check (or the last eig_eval_host) saw an activation leave the split-fp16 range, and clears the flag.
+ * The reference has no counterpart (its Chainer convolutions are plain fp32, net.py:45-62). */
+int eig_range_check(eig_ctx* ctx, void* stream);
+
 /* Debug / test taps: device pointers to the context's internal buffers of the last eig_eval
  * (rendered images [n][h][w][c] u8, frames [3][n][h][w][c] u8, vectors, nvec, corners, ncorners). */
 int eig_debug_buffers(eig_ctx* ctx, uint8_t** d_img, uint8_t** d_frames, float** d_vectors, int** d_nvec,

@@ -34,6 +34,12 @@ def _worker(rank, world, port, n, out_dir):
     fit = runtime.evaluate_population(eng, progs, 2)
     lo, hi, per = runtime.shard_bounds(n, rank, world)
     np.save(os.path.join(out_dir, "fit_%d.npy" % rank), fit)
+    # the streamed route get_fitnesses_neat takes: every rank flattens only its shard, one genome per chunk here
+    cache = G.ProgramCache()
+    pop = [(i, G.synthetic_genome("circles_bw", i)) for i in range(n)]
+    streamed = runtime.evaluate_genomes(eng, pop, lambda gid, g: cache.get(gid, g, cfg, 1), 2, chunk=1)
+    assert cache.misses == hi - lo
+    np.save(os.path.join(out_dir, "fit_streamed_%d.npy" % rank), streamed)
     np.save(os.path.join(out_dir, "shard_%d.npy" % rank), np.array([lo, hi, per]))
     dist.barrier()
     dist.destroy_process_group()
@@ -53,6 +59,12 @@ def test_sharded_evaluation_equals_single_process(emu_lib, tmp_path):
     f0, f1 = np.load(tmp_path / "fit_0.npy"), np.load(tmp_path / "fit_1.npy")
     assert np.array_equal(f0, f1) and f0.shape == (n,)
     assert np.array_equal(f0, single) and np.any(single > 0)
+    assert np.array_equal(np.load(tmp_path / "fit_streamed_0.npy"), single)
+    assert np.array_equal(np.load(tmp_path / "fit_streamed_1.npy"), single)
+    pop = [(i, G.synthetic_genome("circles_bw", i)) for i in range(n)]
+    for chunk in (None, 2):
+        one = eng.evaluate_streamed(pop, lambda gid, g: G.flatten_genome(g, cfg, n_outputs=1), 2, chunk=chunk)
+        assert np.array_equal(one.numpy(), single)
     assert list(np.load(tmp_path / "shard_0.npy")) == [0, 2, 2] and list(np.load(tmp_path / "shard_1.npy")) == [2, 3, 2]
 
 

@@ -339,6 +339,41 @@ def test_out_of_range_activations_fail_loudly_in_tensor_core_mode(gpu_engine_fac
     assert np.all(np.isfinite(eng.evaluate(progs, 1)))
 
 
+def test_streamed_evaluation_equals_host_entry_point(gpu_engine_factory):
+    """Engine.evaluate_streamed (what get_fitnesses_neat runs: flatten chunk k+1 while the GPU evaluates chunk k) gives
+    the bits of eig_eval_host for every chunking, repeatedly (graph replay per chunk size), and reports the range flag
+    of the resident path through eig_range_check."""
+    w, h, ch = 64, 64, (1, 16, 32, 64)
+    cfg, pop, progs = _programs("circles_bw", 1, list(range(7)))
+    items = list(enumerate(pop))
+    calls = []
+
+    def flatten(gid, g):
+        calls.append(gid)
+        return G.flatten_genome(g, cfg, n_outputs=1)
+
+    eng = gpu_engine_factory(w, h, ch, 8)
+    eng.set_conv_mode(_lib.CONV_TC)
+    eng.set_grid(1)
+    eng.load_weights(W.synthetic_predictor_weights(w, h, ch, seed=0))
+    want = eng.evaluate(progs, 1)
+    for chunk in (None, 3, 3, 3, 1, 7, 2):
+        got = eng.evaluate_streamed(items, flatten, 1, chunk=chunk).cpu().numpy()
+        assert np.array_equal(got, want, equal_nan=True), (chunk, got, want)
+    assert calls[:7] == list(range(7))
+    assert eng.stream_chunk(7) == 7                       # small gray genomes: one chunk
+    big = gpu_engine_factory(160, 120, (3, 48, 96, 192), 8)
+    assert big.stream_chunk(128) == 32 and big.stream_chunk(16) == 16
+    bad = dict(W.synthetic_predictor_weights(w, h, ch, seed=0))
+    bad["predictor/ConvA2/W"] = bad["predictor/ConvA2/W"] * np.float32(3e5)
+    eng.load_weights(bad)
+    with pytest.raises(_lib.EigError) as ei:
+        eng.evaluate_streamed(items, flatten, 1, chunk=4)
+    assert ei.value.code == _lib.EIG_E_RANGE
+    eng.load_weights(W.synthetic_predictor_weights(w, h, ch, seed=0))      # the flag was cleared by the check
+    assert np.array_equal(eng.evaluate_streamed(items, flatten, 1, chunk=4).cpu().numpy(), want, equal_nan=True)
+
+
 def test_graph_replay_is_transparent(gpu_engine_factory):
     """The library replays everything after the render from a CUDA graph from the third identical call on.  Direct run,
     capture run and replays must give the same bits; a new weight file, another population size and another structure
@@ -404,6 +439,7 @@ def test_reference_call_surface(tmp_path):
     t_async = __import__("time").perf_counter() - t0
     GI.wait_for_exports()
     print("get_fitnesses_neat with background export: %.1f ms" % (1e3 * t_async))
+    assert GI.program_cache.hits >= n                     # the second generation re-used every flattened program
     gc = cfg.genome_config
     ref, extra = OPL.evaluate_population(pop, gc.input_keys, gc.output_keys, 2, wts, w, h, ch, 1, keep=True)
     got = np.array([g.fitness for _, g in population])
