@@ -613,8 +613,13 @@ static int prednet_reset(eig_ctx* c, int B, cudaStream_t s) {
     for (int n = 0; n < 4; ++n) {
         const size_t px = (size_t)B * c->H[n] * c->W[n];
         for (int k = 0; k < 2; ++k) {
-            if (n >= 1) CK(cudaMemsetAsync(c->X[n][k], 0, px * c->ctot[n] * sizeof(float), s));
-            else CK(cudaMemsetAsync(c->h0[k], 0, px * c->ch[0] * sizeof(float), s));
+            if (n == 0) { CK(cudaMemsetAsync(c->h0[k], 0, px * c->ch[0] * sizeof(float), s)); continue; }
+            float* lo = lo_plane(c, n, c->X[n][k]);
+            if (!lo) { CK(cudaMemsetAsync(c->X[n][k], 0, px * c->ctot[n] * sizeof(float), s)); continue; }
+            // split-fp16 storage: the lo plane starts after the hi plane of all `cap` genomes, so each plane has its own
+            // prefix of B genomes to clear
+            CK(cudaMemsetAsync(c->X[n][k], 0, px * c->ctot[n] * sizeof(h16), s));
+            CK(cudaMemsetAsync(lo, 0, px * c->ctot[n] * sizeof(h16), s));
         }
         CK(cudaMemsetAsync(c->cst[n], 0, px * c->ch[n] * sizeof(float), s));
         CK(cudaMemsetAsync(c->P[n], 0, px * c->ch[n] * sizeof(float), s));

@@ -182,10 +182,10 @@ class Engine:
 
     def stream_chunk(self, n):
         """Genomes per chunk of `evaluate_streamed`: large enough that a chunk still fills the GPU (a chunk below
-        ~2e8 layer-0-pixel x channel units is latency-bound: splitting C2's 32 gray genomes would only lengthen
+        ~4e8 layer-0-pixel x channel units is latency-bound: splitting C2's 32 gray genomes would only lengthen
         the evaluation), at most 8 chunks."""
         units = self.w * self.h * sum(self.channels)
-        chunk = -(-int(2e8) // units)
+        chunk = -(-int(4e8) // units)
         chunk = max(-(-chunk // 8) * 8, -(-n // 8))
         return min(max(chunk, 1), max(n, 1))
 

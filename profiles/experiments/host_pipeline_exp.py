@@ -64,3 +64,8 @@ print("  flatten up front + eig_eval_host           %8.2f ms  (%.0f evals/s)" % 
 print("  evaluate_streamed, every genome flattened  %8.2f ms  (%.0f evals/s)" % (t_b, n / t_b * 1e3))
 print("  evaluate_streamed, program cache warm      %8.2f ms  (%.0f evals/s)" % (t_c, n / t_c * 1e3))
 print("  same fitness bits: %s" % bool(np.array_equal(fa, fb, equal_nan=True) and np.array_equal(fa, fc, equal_nan=True)))
+for chunk in sorted({n, n // 2, n // 4, n // 8}, reverse=True):
+    t_cold, f1 = timeit(lambda: eng.evaluate_streamed(pop, lambda gid, g: G.flatten_genome(g, cfg, n_outputs=c), 1, chunk=chunk).cpu().numpy(), reps)
+    t_warm, f2 = timeit(lambda: eng.evaluate_streamed(pop, lambda gid, g: cache.get(gid, g, cfg, c), 1, chunk=chunk).cpu().numpy(), reps)
+    print("  chunk %3d: every genome flattened %8.2f ms, cache warm %8.2f ms, same bits %s"
+          % (chunk, t_cold, t_warm, bool(np.array_equal(fa, f1, equal_nan=True) and np.array_equal(fa, f2, equal_nan=True))))

@@ -363,7 +363,7 @@ def test_streamed_evaluation_equals_host_entry_point(gpu_engine_factory):
     assert calls[:7] == list(range(7))
     assert eng.stream_chunk(7) == 7                       # small gray genomes: one chunk
     big = gpu_engine_factory(160, 120, (3, 48, 96, 192), 8)
-    assert big.stream_chunk(128) == 32 and big.stream_chunk(16) == 16
+    assert big.stream_chunk(128) == 64 and big.stream_chunk(16) == 16
     bad = dict(W.synthetic_predictor_weights(w, h, ch, seed=0))
     bad["predictor/ConvA2/W"] = bad["predictor/ConvA2/W"] * np.float32(3e5)
     eng.load_weights(bad)
@@ -372,6 +372,25 @@ def test_streamed_evaluation_equals_host_entry_point(gpu_engine_factory):
     assert ei.value.code == _lib.EIG_E_RANGE
     eng.load_weights(W.synthetic_predictor_weights(w, h, ch, seed=0))      # the flag was cleared by the check
     assert np.array_equal(eng.evaluate_streamed(items, flatten, 1, chunk=4).cpu().numpy(), want, equal_nan=True)
+
+
+def test_results_do_not_depend_on_what_was_evaluated_before(gpu_engine_factory):
+    """A population smaller than the engine capacity must see freshly reset recurrent state in both fp16 planes of the
+    split storage (the lo plane lies behind the hi plane of all `cap` genomes): same bits as a fresh, exactly sized engine,
+    whatever ran before."""
+    w, h, ch = 64, 64, (1, 16, 32, 64)
+    _, _, progs = _programs("circles_bw", 1, list(range(8)))
+    wts = W.synthetic_predictor_weights(w, h, ch, seed=0)
+    for mode in (_lib.CONV_TC, _lib.CONV_SIMT):
+        big = gpu_engine_factory(w, h, ch, 8)
+        big.set_conv_mode(mode); big.set_grid(1); big.load_weights(wts)
+        big.evaluate(progs, 1)                                     # leaves state of 8 other genomes behind
+        for n in (3, 1, 5):
+            fresh = gpu_engine_factory(w, h, ch, n)
+            fresh.set_conv_mode(mode); fresh.set_grid(1); fresh.load_weights(wts)
+            want = fresh.evaluate(progs[:n], 1)
+            assert np.array_equal(big.evaluate(progs[:n], 1), want, equal_nan=True), (mode, n)
+            big.evaluate(progs[3:8], 1)
 
 
 def test_graph_replay_is_transparent(gpu_engine_factory):
