@@ -55,6 +55,11 @@ def tc_kernel_macs(ch):
     if c1 >= 32:
         total += 9 * 2 * c0 * c1                                                  # ConvA1 (on tcgen05 for wide first layers)
     return total
+
+
+def tc_dead_macs(ch):
+    """ConvP2 / ConvP3 of the final step feed nothing (no next step): not launched, not counted."""
+    return 9 * ch[2] * ch[2] / 16.0 + 9 * ch[3] * ch[3] / 64.0
 USEFUL_STEPS = 21  # 20 static frames + 1 self-fed (the reference's 22nd forward is never read)
 METRIC = "NEAT genome fitness evals/sec (CPPN+PredNet+flow) @160x120"
 
@@ -264,7 +269,7 @@ def run_ours(args):
         total = world * pop * args.steps
         value = total / (dev_ms / 1e3)
         e2e = total / (e2e_ms / 1e3)
-        flop_step = 2.0 * tc_kernel_macs(ch) * w * h * USEFUL_STEPS * pop   # algorithmic FLOP of the tcgen05 launches, one GPU
+        flop_step = 2.0 * (tc_kernel_macs(ch) * USEFUL_STEPS - tc_dead_macs(ch)) * w * h * pop   # algorithmic FLOP of the tcgen05 launches, one GPU
         conv_ms = cls_ms["conv_simt"] + cls_ms["conv_tcgen05"]
         conv_n = cls_n["conv_simt"] + cls_n["conv_tcgen05"]
         achieved = flop_step / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0

@@ -225,6 +225,28 @@ __global__ void __launch_bounds__(256) quantize_gray_kernel(const float* P0, uns
                                   : (unsigned char)ch[0];
 }
 
+// reset_state (net.py:159-164, called per genome in call_prednet.py:203): every state region that step 0 reads before it
+// is written, zeroed by one launch (blockIdx.y = region) instead of one memset node per region.
+#define RESET_MAX_REGIONS 16
+struct ResetArgs {
+    void* ptr[RESET_MAX_REGIONS];
+    unsigned long long bytes[RESET_MAX_REGIONS];
+};
+__global__ void __launch_bounds__(256) reset_state_kernel(ResetArgs a) {
+    unsigned char* p = static_cast<unsigned char*>(a.ptr[blockIdx.y]);
+    const unsigned long long n = a.bytes[blockIdx.y];
+    unsigned long long head = (16 - (reinterpret_cast<unsigned long long>(p) & 15)) & 15;
+    if (head > n) head = n;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = tid; i < head; i += stride) p[i] = 0;
+    uint4* q = reinterpret_cast<uint4*>(p + head);
+    const unsigned long long nq = (n - head) >> 4;
+    uint4 z; z.x = 0; z.y = 0; z.z = 0; z.w = 0;
+    for (unsigned long long i = tid; i < nq; i += stride) q[i] = z;
+    for (unsigned long long i = head + (nq << 4) + tid; i < n; i += stride) p[i] = 0;
+}
+
 // gray from an interleaved u8 image (used for the rendered input image in the single-image pairing)
 __global__ void __launch_bounds__(256) gray_u8_kernel(const unsigned char* img, unsigned char* gray, long long npix, int C0) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -477,7 +477,8 @@ static L0Args l0_args(eig_ctx* c, const float* x, int B, int cur, int nxt) {
 // One PredNet time step (net.py:175-211) for B genomes.  x: [B][h][w][c] input frame, t: step index.
 // Layer 0 runs on the fused full-resolution kernels of conv_l0.cuh; layers 1..3 on the tcgen05 kernel (conv_mode TC,
 // shapes with N % 16 == 0) or on the exact-fp32 SIMT kernel.
-static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s) {
+// `last`: no step follows, so the predictions P_2 / P_3 (only read by the next step's error units) are not computed
+static int prednet_step(eig_ctx* c, const float* x, int B, int t, bool last, cudaStream_t s) {
     const int cur = t & 1, nxt = cur ^ 1;
     const bool tc = c->conv_mode == EIG_CONV_TC;
     const bool side_ok = c->overlap && !g_prof.on;   // the per-class profiler times launches on one stream
@@ -574,7 +575,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
 #ifndef EIG_EMU
-        if (side_ok && n >= 2) {   // ConvP_n only needs h_n: it overlaps ConvLSTM_{n-1} .. ConvP_0 of this step
+        if (side_ok && n >= 2 && !last) {   // ConvP_n only needs h_n: it overlaps ConvLSTM_{n-1} .. ConvP_0 of this step
             CK(cudaEventRecord(c->ev_lstm[n], s));
             CK(cudaStreamWaitEvent(c->side, c->ev_lstm[n], 0));
             if ((rc = conv_p(n, c->side))) return rc;
@@ -593,7 +594,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, cudaStream_t s
         else { auto k = l0_convp_kernel<3>; LAUNCH_K_PDL(CLS_L0, k, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, l0); }
         CKL();
     }
-    if (!side_ok)
+    if (!side_ok && !last)
         for (int n = 2; n < 4; ++n)
             if ((rc = conv_p(n, s))) return rc;
     return EIG_OK;
@@ -609,21 +610,32 @@ static int join_side(eig_ctx* c, cudaStream_t s) {
     return EIG_OK;
 }
 
+// Step 0 reads, before anything writes them: h_prev inside the even concat buffers (X[n][0], h0[0]), the cell states and the
+// predictions P_n.  The odd buffers are fully written before they are read (h by step 0, E / up(R) by step 1).
 static int prednet_reset(eig_ctx* c, int B, cudaStream_t s) {
+    ResetArgs ra;
+    memset(&ra, 0, sizeof ra);
+    int r = 0;
+    unsigned long long most = 0;
+    auto add = [&](void* p, size_t bytes) { ra.ptr[r] = p; ra.bytes[r] = bytes; if (bytes > most) most = bytes; ++r; };
     for (int n = 0; n < 4; ++n) {
         const size_t px = (size_t)B * c->H[n] * c->W[n];
-        for (int k = 0; k < 2; ++k) {
-            if (n == 0) { CK(cudaMemsetAsync(c->h0[k], 0, px * c->ch[0] * sizeof(float), s)); continue; }
-            float* lo = lo_plane(c, n, c->X[n][k]);
-            if (!lo) { CK(cudaMemsetAsync(c->X[n][k], 0, px * c->ctot[n] * sizeof(float), s)); continue; }
+        if (n == 0) add(c->h0[0], px * c->ch[0] * sizeof(float));
+        else if (float* lo = lo_plane(c, n, c->X[n][0])) {
             // split-fp16 storage: the lo plane starts after the hi plane of all `cap` genomes, so each plane has its own
             // prefix of B genomes to clear
-            CK(cudaMemsetAsync(c->X[n][k], 0, px * c->ctot[n] * sizeof(h16), s));
-            CK(cudaMemsetAsync(lo, 0, px * c->ctot[n] * sizeof(h16), s));
-        }
-        CK(cudaMemsetAsync(c->cst[n], 0, px * c->ch[n] * sizeof(float), s));
-        CK(cudaMemsetAsync(c->P[n], 0, px * c->ch[n] * sizeof(float), s));
+            add(c->X[n][0], px * c->ctot[n] * sizeof(h16));
+            add(lo, px * c->ctot[n] * sizeof(h16));
+        } else add(c->X[n][0], px * c->ctot[n] * sizeof(float));
+        add(c->cst[n], px * c->ch[n] * sizeof(float));
+        add(c->P[n], px * c->ch[n] * sizeof(float));
     }
+    static_assert(RESET_MAX_REGIONS >= 15, "regions");
+    unsigned bx = (unsigned)((most / 16 + 255) / 256);
+    if (bx < 1) bx = 1;
+    if (bx > 64) bx = 64;
+    LAUNCH_K(CLS_ELEMENTWISE, reset_state_kernel, dim3(bx, r), dim3(256), 0, s, ra);
+    CKL();
     return EIG_OK;
 }
 
@@ -638,7 +650,7 @@ static int prednet_sequence(eig_ctx* c, const float* d_x, int B, int n_in, int n
     for (int t = 0; t < n_in + n_ext; ++t) {
         // extension steps are fed the previous, unquantised prediction (call_prednet.py:185,200)
         const float* x = t < n_in ? d_x : c->P[0];
-        if ((rc = prednet_step(c, x, B, t, s))) return rc;
+        if ((rc = prednet_step(c, x, B, t, t == n_in + n_ext - 1, s))) return rc;
         if (t >= n_in - 1) {
             const int k = t - (n_in - 1);
             unsigned char* fo = frames_out ? frames_out + (size_t)k * npix * c->c_dim : nullptr;

@@ -437,7 +437,7 @@ def test_tensor_core_path_is_the_one_that_runs(gpu_engine_factory):
         n_tc, n_simt = int(cnt[2]), int(cnt[1])
         print("channels %s: %d tcgen05 conv launches, %d SIMT conv launches" % (ch, n_tc, n_simt))
         assert n_simt == 0
-        assert n_tc == 21 * (9 if ch[1] >= 32 else 8)     # A2 A3 L3 L2 L1 P1+Z P2 P3 (+ ConvA1 for wide first layers)
+        assert n_tc == 21 * (9 if ch[1] >= 32 else 8) - 2  # A2 A3 L3 L2 L1 P1+Z P2 P3 (+ ConvA1 for wide first layers); no P2 / P3 on the last step
 
 
 def test_reference_call_surface(tmp_path):
