@@ -184,6 +184,8 @@ def run_ours(args):
     preset, c_dim, ch, w, h, structure, pop, macs = WORKLOADS[args.workload]
     if args.pop:
         pop = args.pop
+    if args.scaling == "strong":   # SURVEY.md §8 d sweep (i): the workload's population split over the ranks
+        pop = -(-pop // world)
     dev = torch.device("cuda", local)
     eng = E.Engine(w, h, ch, pop, device=local)
     eng.set_conv_mode(_lib.CONV_TC if args.conv == "tc" else _lib.CONV_SIMT)
@@ -303,7 +305,7 @@ def run_ours(args):
                              "%.1f s" % (n_s, args.workload, dt)}
         line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (3-pass split-fp16 tcgen05, fp32 accumulate)" if args.conv == "tc" else "fp32",
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "fp32 (3-pass split-fp16 tcgen05, fp32 accumulate)" if args.conv == "tc" else "fp32",
                 "data": "synthetic",
                 "config": {"workload": args.workload, "pop_per_gpu": pop, "global_pop": world * pop,
                            "resolution": "%dx%d" % (w, h), "channels": list(ch), "neat_config": preset,
@@ -330,6 +332,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--conv", default=os.environ.get("EIG_BENCH_CONV", "auto"), choices=["auto", "simt", "tc"])
     ap.add_argument("--pop", type=int, default=0, help="genomes per GPU (default: the workload's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: fixed genomes per GPU (default, the driver's contract); strong: the population is split over the GPUs")
     ap.add_argument("--ref-sample", type=int, default=8, help="genomes per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -13,6 +13,7 @@ outputs 0..2 of 6-output configs, the dead 22nd PredNet forward is not computed.
 """
 import argparse
 import os
+import time
 
 import numpy as np
 
@@ -58,9 +59,12 @@ def get_fitnesses_neat(structure, population, model_name, config, w, h, channels
     n_out = _used_outputs(c_dim)
     # each rank flattens its own shard, chunk by chunk, while the GPU evaluates the previous chunk; unchanged genomes
     # (elites) come out of the program cache
+    t0 = time.perf_counter()
     fit = runtime.evaluate_genomes(eng, population, lambda gid, g: program_cache.get(gid, g, config, n_out),
                                    int(structure), mode, PAIR_POPULATION)
+    dt = time.perf_counter() - t0
     program_cache.end_generation()
+    print("evaluated %d genomes in %.1f ms (%.0f evals/s)" % (len(population), 1e3 * dt, len(population) / max(dt, 1e-9)))
     best_score, best_i = 0, 0
     for i, (_, genome) in enumerate(population):
         genome.fitness = float(fit[i])

@@ -183,11 +183,21 @@ def synthetic_population(preset, n, evolved=False, num_inputs=None, start=0):
 
 # ----------------------------------------------------------------------------- flattener
 def required_for_output(inputs, outputs, connections):
+    """neat.graphs.required_for_output restated: nodes whose value can reach an output, found layer by layer from the
+    outputs backwards (the walk stops at a layer that holds only input pins)."""
+    preds = {}
+    for a, b in connections:
+        preds.setdefault(b, []).append(a)
     needed = set(outputs)
     seen = set(outputs)
     inputs = set(inputs)
+    frontier = list(outputs)
     while True:
-        layer = {a for (a, b) in connections if b in seen and a not in seen}
+        layer = set()
+        for b in frontier:
+            for a in preds.get(b, ()):
+                if a not in seen:
+                    layer.add(a)
         if not layer:
             return needed
         hidden = layer - inputs
@@ -195,6 +205,7 @@ def required_for_output(inputs, outputs, connections):
             return needed
         needed |= hidden
         seen |= layer
+        frontier = layer
 
 
 _F32_ACT = {
@@ -263,42 +274,51 @@ def flatten_genome(genome, config, n_outputs=None):
         incoming.setdefault(src, [])
 
     prog = FlatProgram()
-    memo = {in_keys[0]: ("var", SLOT_X), in_keys[1]: ("var", SLOT_Y)}
+    nodes, terms_out, nodes_out = genome.nodes, prog.terms, prog.nodes
+    # memo: node key -> int slot (value depends on x / y) or float32 tensor (input-independent, folded on the host)
+    memo = {in_keys[0]: SLOT_X, in_keys[1]: SLOT_Y}
 
     def emit(act, agg, terms, bias, resp):
-        t0 = len(prog.terms)
-        prog.terms.extend(terms)
-        prog.nodes.append((act, agg, t0, len(terms), float(bias), float(resp)))
-        return SLOT_NODE0 + len(prog.nodes) - 1
+        t0 = len(terms_out)
+        terms_out.extend(terms)
+        nodes_out.append((act, agg, t0, len(terms), float(bias), float(resp)))
+        return SLOT_NODE0 + len(nodes_out) - 1
 
     def visit(key):
-        if key in memo:
-            return memo[key]
-        gene = genome.nodes[key]
+        res = memo.get(key)
+        if res is not None:
+            return res
+        gene = nodes[key]
         srcs = incoming[key]
         if not srcs:
-            res = ("const", torch.full((_FOLD_N,), gene.bias))
-            memo[key] = res
+            res = memo[key] = torch.full((_FOLD_N,), gene.bias)
             return res
-        vals = [(w, visit(s)) for s, w in srcs]
         agg = gene.aggregation
         if agg not in AGG_IDS:
             raise KeyError("unsupported aggregation %r" % agg)
-        combine = (lambda a, b: a + b) if agg == "sum" else (lambda a, b: a * b)
-        if all(v[0] == "const" for _, v in vals):
+        vals = [(w, visit(s)) for s, w in srcs]
+        n_var = 0
+        for _, v in vals:
+            if type(v) is int:
+                n_var += 1
+        if n_var == len(vals):          # the common case: every source depends on the inputs
+            res = memo[key] = emit(ACT_IDS[gene.activation], AGG_IDS[agg], [(float(w), v) for w, v in vals],
+                                   gene.bias, gene.response)
+            return res
+        is_sum = agg == "sum"
+        if n_var == 0:
             acc = None
-            for w, (_, t) in vals:
+            for w, t in vals:
                 term = w * t
-                acc = term if acc is None else combine(acc, term)
-            res = ("const", _F32_ACT[gene.activation](gene.response * acc + gene.bias))
-            memo[key] = res
+                acc = term if acc is None else (acc + term if is_sum else acc * term)
+            res = memo[key] = _F32_ACT[gene.activation](gene.response * acc + gene.bias)
             return res
         terms, prefix, seen_var = [], None, False
-        for w, (kind, v) in vals:
-            if kind == "const":
+        for w, v in vals:
+            if type(v) is not int:
                 term = w * v
                 if not seen_var:
-                    prefix = term if prefix is None else combine(prefix, term)
+                    prefix = term if prefix is None else (prefix + term if is_sum else prefix * term)
                 else:
                     terms.append((float(term[0].item()), SLOT_ONE))
             else:
@@ -306,14 +326,12 @@ def flatten_genome(genome, config, n_outputs=None):
                     terms.append((float(prefix[0].item()), SLOT_ONE))
                 seen_var = True
                 terms.append((float(w), v))
-        slot = emit(ACT_IDS[gene.activation], AGG_IDS[agg], terms, gene.bias, gene.response)
-        res = ("var", slot)
-        memo[key] = res
+        res = memo[key] = emit(ACT_IDS[gene.activation], AGG_IDS[agg], terms, gene.bias, gene.response)
         return res
 
     for k in used_outs:
-        kind, v = visit(k)
-        if kind == "const":
+        v = visit(k)
+        if type(v) is not int:
             # constant output plane: identity node 1.0*(c*1.0)+0.0
             # (bit 30 tells the kernel the plane is float32 in the reference: gray images multiply it in fp32)
             v = emit(ACT_IDS["identity"], AGG_IDS["sum"], [(float(v[0].item()), SLOT_ONE)], 0.0, 1.0) | OUT_F32_CONST
