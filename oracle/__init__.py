@@ -12,7 +12,9 @@ Parity pinning status (see DESIGN.md "Oracle"):
   * scoring               : pinned against the reference's fitness_calculator.py (same harness).
   * optical flow          : pinned against the cv2 4.13 binary the reference calls (cv2 is third-party,
                             unpinned by the reference; restated in numpy in flow.py).
-  * PredNet               : PARITY UNPINNED - Chainer is not installable offline and the reference has no
-                            test or golden vector for net.py; prednet.py restates net.py/call_prednet.py
-                            in torch-CPU fp32 with the Chainer semantics listed in SURVEY.md §8(c).
+  * PredNet + whole path  : pinned against the reference's own net.py / call_prednet.py / get_fitnesses_neat,
+                            executed unmodified with Chainer replaced by the functional stand-in
+                            tests/golden/chainer_shim (tests/golden/reference_pipeline.npz: frames within 1 LSB,
+                            fitness within 4e-4 relative).  Unpinned: the arithmetic inside Chainer's own
+                            primitives (Chainer is not installable offline; restated from its documentation).
 """

@@ -1,7 +1,11 @@
 """Oracle: PredNet inference in torch-CPU fp32.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
-PARITY UNPINNED: Chainer cannot be installed offline and the reference holds no test / golden vector for
-this stage, so this file restates
+PINNED TO THE REFERENCE'S OWN CODE UNDER A CHAINER STAND-IN: Chainer (third-party, v5-v7) cannot be installed offline
+and the reference holds no test / golden vector for this stage.  `tests/golden/chainer_shim` restates the few Chainer
+primitives net.py uses; with it the reference's net.py, call_prednet.py and the whole get_fitnesses_neat run unmodified
+(tests/golden/ref_harness.py), and tests/golden/reference_pipeline.npz holds their frames and fitness values.  This file
+reproduces them (frames within 1 LSB, fitness within 4e-4 relative; tests/test_oracle_golden.py).  What stays
+unpinned is the arithmetic inside Chainer's primitives, restated from its documentation.  This file restates
   * `PredNet.__call__`   /root/reference/chainer_prednet/PredNet/net.py:175-211
   * `ConvLSTM.__call__`  net.py:84-126,  `EltFilter.__call__` net.py:30-34
   * frame protocol       /root/reference/chainer_prednet/PredNet/call_prednet.py:129-205 (`test_image_list`),

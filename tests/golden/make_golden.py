@@ -175,7 +175,64 @@ def make_pipeline_predictor():
     np.savez_compressed(os.path.join(HERE, "pipeline_predictor.npz"), **out)
 
 
+REFERENCE_CASES = [
+    # name, preset, c_dim, channels, w, h, structure, gradient, n genomes, evolved, weight seed
+    ("r_small_gray", "circles_bw", 1, (1, 4, 8, 8), 64, 64, 1, 1, 6, True, 3),
+    ("r_small_free", "circles_bw", 1, (1, 16, 32, 64), 64, 64, 2, 1, 6, True, 0),
+    ("r_small_colour_palette", "circles", 3, (3, 6, 12, 24), 64, 64, 1, 0, 4, True, 5),
+    ("r_c2", "circles_bw", 1, (1, 16, 32, 64), 160, 120, 1, 1, 8, False, 0),
+    ("r_c3", "circles", 3, (3, 48, 96, 192), 160, 120, 1, 1, 4, False, 0),
+]
+
+
+def run_reference_case(ns, case, workdir):
+    """The reference's own `get_fitnesses_neat` (generate_illusion.py:478-673), UNMODIFIED, on a seeded population and a
+    seeded weight file, with Chainer replaced by tests/golden/chainer_shim and "the GPU" being numpy.  Returns the
+    fitness the reference assigned to every genome plus the two frames it fed to lucas_kanade for every genome."""
+    from PIL import Image
+    name, preset, c_dim, ch, w, h, structure, gradient, n, evolved, wseed = case
+    os.makedirs(os.path.join(workdir, "best"), exist_ok=True)
+    model = os.path.join(workdir, "model.npz")
+    W.save_npz(model, W.synthetic_predictor_weights(w, h, ch, seed=wseed))
+    cfg = G.make_config(2, G.NEAT_PRESETS[preset]["num_outputs"])    # circles / circles_bw: 3 / 1 outputs
+    pop = G.synthetic_population(preset, n, evolved=evolved)
+    cwd = os.getcwd()
+    os.chdir(workdir)
+    try:
+        ns.gi.get_fitnesses_neat(ns.gi.StructureType(structure), pop, model, cfg, w, h, list(ch), c_dim=c_dim,
+                                 best_dir=os.path.join(workdir, "best"), gradient=gradient)
+        repeat, ext = 20, 2
+        frames = []
+        for i in range(n):              # generate_illusion.py:543-546
+            i0 = i * repeat + repeat - 1
+            f0 = np.asarray(Image.open("temp/prediction/%s.png" % str(i0).zfill(10)))
+            f1 = np.asarray(Image.open("temp/prediction/%s_extended.png" % str(i0 + ext - 1).zfill(10)))
+            frames.append(np.stack([f0, f1]))
+    finally:
+        os.chdir(cwd)
+    return np.array([float(g.fitness) for _, g in pop]), np.stack(frames)
+
+
+def make_reference_pipeline(ns):
+    """tests/golden/reference_pipeline.npz: fitness vectors and frames produced by the reference itself."""
+    import tempfile
+    out, meta = {}, []
+    for case in REFERENCE_CASES:
+        with tempfile.TemporaryDirectory() as d:
+            fit, frames = run_reference_case(ns, case, d)
+        name = case[0]
+        out["fitness_" + name], out["frames_" + name] = fit, frames
+        meta.append(dict(zip(("name", "preset", "c_dim", "channels", "w", "h", "structure", "gradient", "n", "evolved",
+                              "weight_seed"), case)))
+        print(name, "reference fitness", np.round(fit, 6))
+    out["meta"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(HERE, "reference_pipeline.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "reference":
+        make_reference_pipeline(ref_harness.load())
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "predictor":
         make_pipeline_predictor()
         sys.exit(0)
@@ -189,3 +246,4 @@ if __name__ == "__main__":
     make_enhanced_digest(ns)
     make_flow_and_pipeline()
     make_pipeline_predictor()
+    make_reference_pipeline(ns)

@@ -211,6 +211,37 @@ def test_whole_path_fitness_vs_oracle_golden(gpu_engine_factory, mode):
     assert np.mean([r[1] for r in report]) >= 0.8
 
 
+@pytest.mark.parametrize("mode", ["simt", "tc"])
+def test_whole_path_fitness_vs_the_reference_itself(gpu_engine_factory, mode):
+    """tests/golden/reference_pipeline.npz: fitness assigned by the REFERENCE's own get_fitnesses_neat (run unmodified
+    under the Chainer shim, see tests/golden/make_golden.py) and the frames it handed to lucas_kanade.  The CUDA path
+    must match it directly: fitness within 1e-3 relative (north_star), frames within 1 LSB."""
+    z = np.load(os.path.join(GOLDEN, "reference_pipeline.npz"))
+    worst = 0.0
+    for m in json.loads(str(z["meta"])):
+        w, h, ch, c = m["w"], m["h"], tuple(m["channels"]), m["c_dim"]
+        cfg = G.make_config(2, G.NEAT_PRESETS[m["preset"]]["num_outputs"])
+        pop = G.synthetic_population(m["preset"], m["n"], evolved=m["evolved"])
+        progs = [G.flatten_genome(g, cfg, n_outputs=c if c > 1 else 1) for _, g in pop]
+        eng = gpu_engine_factory(w, h, ch, m["n"])
+        eng.set_conv_mode(_lib.CONV_TC if mode == "tc" else _lib.CONV_SIMT)
+        eng.set_grid(m["structure"])
+        eng.load_weights(W.synthetic_predictor_weights(w, h, ch, seed=m["weight_seed"]))
+        fit = eng.evaluate(progs, m["structure"], E.render_mode_for(c, m["gradient"]))
+        ref = z["fitness_" + m["name"]]
+        frames = eng.debug_buffers(m["n"])["frames"]
+        ref_frames = z["frames_" + m["name"]]
+        for k in range(2):
+            d = np.abs(_sq(frames[k], c).astype(int) - ref_frames[:, k].astype(int))
+            assert d.max() <= 1 and (d > 0).mean() < 1e-3, (m["name"], k, int(d.max()), float((d > 0).mean()))
+        assert np.allclose(fit, ref, rtol=1e-3, atol=1e-9, equal_nan=True), (m["name"], mode, fit, ref)
+        nz = np.isfinite(ref) & (ref != 0)
+        if nz.any():
+            worst = max(worst, float(np.max(np.abs(fit[nz] / ref[nz] - 1))))
+        print("%s [%s]: gpu %s reference %s" % (m["name"], mode, np.round(fit, 6), np.round(ref, 6)))
+    print("GPU vs the reference's own get_fitnesses_neat [%s]: worst relative difference %.2e" % (mode, worst))
+
+
 def test_edge_cases_and_errors(gpu_engine_factory):
     w, h, ch = 64, 64, (1, 4, 8, 8)
     eng = E.Engine(w, h, ch, 2)

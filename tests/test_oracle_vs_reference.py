@@ -78,3 +78,26 @@ def test_reference_test_cppn_cases_pass_under_stub():
         "t.test_cppn_simple(); t.test_cppn_unconnected(); t.test_cppn_call(); t.test_cppn_deep_call(); print('OK4')\n")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "OK4" in out.stdout, out.stderr[-2000:]
+
+
+def test_reference_get_fitnesses_neat_runs_and_reproduces_the_fixture(ns, tmp_path):
+    """The smallest case of tests/golden/reference_pipeline.npz, re-run live: the reference's whole fitness function,
+    unmodified, under the Chainer shim.  Also checks that the parameter paths of the reference's own model definition
+    (net.py:128-157, L.Classifier) are exactly the keys `weights.py` writes."""
+    import json
+    import os
+    import sys
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    import make_golden
+    import chainer
+    from evolutionary_illusion_generator_b200 import weights as W
+    from chainer_prednet.PredNet import net
+    model = chainer.links.Classifier(net.PredNet(64, 64, (1, 4, 8, 8)))
+    assert sorted(p.lstrip("/") for p, _ in model.namedparams()) == sorted(W.synthetic_weights(64, 64, (1, 4, 8, 8), seed=0))
+    z = np.load(os.path.join(GOLDEN, "reference_pipeline.npz"))
+    case = make_golden.REFERENCE_CASES[0]
+    fit, frames = make_golden.run_reference_case(ns, case, str(tmp_path))
+    assert np.array_equal(fit, z["fitness_" + case[0]], equal_nan=True)
+    assert np.array_equal(frames, z["frames_" + case[0]])
+    assert json.loads(str(z["meta"]))[0]["name"] == case[0]
