@@ -229,9 +229,71 @@ def make_reference_pipeline(ns):
     np.savez_compressed(os.path.join(HERE, "reference_pipeline.npz"), **out)
 
 
+SINGLE_IMAGE_CASES = [
+    # name, preset, c_dim, channels, w, h, genome indices, weight seed
+    ("s_small_gray", "circles_bw", 1, (1, 16, 32, 64), 64, 64, [0, 1, 2], 0),
+    ("s_c3", "circles", 3, (3, 48, 96, 192), 160, 120, [1, 2], 0),
+]
+
+
+def run_single_image_case(ns, case, workdir):
+    """The reference's single-image rating flow (fitness_calculator.py:468-548: `get_vectors` pairs the input image with
+    extension #2, `calculate_fitness` scores it), unmodified, on images rendered by the reference's own
+    `get_image_from_cppn`.  A `calculate_fitness` call that hits the reference's UnboundLocalError is recorded as NaN."""
+    name, preset, c_dim, ch, w, h, idx, wseed = case
+    model = os.path.join(workdir, "model.npz")
+    W.save_npz(model, W.synthetic_predictor_weights(w, h, ch, seed=wseed))
+    cfg = G.make_config(2, G.NEAT_PRESETS[preset]["num_outputs"])
+    grid = ns.gi.create_grid(ns.gi.StructureType.Circles, w, h, 10)
+    cwd = os.getcwd()
+    os.chdir(workdir)
+    images, vectors, scores = [], [], []
+    try:
+        for i in idx:
+            img = ns.gi.get_image_from_cppn(grid, G.synthetic_genome(preset, i), c_dim, w, h, cfg)
+            path = os.path.join(workdir, "img_%d.png" % i)
+            img.save(path, "PNG")
+            vec = ns.fc.get_vectors(path, model, list(ch), w, h)
+            row = []
+            for st in (ns.gi.StructureType.Circles, ns.gi.StructureType.Free):
+                try:
+                    row.append(float(ns.fc.calculate_fitness(st, vec, path, w, h)) if vec[0] is not None else float("nan"))
+                except UnboundLocalError:
+                    row.append(float("nan"))
+            images.append(np.asarray(img))
+            vectors.append(np.zeros((0, 4), np.float32) if vec[0] is None else np.asarray(vec, np.float32).reshape(-1, 4))
+            scores.append(row)
+    finally:
+        os.chdir(cwd)
+    return images, vectors, np.array(scores)
+
+
+def make_reference_single_image(ns):
+    import tempfile
+    out, meta = {}, []
+    for case in SINGLE_IMAGE_CASES:
+        with tempfile.TemporaryDirectory() as d:
+            images, vectors, scores = run_single_image_case(ns, case, d)
+        name = case[0]
+        out["images_" + name] = np.stack(images)
+        out["nvec_" + name] = np.array([len(v) for v in vectors])
+        pad = np.zeros((len(vectors), 100, 4), np.float32)
+        for i, v in enumerate(vectors):
+            pad[i, :len(v)] = v
+        out["vectors_" + name], out["scores_" + name] = pad, scores
+        meta.append(dict(zip(("name", "preset", "c_dim", "channels", "w", "h", "genomes", "weight_seed"), case)))
+        print(name, "vectors", out["nvec_" + name], "scores (Circles, Free)", np.round(scores, 5).tolist())
+    out["meta"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(HERE, "reference_single_image.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "reference":
         make_reference_pipeline(ref_harness.load())
+        make_reference_single_image(ref_harness.load())
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "single":
+        make_reference_single_image(ref_harness.load())
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "predictor":
         make_pipeline_predictor()
@@ -247,3 +309,4 @@ if __name__ == "__main__":
     make_flow_and_pipeline()
     make_pipeline_predictor()
     make_reference_pipeline(ns)
+    make_reference_single_image(ns)

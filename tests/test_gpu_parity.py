@@ -524,6 +524,34 @@ def test_reference_call_surface(tmp_path):
     assert os.path.isfile(str(tmp_path / "flow" / "a.png")) and os.path.isfile(str(tmp_path / "flow" / "csv" / "a.csv"))
 
 
+def test_single_image_rating_vs_the_reference_itself(tmp_path):
+    """`fitness_calculator.get_vectors` / `calculate_fitness` of the drop-in package against what the reference's own
+    functions returned for the same image and weight file (tests/golden/reference_single_image.npz)."""
+    from PIL import Image
+    from evolutionary_illusion_generator_b200 import fitness_calculator as FC, generate_illusion as GI
+    z = np.load(os.path.join(GOLDEN, "reference_single_image.npz"))
+    for m in json.loads(str(z["meta"])):
+        w, h, ch, c = m["w"], m["h"], tuple(m["channels"]), m["c_dim"]
+        model = str(tmp_path / (m["name"] + ".npz"))
+        W.save_npz(model, W.synthetic_predictor_weights(w, h, ch, seed=m["weight_seed"]))
+        for i in range(len(m["genomes"])):
+            img = z["images_" + m["name"]][i]
+            path = str(tmp_path / ("%s_%d.png" % (m["name"], i)))
+            (Image.fromarray(img) if c == 3 else Image.fromarray(img, "L")).save(path)
+            vec = FC.get_vectors(path, model, ch, w, h)
+            n = int(z["nvec_" + m["name"]][i])
+            assert (len(vec) == n) if n else (vec[0] is None)
+            assert np.allclose(np.asarray(vec, np.float32).reshape(-1, 4), z["vectors_" + m["name"]][i, :n], atol=2e-3)
+            for k, st in enumerate((GI.StructureType.Circles, GI.StructureType.Free)):
+                ref = z["scores_" + m["name"]][i, k]
+                got = FC.calculate_fitness(st, vec, path, w, h)
+                if np.isnan(ref):
+                    assert got == 0.0                      # the reference raises UnboundLocalError here
+                else:
+                    assert np.isclose(got, ref, rtol=1e-3, atol=1e-9), (m["name"], i, st, got, ref)
+            print("%s image %d: %d vectors, scores match the reference %s" % (m["name"], i, n, np.round(z["scores_" + m["name"]][i], 5)))
+
+
 def test_tcgen05_conv_self_check():
     """tests/gpu/tc_check (built by csrc/build.sh): the tcgen05 conv against a float64 CPU convolution and, epilogue by
     epilogue, against the exact-fp32 SIMT kernel on identical inputs."""
