@@ -180,6 +180,8 @@ REFERENCE_CASES = [
     ("r_small_gray", "circles_bw", 1, (1, 4, 8, 8), 64, 64, 1, 1, 6, True, 3),
     ("r_small_free", "circles_bw", 1, (1, 16, 32, 64), 64, 64, 2, 1, 6, True, 0),
     ("r_small_colour_palette", "circles", 3, (3, 6, 12, 24), 64, 64, 1, 0, 4, True, 5),
+    ("r_circlesfree", "circles_bw", 1, (1, 16, 32, 64), 160, 120, 3, 1, 3, False, 0),
+    ("r_small_gray_round", "circles_bw", 1, (1, 4, 8, 8), 64, 64, 1, 0, 4, False, 3),
     ("r_c2", "circles_bw", 1, (1, 16, 32, 64), 160, 120, 1, 1, 8, False, 0),
     ("r_c3", "circles", 3, (3, 48, 96, 192), 160, 120, 1, 1, 4, False, 0),
 ]
