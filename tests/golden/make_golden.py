@@ -187,6 +187,9 @@ REFERENCE_CASES = [
 ]
 
 
+EXPORT_CASES = ("r_small_free", "r_small_colour_palette")
+
+
 def run_reference_case(ns, case, workdir):
     """The reference's own `get_fitnesses_neat` (generate_illusion.py:478-673), UNMODIFIED, on a seeded population and a
     seeded weight file, with Chainer replaced by tests/golden/chainer_shim and "the GPU" being numpy.  Returns the
@@ -210,9 +213,11 @@ def run_reference_case(ns, case, workdir):
             f0 = np.asarray(Image.open("temp/prediction/%s.png" % str(i0).zfill(10)))
             f1 = np.asarray(Image.open("temp/prediction/%s_extended.png" % str(i0 + ext - 1).zfill(10)))
             frames.append(np.stack([f0, f1]))
+        exported = {k: np.asarray(Image.open(os.path.join(workdir, "best", k + ".png")))
+                    for k in ("best", "best_black_bg", "best_flow", "enhanced")}      # generate_illusion.py:650-671
     finally:
         os.chdir(cwd)
-    return np.array([float(g.fitness) for _, g in pop]), np.stack(frames)
+    return np.array([float(g.fitness) for _, g in pop]), np.stack(frames), exported
 
 
 def make_reference_pipeline(ns):
@@ -221,9 +226,12 @@ def make_reference_pipeline(ns):
     out, meta = {}, []
     for case in REFERENCE_CASES:
         with tempfile.TemporaryDirectory() as d:
-            fit, frames = run_reference_case(ns, case, d)
+            fit, frames, exported = run_reference_case(ns, case, d)
         name = case[0]
         out["fitness_" + name], out["frames_" + name] = fit, frames
+        if name in EXPORT_CASES:        # the files the reference writes for the best genome of the generation
+            for k, v in exported.items():
+                out["export_%s_%s" % (k, name)] = v
         meta.append(dict(zip(("name", "preset", "c_dim", "channels", "w", "h", "structure", "gradient", "n", "evolved",
                               "weight_seed"), case)))
         print(name, "reference fitness", np.round(fit, 6))

@@ -524,6 +524,34 @@ def test_reference_call_surface(tmp_path):
     assert os.path.isfile(str(tmp_path / "flow" / "a.png")) and os.path.isfile(str(tmp_path / "flow" / "csv" / "a.csv"))
 
 
+def test_exported_files_vs_the_reference_itself(tmp_path):
+    """get_fitnesses_neat of the drop-in package on the populations of tests/golden/reference_pipeline.npz: genome.fitness
+    within 1e-3 of what the reference assigned, and best.png / best_black_bg.png / enhanced.png (800x800 mosaic) pixel-identical
+    to the files the reference wrote for its best genome (generate_illusion.py:650-671)."""
+    from PIL import Image
+    from evolutionary_illusion_generator_b200 import generate_illusion as GI
+    z = np.load(os.path.join(GOLDEN, "reference_pipeline.npz"))
+    for m in json.loads(str(z["meta"])):
+        if "export_best_" + m["name"] not in z.files:
+            continue
+        w, h, ch, c = m["w"], m["h"], tuple(m["channels"]), m["c_dim"]
+        model = str(tmp_path / (m["name"] + ".npz"))
+        W.save_npz(model, W.synthetic_predictor_weights(w, h, ch, seed=m["weight_seed"]))
+        cfg = G.make_config(2, G.NEAT_PRESETS[m["preset"]]["num_outputs"])
+        pop = G.synthetic_population(m["preset"], m["n"], evolved=m["evolved"])
+        best_dir = str(tmp_path / ("best_" + m["name"]))
+        GI.get_fitnesses_neat(GI.StructureType(m["structure"]), pop, model, cfg, w, h, ch, c_dim=c, best_dir=best_dir,
+                              gradient=m["gradient"])
+        got = np.array([g.fitness for _, g in pop])
+        assert np.allclose(got, z["fitness_" + m["name"]], rtol=1e-3, atol=1e-9, equal_nan=True)
+        for k in ("best", "best_black_bg", "enhanced"):
+            mine = np.asarray(Image.open(os.path.join(best_dir, k + ".png")))
+            ref = z["export_%s_%s" % (k, m["name"])]
+            assert mine.shape == ref.shape and np.array_equal(mine, ref), (m["name"], k, mine.shape, ref.shape)
+        assert np.asarray(Image.open(os.path.join(best_dir, "best_flow.png"))).shape == z["export_best_flow_" + m["name"]].shape
+        print("%s: best.png, best_black_bg.png, enhanced.png identical to the reference's files" % m["name"])
+
+
 def test_single_image_rating_vs_the_reference_itself(tmp_path):
     """`fitness_calculator.get_vectors` / `calculate_fitness` of the drop-in package against what the reference's own
     functions returned for the same image and weight file (tests/golden/reference_single_image.npz)."""

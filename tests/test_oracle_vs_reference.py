@@ -97,7 +97,7 @@ def test_reference_get_fitnesses_neat_runs_and_reproduces_the_fixture(ns, tmp_pa
     assert sorted(p.lstrip("/") for p, _ in model.namedparams()) == sorted(W.synthetic_weights(64, 64, (1, 4, 8, 8), seed=0))
     z = np.load(os.path.join(GOLDEN, "reference_pipeline.npz"))
     case = make_golden.REFERENCE_CASES[0]
-    fit, frames = make_golden.run_reference_case(ns, case, str(tmp_path))
+    fit, frames, _ = make_golden.run_reference_case(ns, case, str(tmp_path))
     assert np.array_equal(fit, z["fitness_" + case[0]], equal_nan=True)
     assert np.array_equal(frames, z["frames_" + case[0]])
     assert json.loads(str(z["meta"]))[0]["name"] == case[0]
