@@ -27,6 +27,8 @@ SYMBOLS = [
     ("eig_set_grid", _I, [_P, _P, _P]),
     ("eig_cppn_render", _I, [_P, _P, _P, _I, _I, _I, _I, _D, _P, _P, _P]),
     ("eig_prednet_run", _I, [_P, _P, _I, _I, _I, _P, _P]),
+    ("eig_prednet_reset", _I, [_P, _I, _P]),
+    ("eig_prednet_forward", _I, [_P, _P, _I, _P, _P, _P]),
     ("eig_flow", _I, [_P, _P, _P, _I, _P, _P, _P, _P, _P]),
     ("eig_score", _I, [_P, _P, _P, _I, _I, _P, _P]),
     ("eig_eval", _I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),

@@ -117,6 +117,7 @@ struct eig_ctx {
     // host staging for eig_eval_host
     void* d_blob = nullptr; size_t d_blob_cap = 0; long long* d_off = nullptr;
     size_t corner_smem = 0;   // bitmap of the greedy corner spacing: one bit per pixel
+    int seq_t = 0, seq_n = -1;   // stateful stepping (eig_prednet_reset / eig_prednet_forward)
     void* h_pin = nullptr; size_t h_pin_cap = 0;
     cudaStream_t stream = 0;
     // ConvP_2 / ConvP_3 are off the critical path of a PredNet step: they run on a side stream, ordered by events
@@ -645,6 +646,7 @@ static int prednet_sequence(eig_ctx* c, const float* d_x, int B, int n_in, int n
                             unsigned char* const* gray_dst, cudaStream_t s) {
     int rc;
     if ((rc = join_side(c, s))) return rc;   // a previous sequence may still have ConvP launches on the side stream
+    c->seq_n = -1;                           // the stepping state (eig_prednet_forward) does not survive a whole-sequence run
     if ((rc = prednet_reset(c, B, s))) return rc;
     const long long npix = (long long)B * c->h * c->w;
     for (int t = 0; t < n_in + n_ext; ++t) {
@@ -703,6 +705,37 @@ extern "C" int eig_prednet_run(eig_ctx* c, const float* d_x, int n, int n_in, in
     if (!d_x || !d_frames || n_in < 1 || n_ext < 0) return fail(EIG_E_INVALID, "eig_prednet_run: bad argument");
     CK(cudaSetDevice(c->device));
     return prednet_sequence(c, d_x, n, n_in, n_ext, d_frames, nullptr, TO_STREAM(stream));
+}
+
+// stateful single steps: sequences of distinct frames, every prediction readable (test_image_list, call_prednet.py:129-205)
+extern "C" int eig_prednet_reset(eig_ctx* c, int n, void* stream) {
+    int rc;
+    if ((rc = check_ready(c, n, true, false))) return rc;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = TO_STREAM(stream);
+    if ((rc = join_side(c, s))) return rc;
+    c->seq_t = 0;
+    c->seq_n = n;
+    return prednet_reset(c, n, s);
+}
+
+extern "C" int eig_prednet_forward(eig_ctx* c, const float* d_x, int n, float* d_pred, uint8_t* d_frame, void* stream) {
+    int rc;
+    if ((rc = check_ready(c, n, true, false))) return rc;
+    if (!d_x) return fail(EIG_E_INVALID, "eig_prednet_forward: null input");
+    if (c->seq_n != n) return fail(EIG_E_STATE, "eig_prednet_forward: call eig_prednet_reset with the same n first");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = TO_STREAM(stream);
+    if ((rc = prednet_step(c, d_x, n, c->seq_t, false, s))) return rc;
+    ++c->seq_t;
+    const long long npix = (long long)n * c->h * c->w;
+    if (d_pred) CK(cudaMemcpyAsync(d_pred, c->P[0], sizeof(float) * npix * c->c_dim, cudaMemcpyDeviceToDevice, s));
+    if (d_frame) {
+        LAUNCH_K(CLS_ELEMENTWISE, quantize_gray_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s,
+                   (const float*)c->P[0], d_frame, (unsigned char*)nullptr, npix, c->c_dim);
+        CKL();
+    }
+    return EIG_OK;
 }
 
 // corners + LK + vector rows from the gray level-0 images already in c->gray[0] ([0,B) frame 1, [B,2B) frame 2)
@@ -816,6 +849,7 @@ extern "C" int eig_eval(eig_ctx* c, const void* d_blob, const int64_t* d_offsets
     if ((rc = check_ready(c, n, true, true))) return rc;
     if (!d_fitness) return fail(EIG_E_INVALID, "eig_eval: null fitness pointer");
     if (pair_mode != EIG_PAIR_POPULATION && pair_mode != EIG_PAIR_SINGLE_IMAGE) return fail(EIG_E_INVALID, "unknown pair mode");
+    c->seq_n = -1;   // the evaluation (possibly a graph replay) overwrites the recurrent state of eig_prednet_forward
     cudaStream_t s = TO_STREAM(stream);
     if ((rc = eig_cppn_render(c, d_blob, d_offsets, n, max_slots, max_blob_bytes, render_mode, 1.0, c->img, c->x_in, stream))) return rc;
 #ifndef EIG_EMU

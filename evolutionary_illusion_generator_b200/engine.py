@@ -139,6 +139,23 @@ class Engine:
         self.sync()
         return frames
 
+    def prednet_reset(self, n=1):
+        """`prednet.reset_state()` for n parallel sequences (stateful stepping, see prednet_forward)."""
+        self._seq_n = int(n)
+        self.lib.check(self.lib.eig_prednet_reset(self.ctx, self._seq_n, self._stream()))
+
+    def prednet_forward(self, x):
+        """One forward step on x (n,h,w,c) float32 with the state carried over from the previous call:
+        -> (unquantised prediction float32 (n,h,w,c), uint8 frame as `write_image` stores it)."""
+        x = x.contiguous()
+        n = x.shape[0]
+        pred = torch.empty((n, self.h, self.w, self.c_dim), dtype=torch.float32, device=self.tdev)
+        frame = torch.empty((n, self.h, self.w, self.c_dim), dtype=torch.uint8, device=self.tdev)
+        self.lib.check(self.lib.eig_prednet_forward(self.ctx, x.data_ptr(), n, pred.data_ptr(), frame.data_ptr(),
+                                                    self._stream()))
+        self.sync()
+        return pred, frame
+
     def flow(self, img1, img2):
         """img1/img2: (n,h,w,c) uint8 device tensors -> (corners, ncorners, vectors, nvec) device tensors."""
         n = img1.shape[0]

@@ -72,6 +72,14 @@ int eig_cppn_render(eig_ctx* ctx, const void* d_blob, const int64_t* d_offsets, 
 int eig_prednet_run(eig_ctx* ctx, const float* d_x, int n, int n_input_steps, int n_ext, uint8_t* d_frames,
                     void* stream);
 
+/* The same network stepped frame by frame, for sequences of DISTINCT frames and when every prediction is wanted
+ * (`test_image_list`, call_prednet.py:129-205): eig_prednet_reset = `prednet.reset_state()` (net.py:159-164) for n
+ * parallel sequences; eig_prednet_forward = one `model(x, y)` call (call_prednet.py:155): d_x [n][h][w][c] fp32 in,
+ * d_pred (nullable) the unquantised prediction `model.y.data` that the extension steps feed back (line 185/200),
+ * d_frame (nullable) what `write_image` stores (uint8 truncation of P0*255). */
+int eig_prednet_reset(eig_ctx* ctx, int n, void* stream);
+int eig_prednet_forward(eig_ctx* ctx, const float* d_x, int n, float* d_pred, uint8_t* d_frame, void* stream);
+
 /* Replaces `lucas_kanade(file1, file2)` for n image pairs (optical_flow/optical_flow.py:40-89).
  * d_img1/d_img2: [n][h][w][c_dim] uint8 (RGB order).  Outputs (all nullable except d_vectors/d_nvec):
  * d_corners [n][100][2] fp32, d_ncorners [n], d_vectors [n][100][4] fp32 rows (x, y, dx, dy), d_nvec [n]. */

@@ -56,6 +56,51 @@ def test_prednet_kernels_frames(emu_lib):
         eng.close()
 
 
+def test_stepping_api_and_test_image_list_mirror(emu_lib, tmp_path):
+    """eig_prednet_reset / eig_prednet_forward (state carried from call to call) and the `call_prednet.test_image_list`
+    mirror built on them: frames written for 3 repeats + 2 extensions, twice in a row (state reset after the extension
+    block), equal the whole-sequence kernel path; a sequence of DISTINCT frames equals the oracle stepped by hand."""
+    from PIL import Image
+    from evolutionary_illusion_generator_b200 import call_prednet as CP
+    w, h, ch = 64, 56, (1, 4, 8, 12)
+    eng = E.Engine(w, h, ch, 4, lib=emu_lib)
+    eng.set_grid(1)
+    wts = W.synthetic_weights(w, h, ch, seed=1, bias_std=0.1)
+    eng.load_weights(wts)
+    cfg = G.make_config(2, 1)
+    pop = [G.synthetic_genome("circles_bw", i) for i in range(2)]
+    img, x = eng.render([G.flatten_genome(g, cfg, n_outputs=1) for g in pop])
+    frames = eng.prednet(x, n_input_steps=3, n_ext=2).numpy()
+    paths = []
+    for i in range(2):
+        paths.append(str(tmp_path / ("in_%d.png" % i)))
+        Image.fromarray(img[i].numpy()[:, :, 0], "L").save(paths[-1])
+    out = tmp_path / "pred"
+    out.mkdir()
+    with open(tmp_path / "log.txt", "w") as logf:
+        step = CP.test_image_list(eng, [paths[0]] * 3 + [paths[1]] * 3, None, str(out), ch, [w, h], [0, 0], 0, logf,
+                                  skip_save_frames=1, extension_start=3, extension_duration=2, verbose=0, c=1)
+    assert step == 6
+    for i in range(2):      # generate_illusion.py:543-546 naming: prediction i*3+2, extensions (i*3+3)+j
+        got = [np.asarray(Image.open(out / ("%010d.png" % (i * 3 + 2))))] + \
+              [np.asarray(Image.open(out / ("%010d_extended.png" % (i * 3 + 3 + j)))) for j in range(2)]
+        for k in range(3):
+            assert np.array_equal(got[k], frames[k, i, :, :, 0]), (i, k)
+    assert len((tmp_path / "log.txt").read_text().splitlines()) == 5          # no loss line for the last frame
+    # distinct frames, no extension: against the oracle network stepped by hand
+    net = OP.PredNetOracle(wts, ch, w, h)
+    eng.prednet_reset(1)
+    for k in range(4):
+        frame_in = img[k % 2].numpy()
+        pred, u8 = eng.prednet_forward(x[k % 2:k % 2 + 1])
+        with torch.no_grad():
+            p0 = net.step(torch.from_numpy(OP.image_to_input(_squeeze(frame_in, 1)))[None])
+        want = OP.prediction_to_image(p0[0].numpy())
+        d = u8[0, :, :, 0].numpy().astype(int) - np.asarray(want).reshape(h, w).astype(int)
+        assert np.abs(d).max() <= 1 and (d != 0).mean() < 2e-3, k
+    eng.close()
+
+
 def test_flow_and_score_kernels(emu_lib):
     rng = np.random.RandomState(3)
     import cv2

@@ -552,6 +552,49 @@ def test_exported_files_vs_the_reference_itself(tmp_path):
         print("%s: best.png, best_black_bg.png, enhanced.png identical to the reference's files" % m["name"])
 
 
+def test_test_prednet_mirror_vs_the_reference_frames(gpu_engine_factory, tmp_path, monkeypatch):
+    """`call_prednet.test_prednet` of the drop-in package with the argument list `get_fitnesses_neat` uses
+    (generate_illusion.py:531-535): same file names, frames within 1 LSB of the PNGs the reference's own test_prednet wrote
+    (tests/golden/reference_pipeline.npz), state carried frame to frame and reset after every extension block."""
+    from PIL import Image
+    from evolutionary_illusion_generator_b200 import call_prednet as CP
+    monkeypatch.chdir(tmp_path)                       # test_log.txt lands in the working directory, like the reference's
+    z = np.load(os.path.join(GOLDEN, "reference_pipeline.npz"))
+    for m in json.loads(str(z["meta"])):
+        if m["name"] not in ("r_small_free", "r_small_colour_palette"):
+            continue
+        w, h, ch, c, n = m["w"], m["h"], tuple(m["channels"]), m["c_dim"], m["n"]
+        model = str(tmp_path / (m["name"] + ".npz"))
+        W.save_npz(model, W.synthetic_predictor_weights(w, h, ch, seed=m["weight_seed"]))
+        cfg = G.make_config(2, G.NEAT_PRESETS[m["preset"]]["num_outputs"])
+        pop = G.synthetic_population(m["preset"], n, evolved=m["evolved"])
+        eng = gpu_engine_factory(w, h, ch, n)
+        eng.set_grid(m["structure"])
+        img, _ = eng.render([G.flatten_genome(g, cfg, n_outputs=c if c > 1 else 1) for _, g in pop],
+                            mode=E.render_mode_for(c, m["gradient"]))
+        img = img.cpu().numpy()
+        out = tmp_path / ("pred_" + m["name"])
+        out.mkdir()
+        repeated = []
+        for i in range(n):
+            path = str(tmp_path / ("%s_%d.png" % (m["name"], i)))
+            (Image.fromarray(img[i]) if c == 3 else Image.fromarray(img[i][:, :, 0], "L")).save(path)
+            repeated += [path] * 20
+        CP.test_prednet(initmodel=model, sequence_list=[repeated], size=[w, h], channels=list(ch), gpu=0,
+                        output_dir=str(out), skip_save_frames=1, extension_start=20, extension_duration=2,
+                        reset_at=22, verbose=0, c_dim=c)
+        assert len(list(out.iterdir())) == 22 * n
+        ref = z["frames_" + m["name"]]
+        for i in range(n):
+            got = [np.asarray(Image.open(out / ("%010d.png" % (20 * i + 19)))),
+                   np.asarray(Image.open(out / ("%010d_extended.png" % (20 * i + 20))))]
+            for k in range(2):
+                d = np.abs(got[k].astype(int) - ref[i, k].astype(int))
+                assert d.max() <= 1 and (d > 0).mean() < 1e-3, (m["name"], i, k, int(d.max()), float((d > 0).mean()))
+        assert len(open("test_log.txt").read().splitlines()) == 20 * n - 1
+        print("%s: %d files, frames within 1 LSB of the reference's test_prednet output" % (m["name"], 22 * n))
+
+
 def test_single_image_rating_vs_the_reference_itself(tmp_path):
     """`fitness_calculator.get_vectors` / `calculate_fitness` of the drop-in package against what the reference's own
     functions returned for the same image and weight file (tests/golden/reference_single_image.npz)."""
