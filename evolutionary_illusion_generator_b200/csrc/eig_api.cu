@@ -153,6 +153,8 @@ extern "C" const char* eig_last_error(void) { return g_err.c_str(); }
 extern "C" int eig_version(void) { return 100; }
 extern "C" int64_t eig_launch_count(void) { return launch_counter().n; }
 
+static int create_buffers(eig_ctx* c, int w, int h, int c_dim, const int channels[4], int max_genomes);
+
 extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, const int channels[4], int max_genomes) {
     if (!out || !channels || max_genomes <= 0) return fail(EIG_E_INVALID, "eig_create: null/invalid argument");
     if (w % 8 || h % 8 || w <= 0 || h <= 0) return fail(EIG_E_INVALID, "eig_create: w and h must be positive multiples of 8");
@@ -165,7 +167,15 @@ extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, co
     if (device < 0 || device >= ndev) return fail(EIG_E_INVALID, "eig_create: bad device index");
     CK(cudaSetDevice(device));
     eig_ctx* c = new eig_ctx();
-    c->device = device; c->w = w; c->h = h; c->c_dim = c_dim; c->cap = max_genomes;
+    c->device = device;
+    const int rc = create_buffers(c, w, h, c_dim, channels, max_genomes);
+    if (rc != EIG_OK) { eig_destroy(c); return rc; }   // nothing of a half-built context survives (e.g. out of memory)
+    *out = c;
+    return EIG_OK;
+}
+
+static int create_buffers(eig_ctx* c, int w, int h, int c_dim, const int channels[4], int max_genomes) {
+    c->w = w; c->h = h; c->c_dim = c_dim; c->cap = max_genomes;
     for (int n = 0; n < 4; ++n) { c->ch[n] = channels[n]; c->H[n] = h >> n; c->W[n] = w >> n; }
     for (int n = 0; n < 4; ++n) c->ctot[n] = 2 * c->ch[n] + (n < 3 ? c->ch[n + 1] : 0) + c->ch[n];
     const size_t B = max_genomes;
@@ -225,7 +235,6 @@ extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, co
     c->overlap = false;
     c->use_graphs = false;
 #endif
-    *out = c;
     return EIG_OK;
 }
 
