@@ -78,20 +78,15 @@ def test_flattener_edge_cases():
 def test_program_cache_hits_elites_and_sees_in_place_mutation():
     """SURVEY §8 f row 4: unchanged genomes re-submitted under the same id reuse their packed program; a genome mutated
     in place is re-flattened; entries of genomes that left the population are dropped."""
-    import time
     cfg = G.make_config(2, 3)
     pop = G.synthetic_population("circles", 24, evolved=True)
     cache = G.ProgramCache(keep=2)
-    t0 = time.perf_counter()
     first = cache.flatten_population(pop, cfg, n_outputs=3)
-    t1 = time.perf_counter()
     again = cache.flatten_population(pop, cfg, n_outputs=3)
-    t2 = time.perf_counter()
     assert cache.misses == 24 and cache.hits == 24
     assert all(a is b for a, b in zip(first, again))
     direct = [G.flatten_genome(g, cfg, n_outputs=3).to_bytes() for _, g in pop]
     assert [p.to_bytes() for p in again] == direct
-    assert (t2 - t1) < (t1 - t0)                                 # a hit is cheaper than a flatten
     # in-place mutation under the same id
     gid, g = pop[3]
     next(iter(g.connections.values())).weight += 0.25
