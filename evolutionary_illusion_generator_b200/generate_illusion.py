@@ -71,10 +71,16 @@ def get_fitnesses_neat(structure, population, model_name, config, w, h, channels
         if genome.fitness >= best_score:  # generate_illusion.py:625 (NaN never wins, like the reference)
             best_score, best_i = genome.fitness, i
     print("scores", [[i, float(f)] for i, f in enumerate(fit)])
-    if export_best and population:
+    if export_best and population and _is_export_rank():
         _export_best(eng, population[best_i], config, c_dim, gradient, best_dir, structure, export_async)
     print("best", best_score, best_i)
     return None
+
+
+def _is_export_rank():
+    """One process per GPU: every rank holds the full fitness vector after the all-gather, rank 0 writes the files."""
+    import torch.distributed as dist
+    return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
 
 
 ENHANCED_SIZE = 800  # generate_illusion.py:665-666
