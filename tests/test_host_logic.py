@@ -56,6 +56,27 @@ def test_flattener_matches_oracle_on_evolved_genomes():
         assert n_const > 5  # the constant-folding rule is actually exercised
 
 
+def test_flattener_matches_oracle_on_random_topologies():
+    """Seeded random feed-forward genomes (tests/fuzz_genomes.py: disabled connections, hidden chains, product aggregation,
+    input-less and dangling nodes, connections leaving outputs, non-unit responses): the flattened program, interpreted
+    the way render.cuh does, gives the oracle's bytes - and the oracle is byte-equal to the reference on the same genomes
+    (tests/test_oracle_vs_reference.py)."""
+    from fuzz_genomes import fuzz_genome
+    w, h = 40, 32
+    n_const = 0
+    for c_dim, n_out, structure in ((1, 1, 1), (3, 3, 2), (3, 3, 1)):
+        grid = OG.create_grid(structure, w, h, 10)
+        cfg = G.make_config(2, n_out)
+        gc = cfg.genome_config
+        for seed in range(120):
+            g = fuzz_genome(seed * 7 + c_dim, n_out)
+            prog = G.flatten_genome(g, cfg, n_outputs=c_dim if c_dim > 1 else 1)
+            n_const += any(s == G.SLOT_ONE for _, s in prog.terms)
+            want = OC.render(grid, g, c_dim, w, h, gc.input_keys, gc.output_keys)
+            assert np.array_equal(render_flat(prog, grid, c_dim, w, h), want), (c_dim, structure, seed)
+    assert n_const > 100
+
+
 def test_flattener_edge_cases():
     cfg = G.make_config(2, 1)
     g = G.Genome()

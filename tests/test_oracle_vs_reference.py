@@ -48,6 +48,20 @@ def test_render_matches_reference_on_fresh_genomes(ns):
             assert np.array_equal(ref, got), (preset, i)
 
 
+def test_render_matches_reference_on_random_topologies(ns):
+    from fuzz_genomes import fuzz_genome
+    w, h = 40, 32
+    for c_dim, n_out, structure in ((1, 1, 1), (3, 3, 2), (3, 3, 1)):
+        grid = ns.gi.create_grid(ns.gi.StructureType(structure), w, h, 10)
+        cfg = G.make_config(2, n_out)
+        gc = cfg.genome_config
+        for seed in range(60):
+            g = fuzz_genome(seed * 7 + c_dim, n_out)
+            ref = np.asarray(ns.gi.get_image_from_cppn(grid, g, c_dim, w, h, cfg))
+            got = OC.render(grid, g, c_dim, w, h, gc.input_keys, gc.output_keys)
+            assert np.array_equal(ref, got.reshape(ref.shape)), (c_dim, structure, seed)
+
+
 def test_scoring_matches_reference_functions(ns):
     rng = np.random.RandomState(11)
     w, h = 160, 120
