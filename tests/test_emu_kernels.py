@@ -35,6 +35,25 @@ def test_render_kernel_bytes(emu_lib):
         eng.close()
 
 
+def test_render_kernel_on_random_topologies(emu_lib):
+    """cppn_render_kernel (host-compiled) on seeded random genome topologies (tests/fuzz_genomes.py) = the oracle's bytes."""
+    from fuzz_genomes import fuzz_genome
+    w, h = 64, 56
+    for c, n_out, structure, gradient in ((1, 1, 1, 1), (3, 3, 2, 1), (3, 3, 1, 0), (1, 1, 2, 0)):
+        eng = E.Engine(w, h, (c, 4, 8, 8), 8, lib=emu_lib)
+        eng.set_grid(structure)
+        cfg = G.make_config(2, n_out)
+        gc = cfg.genome_config
+        grid = OG.create_grid(structure, w, h, 10)
+        for base in range(0, 24, 8):
+            pop = [fuzz_genome(1000 + (base + i) * 7 + c, n_out) for i in range(8)]
+            img, _ = eng.render([G.flatten_genome(g, cfg, n_outputs=c) for g in pop], mode=E.render_mode_for(c, gradient))
+            for i, g in enumerate(pop):
+                want = OC.render(grid, g, c, w, h, gc.input_keys, gc.output_keys, gradient=gradient)
+                assert np.array_equal(_squeeze(img[i].numpy(), c), want), (c, structure, gradient, base + i)
+        eng.close()
+
+
 def test_prednet_kernels_frames(emu_lib):
     w, h = 64, 56   # layer sizes 56/28/14/7: partial tiles and an odd top layer
     for preset, ch in (("circles_bw", (1, 4, 8, 12)), ("circles", (3, 6, 8, 20))):
