@@ -163,3 +163,44 @@ def test_whole_path_matches_oracle(emu_lib):
         assert list(dbg["nvec"]) == [len(e["vectors"]) for e in ex]
         assert np.allclose(fit, ref, rtol=1e-3, atol=1e-9)
         eng.close()
+
+
+def test_raw_ctypes_binding_of_integration_md(emu_lib):
+    """The binding INTEGRATION.md section 3 shows (plain ctypes, no helper classes), run against the host-compiled library:
+    eig_create -> eig_load_weights -> eig_set_grid -> eig_eval_host, same fitness as the Engine wrapper."""
+    import ctypes as C
+    from conftest import EMU_SO
+    from evolutionary_illusion_generator_b200.grid import create_grid
+    lib = C.CDLL(EMU_SO)
+    lib.eig_last_error.restype = C.c_char_p
+    w, h, channels, n = 64, 64, (1, 4, 8, 8), 3
+    ctx = C.c_void_p()
+    ch = (C.c_int * 4)(*channels)
+    assert lib.eig_create(C.byref(ctx), 0, w, h, channels[0], ch, n) == 0, lib.eig_last_error()
+    z = W.synthetic_predictor_weights(w, h, channels, seed=3)
+    names = sorted(z)
+    arrs = [np.ascontiguousarray(z[k], np.float32) for k in names]
+    shp = np.ones((len(names), 4), np.int64)
+    for i, a in enumerate(arrs):
+        shp[i, :a.ndim] = a.shape
+    assert lib.eig_load_weights(ctx, len(names), (C.c_char_p * len(names))(*[k.encode() for k in names]),
+                                (C.c_void_p * len(names))(*[a.ctypes.data for a in arrs]),
+                                shp.ctypes.data_as(C.c_void_p)) == 0, lib.eig_last_error()
+    g = create_grid(1, w, h, 10)
+    x = np.ascontiguousarray(g["x_mat"], np.float64)
+    y = np.ascontiguousarray(g["y_mat"], np.float64)
+    assert lib.eig_set_grid(ctx, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p)) == 0
+    cfg = G.make_config(2, 1)
+    pop = [G.synthetic_genome("circles_bw", i) for i in range(n)]
+    blob, offsets, max_slots = G.pack_population([G.flatten_genome(p, cfg, n_outputs=1) for p in pop])
+    fit = np.empty(n, np.float64)
+    rc = lib.eig_eval_host(ctx, blob.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p), n, max_slots, 1, 0, 0,
+                           fit.ctypes.data_as(C.c_void_p))
+    assert rc == 0, lib.eig_last_error()
+    lib.eig_destroy(ctx)
+    eng = E.Engine(w, h, channels, n, lib=emu_lib)
+    eng.set_grid(1)
+    eng.load_weights(z)
+    want = eng.evaluate([G.flatten_genome(p, cfg, n_outputs=1) for p in pop], 1)
+    eng.close()
+    assert np.array_equal(fit, want, equal_nan=True) and np.any(fit > 0)
