@@ -37,7 +37,7 @@ def get_image_from_cppn(inputs, genome, c_dim, w, h, config, bg=1, gradient=1, e
     if eng is None:
         if channels is None:
             channels = (c_dim, 16 * c_dim, 32 * c_dim, 64 * c_dim)
-        eng = engine_mod.Engine(w, h, channels, 8)
+        eng = runtime.engine_factory(w, h, channels, 8)
     eng.set_grid(grid=inputs)
     prog = G.flatten_genome(genome, config, n_outputs=_used_outputs(c_dim))
     mode = engine_mod.render_mode_for(c_dim, gradient)
@@ -92,7 +92,7 @@ def _render_engine(w, h, c_dim, structure):
     grid planes are uploaded once per structure."""
     key = (w, h, c_dim, int(structure))
     if key not in _render_engines:
-        eng = engine_mod.Engine(w, h, (c_dim, 4, 4, 4), 1)
+        eng = runtime.engine_factory(w, h, (c_dim, 4, 4, 4), 1)
         eng.set_grid(grid=enhanced_image_grid(w, h, structure))
         _render_engines[key] = eng
     return _render_engines[key]

@@ -7,7 +7,7 @@ constants (optical_flow.py:51-60, config.yaml).
 import numpy as np
 import torch
 
-from . import engine as engine_mod
+from . import runtime
 
 _flow_engines = {}
 
@@ -15,7 +15,7 @@ _flow_engines = {}
 def _engine_for(w, h, c_dim):
     key = (w, h, c_dim)
     if key not in _flow_engines:
-        _flow_engines[key] = engine_mod.Engine(w, h, (c_dim, 16 * c_dim, 32 * c_dim, 64 * c_dim), 8)
+        _flow_engines[key] = runtime.engine_factory(w, h, (c_dim, 16 * c_dim, 32 * c_dim, 64 * c_dim), 8)
     return _flow_engines[key]
 
 

@@ -15,6 +15,7 @@ import torch.distributed as dist
 from . import _lib, engine as engine_mod, genome as G
 
 _engines = {}
+engine_factory = engine_mod.Engine   # (w, h, channels, max_genomes) -> Engine; the CPU tests bind the host-compiled library here
 
 
 def get_engine(w, h, channels, model_name, max_genomes):
@@ -24,7 +25,7 @@ def get_engine(w, h, channels, model_name, max_genomes):
     if eng is None or eng.max_genomes < max_genomes:
         if eng is not None:
             eng.close()
-        eng = engine_mod.Engine(w, h, channels, max(max_genomes, 8))
+        eng = engine_factory(w, h, channels, max(max_genomes, 8))
         eng.load_weights(model_name)
         _engines[key] = eng
     return eng

@@ -41,6 +41,17 @@ def _worker(rank, world, port, n, out_dir):
     assert cache.misses == hi - lo
     np.save(os.path.join(out_dir, "fit_streamed_%d.npy" % rank), streamed)
     np.save(os.path.join(out_dir, "shard_%d.npy" % rank), np.array([lo, hi, per]))
+    # the whole drop-in call under torch.distributed: every rank ends with the same genome.fitness, rank 0 alone writes files
+    from evolutionary_illusion_generator_b200 import generate_illusion as GI
+    emu = _lib.EigLibrary(EMU_SO)
+    runtime.engine_factory = lambda w_, h_, ch_, n_: E.Engine(w_, h_, ch_, n_, lib=emu)
+    GI.ENHANCED_SIZE = 64
+    model = os.path.join(out_dir, "model_%d.npz" % rank)
+    W.save_npz(model, W.synthetic_weights(w, h, ch, seed=2))
+    pop2 = [(i, G.synthetic_genome("circles_bw", i)) for i in range(n)]
+    GI.get_fitnesses_neat(GI.StructureType.Free, pop2, model, cfg, w, h, ch, c_dim=1,
+                          best_dir=os.path.join(out_dir, "best_%d" % rank))
+    np.save(os.path.join(out_dir, "fit_neat_%d.npy" % rank), np.array([g.fitness for _, g in pop2]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -65,6 +76,12 @@ def test_sharded_evaluation_equals_single_process(emu_lib, tmp_path):
     for chunk in (None, 2):
         one = eng.evaluate_streamed(pop, lambda gid, g: G.flatten_genome(g, cfg, n_outputs=1), 2, chunk=chunk)
         assert np.array_equal(one.numpy(), single)
+    eng.set_grid(2)                                            # get_fitnesses_neat(Free): Free grid and Free scoring
+    single_free = eng.evaluate(progs, 2)
+    assert np.array_equal(np.load(tmp_path / "fit_neat_0.npy"), single_free)
+    assert np.array_equal(np.load(tmp_path / "fit_neat_1.npy"), single_free)
+    assert sorted(os.listdir(tmp_path / "best_0")) == ["best.png", "best_black_bg.png", "best_flow.png", "enhanced.png"]
+    assert not os.path.exists(tmp_path / "best_1")
     assert list(np.load(tmp_path / "shard_0.npy")) == [0, 2, 2] and list(np.load(tmp_path / "shard_1.npy")) == [2, 3, 2]
 
 

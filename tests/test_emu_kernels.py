@@ -204,3 +204,43 @@ def test_raw_ctypes_binding_of_integration_md(emu_lib):
     want = eng.evaluate([G.flatten_genome(p, cfg, n_outputs=1) for p in pop], 1)
     eng.close()
     assert np.array_equal(fit, want, equal_nan=True) and np.any(fit > 0)
+
+
+def test_get_fitnesses_neat_on_the_host_compiled_library_vs_the_reference(emu_lib, tmp_path, monkeypatch):
+    """The drop-in `get_fitnesses_neat` with the kernel sources compiled for the host (exact-fp32 path) against what the
+    REFERENCE's own get_fitnesses_neat assigned to the same population and weight file (tests/golden/reference_pipeline.npz):
+    the CPU-side proof of the end-to-end parity the GPU tests repeat on the B200."""
+    import json
+    import os
+    from PIL import Image
+    from conftest import GOLDEN
+    from evolutionary_illusion_generator_b200 import generate_illusion as GI, runtime
+    monkeypatch.setattr(runtime, "engine_factory", lambda w, h, ch, n: E.Engine(w, h, ch, n, lib=emu_lib))
+    monkeypatch.setattr(runtime, "_engines", {})
+    monkeypatch.setattr(GI, "_render_engines", {})
+    monkeypatch.setattr(GI, "ENHANCED_SIZE", 64)            # the 800x800 mosaic is slow in the emulator
+    monkeypatch.setattr(GI, "program_cache", G.ProgramCache())
+    z = np.load(os.path.join(GOLDEN, "reference_pipeline.npz"))
+    m = [m for m in json.loads(str(z["meta"])) if m["name"] == "r_small_gray"][0]
+    w, h, ch, c = m["w"], m["h"], tuple(m["channels"]), m["c_dim"]
+    model = str(tmp_path / "model.npz")
+    W.save_npz(model, W.synthetic_predictor_weights(w, h, ch, seed=m["weight_seed"]))
+    cfg = G.make_config(2, 1)
+    pop = G.synthetic_population(m["preset"], m["n"], evolved=m["evolved"])
+    best_dir = str(tmp_path / "best")
+    GI.get_fitnesses_neat(GI.StructureType(m["structure"]), pop, model, cfg, w, h, ch, c_dim=c, best_dir=best_dir,
+                          gradient=m["gradient"])
+    got = np.array([g.fitness for _, g in pop])
+    ref = z["fitness_" + m["name"]]
+    assert all(isinstance(g.fitness, float) for _, g in pop)
+    assert np.allclose(got, ref, rtol=1e-3, atol=1e-9), (got, ref)
+    grid = OG.create_grid(m["structure"], w, h, 10)
+    gc = cfg.genome_config
+    want = OC.render(grid, pop[int(np.argmax(ref))][1], c, w, h, gc.input_keys, gc.output_keys)
+    assert np.array_equal(np.asarray(Image.open(os.path.join(best_dir, "best.png"))), want)
+    assert sorted(os.listdir(best_dir)) == ["best.png", "best_black_bg.png", "best_flow.png", "enhanced.png"]
+    GI.get_fitnesses_neat(GI.StructureType(m["structure"]), pop, model, cfg, w, h, ch, c_dim=c, best_dir=best_dir,
+                          gradient=m["gradient"], export_best=False)
+    assert GI.program_cache.hits >= m["n"] and np.array_equal(got, np.array([g.fitness for _, g in pop]))
+    for eng in list(runtime._engines.values()) + list(GI._render_engines.values()):
+        eng.close()
