@@ -244,3 +244,30 @@ def test_get_fitnesses_neat_on_the_host_compiled_library_vs_the_reference(emu_li
     assert GI.program_cache.hits >= m["n"] and np.array_equal(got, np.array([g.fitness for _, g in pop]))
     for eng in list(runtime._engines.values()) + list(GI._render_engines.values()):
         eng.close()
+
+
+def test_single_image_rating_on_the_host_compiled_library_vs_the_reference(emu_lib, tmp_path, monkeypatch):
+    """`fitness_calculator.get_vectors` / `calculate_fitness` of the drop-in package, kernels compiled for the host, against
+    what the reference's own two functions returned for the same image and weights (reference_single_image.npz)."""
+    import json
+    import os
+    from PIL import Image
+    from conftest import GOLDEN
+    from evolutionary_illusion_generator_b200 import fitness_calculator as FC, generate_illusion as GI, runtime
+    monkeypatch.setattr(runtime, "engine_factory", lambda w, h, ch, n: E.Engine(w, h, ch, n, lib=emu_lib))
+    monkeypatch.setattr(runtime, "_engines", {})
+    z = np.load(os.path.join(GOLDEN, "reference_single_image.npz"))
+    m = json.loads(str(z["meta"]))[0]
+    w, h, ch = m["w"], m["h"], tuple(m["channels"])
+    model = str(tmp_path / "model.npz")
+    W.save_npz(model, W.synthetic_predictor_weights(w, h, ch, seed=m["weight_seed"]))
+    path = str(tmp_path / "image.png")
+    Image.fromarray(z["images_" + m["name"]][0], "L").save(path)
+    vec = FC.get_vectors(path, model, ch, w, h)
+    n = int(z["nvec_" + m["name"]][0])
+    assert len(vec) == n and np.allclose(np.asarray(vec).reshape(-1, 4), z["vectors_" + m["name"]][0, :n], atol=2e-3)
+    for k, st in enumerate((GI.StructureType.Circles, GI.StructureType.Free)):
+        assert np.isclose(FC.calculate_fitness(st, vec, path, w, h), z["scores_" + m["name"]][0, k], rtol=1e-3)
+    assert FC.calculate_fitness(GI.StructureType.Circles, [None], path, w, h) == 0.0
+    for eng in runtime._engines.values():
+        eng.close()
