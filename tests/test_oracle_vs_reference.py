@@ -115,3 +115,29 @@ def test_reference_get_fitnesses_neat_runs_and_reproduces_the_fixture(ns, tmp_pa
     assert np.array_equal(fit, z["fitness_" + case[0]], equal_nan=True)
     assert np.array_equal(frames, z["frames_" + case[0]])
     assert json.loads(str(z["meta"]))[0]["name"] == case[0]
+
+
+def test_lucas_kanade_mirror_vs_the_reference_function(ns, emu_lib, tmp_path, monkeypatch):
+    """`optical_flow.lucas_kanade` of the drop-in package (kernels compiled for the host) against the reference's own
+    function on the reference's sample pair optical_flow/penguin{1,2}.png and on an evolved 160x120 image pair."""
+    import os
+    import ref_harness
+    from evolutionary_illusion_generator_b200 import engine as E, optical_flow as OFL, runtime
+    monkeypatch.setattr(runtime, "engine_factory", lambda w, h, ch, n: E.Engine(w, h, ch, n, lib=emu_lib))
+    monkeypatch.setattr(OFL, "_flow_engines", {})
+    ref_dir = os.path.join(ref_harness.REF, "optical_flow")
+    pairs = [(os.path.join(ref_dir, "penguin1.png"), os.path.join(ref_dir, "penguin2.png"))]
+    small = os.path.join(ref_harness.REF, "illusions_rating", "EIGEN-images")
+    imgs = sorted(os.path.join(r, f) for r, _, fs in os.walk(small) for f in fs if f == "small.png")
+    if len(imgs) >= 2:
+        pairs.append((imgs[0], imgs[1]))
+    for f1, f2 in pairs:
+        want = ns.of.lucas_kanade(f1, f2, str(tmp_path / "ref"), save=False, verbose=0)["vectors"]
+        got = OFL.lucas_kanade(f1, f2, output_path=str(tmp_path / "mine"), save=True, verbose=0)
+        assert len(got["vectors"]) == len(want), (f1, len(got["vectors"]), len(want))
+        if want:
+            assert np.allclose(np.asarray(got["vectors"], np.float32), np.asarray(want, np.float32), atol=2e-3), f1
+        stem = os.path.splitext(os.path.basename(f1))[0]
+        assert os.path.isfile(tmp_path / "mine" / (stem + ".png")) and os.path.isfile(tmp_path / "mine" / "csv" / (stem + ".csv"))
+    for eng in OFL._flow_engines.values():
+        eng.close()
