@@ -141,3 +141,26 @@ def test_lucas_kanade_mirror_vs_the_reference_function(ns, emu_lib, tmp_path, mo
         assert os.path.isfile(tmp_path / "mine" / (stem + ".png")) and os.path.isfile(tmp_path / "mine" / "csv" / (stem + ".csv"))
     for eng in OFL._flow_engines.values():
         eng.close()
+
+
+def test_get_image_from_cppn_mirror_vs_the_reference_function(ns, emu_lib):
+    """`generate_illusion.get_image_from_cppn` of the drop-in package (render kernel compiled for the host) returns the very
+    PIL image the reference's function returns: every structure it can render, gray / colour, with and without gradient,
+    white and black background, on synthetic and fuzzed genomes."""
+    from fuzz_genomes import fuzz_genome
+    from evolutionary_illusion_generator_b200 import engine as E, generate_illusion as GI
+    w, h = 64, 56
+    for c_dim, n_out, preset in ((1, 1, "circles_bw"), (3, 3, "circles")):
+        eng = E.Engine(w, h, (c_dim, 4, 8, 8), 8, lib=emu_lib)
+        cfg = G.make_config(2, n_out)
+        genomes = [G.synthetic_genome(preset, i, evolved=bool(i % 2)) for i in range(4)] + \
+                  [fuzz_genome(500 + i, n_out) for i in range(4)]
+        for structure in (ns.gi.StructureType.Circles, ns.gi.StructureType.Free, ns.gi.StructureType.CirclesFree):
+            grid = ns.gi.create_grid(structure, w, h, 10)
+            for k, g in enumerate(genomes):
+                gradient, bg = k % 2, (k // 2) % 2
+                ref = ns.gi.get_image_from_cppn(grid, g, c_dim, w, h, cfg, bg=bg, gradient=gradient)
+                got = GI.get_image_from_cppn(grid, g, c_dim, w, h, cfg, bg=bg, gradient=gradient, engine=eng)
+                assert got.mode == ref.mode and got.size == ref.size
+                assert np.array_equal(np.asarray(got), np.asarray(ref)), (c_dim, int(structure), k)
+        eng.close()
