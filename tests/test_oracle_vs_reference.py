@@ -164,3 +164,46 @@ def test_get_image_from_cppn_mirror_vs_the_reference_function(ns, emu_lib):
                 assert got.mode == ref.mode and got.size == ref.size
                 assert np.array_equal(np.asarray(got), np.asarray(ref)), (c_dim, int(structure), k)
         eng.close()
+
+
+def test_test_prednet_mirror_vs_the_reference_on_distinct_frames(ns, emu_lib, tmp_path, monkeypatch):
+    """A sequence of DISTINCT frames with an extension block in the middle, through the reference's own `test_prednet`
+    (Chainer stand-in) and through the drop-in `call_prednet.test_prednet` (kernels compiled for the host): same file
+    names, every frame within 1 LSB, same number of loss lines."""
+    import os
+    from PIL import Image
+    from evolutionary_illusion_generator_b200 import call_prednet as CP, engine as E, runtime, weights as W
+    monkeypatch.setattr(runtime, "engine_factory", lambda w, h, ch, n: E.Engine(w, h, ch, n, lib=emu_lib))
+    monkeypatch.setattr(runtime, "_engines", {})
+    monkeypatch.chdir(tmp_path)
+    w, h, ch = 64, 64, (1, 4, 8, 8)
+    model = str(tmp_path / "model.npz")
+    W.save_npz(model, W.synthetic_predictor_weights(w, h, ch, seed=3))
+    cfg = G.make_config(2, 1)
+    grid = OG.create_grid(1, w, h, 10)
+    gc = cfg.genome_config
+    paths = []
+    for i in range(4):
+        img = OC.render(grid, G.synthetic_genome("circles_bw", i), 1, w, h, gc.input_keys, gc.output_keys)
+        paths.append(str(tmp_path / ("frame_%d.png" % i)))
+        Image.fromarray(img, "L").save(paths[-1])
+    sequence = [paths[0], paths[1], paths[2], paths[3], paths[1], paths[0]]      # extension after frame 3, then two more
+    kw = dict(size=[w, h], channels=list(ch), skip_save_frames=1, extension_start=3, extension_duration=2, reset_at=5,
+              verbose=0, c_dim=1)
+    os.makedirs("ref_out")
+    os.makedirs("my_out")
+    ns.call_prednet.test_prednet(initmodel=model, sequence_list=[sequence], gpu=-1, output_dir="ref_out", **kw)
+    ref_log = open("test_log.txt").read().splitlines()
+    CP.test_prednet(initmodel=model, sequence_list=[sequence], gpu=0, output_dir="my_out", **kw)
+    my_log = open("test_log.txt").read().splitlines()
+    assert sorted(os.listdir("my_out")) == sorted(os.listdir("ref_out")) and len(os.listdir("ref_out")) == 6 + 2 * 2
+    for name in os.listdir("ref_out"):
+        a = np.asarray(Image.open(os.path.join("ref_out", name))).astype(int)
+        b = np.asarray(Image.open(os.path.join("my_out", name))).astype(int)
+        assert np.abs(a - b).max() <= 1 and (a != b).mean() < 2e-3, name
+    assert len(my_log) == len(ref_log) == 5
+    for mine, ref in zip(my_log, ref_log):
+        assert mine.split(",")[0] == ref.split(",")[0]
+        assert np.isclose(float(mine.split(",")[1]), float(ref.split(",")[1]), rtol=1e-3, atol=1e-7)
+    for eng in runtime._engines.values():
+        eng.close()
