@@ -23,9 +23,11 @@ def get_engine(w, h, channels, model_name, max_genomes):
     key = (w, h, tuple(channels), model_name if isinstance(model_name, str) else id(model_name))
     eng = _engines.get(key)
     if eng is None or eng.max_genomes < max_genomes:
-        if eng is not None:
+        grow = 0
+        if eng is not None:      # NEAT populations drift in size: grow geometrically instead of once per extra genome
+            grow = eng.max_genomes + eng.max_genomes // 2
             eng.close()
-        eng = engine_factory(w, h, channels, max(max_genomes, 8))
+        eng = engine_factory(w, h, channels, max(max_genomes, 8, grow))
         eng.load_weights(model_name)
         _engines[key] = eng
     return eng

@@ -148,6 +148,31 @@ def test_shard_bounds_cover_population_in_order():
             assert got == list(range(n))
 
 
+def test_engine_cache_grows_geometrically(monkeypatch):
+    made = []
+
+    class FakeEngine:
+        def __init__(self, w, h, channels, max_genomes):
+            self.max_genomes, self.closed = max_genomes, False
+            made.append(self)
+
+        def load_weights(self, weights):
+            self.weights = weights
+
+        def close(self):
+            self.closed = True
+
+    monkeypatch.setattr(runtime, "engine_factory", FakeEngine)
+    monkeypatch.setattr(runtime, "_engines", {})
+    a = runtime.get_engine(64, 64, (1, 4, 8, 8), "m.npz", 5)
+    assert a.max_genomes == 8 and runtime.get_engine(64, 64, (1, 4, 8, 8), "m.npz", 8) is a
+    b = runtime.get_engine(64, 64, (1, 4, 8, 8), "m.npz", 9)          # outgrown by one genome: 1.5x, not +1
+    assert b is not a and a.closed and b.max_genomes == 12 and b.weights == "m.npz"
+    assert runtime.get_engine(64, 64, (1, 4, 8, 8), "m.npz", 12) is b
+    assert runtime.get_engine(64, 64, (1, 4, 8, 8), "m.npz", 40).max_genomes == 40
+    assert runtime.get_engine(64, 64, (1, 4, 8, 8), "other.npz", 3) is not made[2] and len(made) == 4
+
+
 def test_libeig_exports_every_symbol_of_the_header():
     header = open(os.path.join(ROOT, "include", "eig.h")).read()
     declared = set(re.findall(r"\b(eig_[a-z0-9_]+)\s*\(", header))
