@@ -184,6 +184,7 @@ REFERENCE_CASES = [
     ("r_small_gray_round", "circles_bw", 1, (1, 4, 8, 8), 64, 64, 1, 0, 4, False, 3),
     ("r_c2", "circles_bw", 1, (1, 16, 32, 64), 160, 120, 1, 1, 8, False, 0),
     ("r_c3", "circles", 3, (3, 48, 96, 192), 160, 120, 1, 1, 4, False, 0),
+    ("r_320x240", "circles", 3, (3, 48, 96, 192), 320, 240, 1, 1, 2, False, 0),      # three LK pyramid levels
 ]
 
 
