@@ -18,6 +18,8 @@ PAIR_POPULATION, PAIR_SINGLE_IMAGE = 0, 1
 _P, _I, _D = C.c_void_p, C.c_int, C.c_double
 SYMBOLS = [
     ("eig_last_error", C.c_char_p, []),
+    ("eig_error", C.c_char_p, [_P]),
+    ("eig_set_option", _I, [_P, C.c_char_p, _I]),
     ("eig_version", _I, []),
     ("eig_launch_count", C.c_int64, []),
     ("eig_create", _I, [C.POINTER(_P), _I, _I, _I, _I, C.POINTER(_I), _I]),

@@ -63,6 +63,7 @@ struct TcParams {
     int SA, SB;
     int tmem_cols;
     int ksteps;                   // k-steps of the last K block (see TcWeights); all other blocks have 2
+    int passes;                   // MMA products per k-step, bit 0: a_lo*w_hi, bit 1: a_hi*w_lo, bit 2: a_hi*w_hi (7 = all three, the default)
     int egroups;                  // epilogue column groups: 2 (warps 8-15) or 3 (+ warps 0-3, for wide accumulators)
     int staging_bytes, stage_ld;  // ConvA pooling tile: 128 rows x stage_ld floats
     float inv_scale;              // 1 / (activation scale * weight scale), exact power of two
@@ -459,7 +460,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                                     const uint32_t d = d0 + (uint32_t)t * (uint32_t)tile_cols;
                                     const uint64_t dah0 = desc_hi | at16, dah1 = desc_hi | (at16 + 2);
                                     const uint64_t dal0 = desc_hi | (at16 + plane_a16), dal1 = desc_hi | (at16 + plane_a16 + 2);
-                                    {   // a_hi is fetched once per k-step: kept by the first MMA that uses it, re-used by the second
+                                    if (p.passes == 7) {   // a_hi is fetched once per k-step: kept by the first MMA that uses it, re-used by the second
                                         tc_mma_f16_pair<0>(d, dal0, desc_hi | bh0, idesc, acc0);
                                         tc_mma_f16_pair<1>(d, dah0, desc_hi | bl0, idesc, 1u);
                                         tc_mma_f16_pair<3>(d, dah0, desc_hi | bh0, idesc, 1u);
@@ -467,6 +468,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                                             tc_mma_f16_pair<0>(d, dal1, desc_hi | bh1, idesc, 1u);
                                             tc_mma_f16_pair<1>(d, dah1, desc_hi | bl1, idesc, 1u);
                                             tc_mma_f16_pair<3>(d, dah1, desc_hi | bh1, idesc, 1u);
+                                        }
+                                    } else {               // reduced-precision variants (TcParams::passes): any non-empty subset of the three products
+                                        uint32_t acc = acc0;
+                                        if (p.passes & 1) { tc_mma_f16_pair<0>(d, dal0, desc_hi | bh0, idesc, acc); acc = 1u; }
+                                        if (p.passes & 2) { tc_mma_f16_pair<0>(d, dah0, desc_hi | bl0, idesc, acc); acc = 1u; }
+                                        if (p.passes & 4) { tc_mma_f16_pair<0>(d, dah0, desc_hi | bh0, idesc, acc); acc = 1u; }
+                                        if (two_ksteps) {
+                                            if (p.passes & 1) tc_mma_f16_pair<0>(d, dal1, desc_hi | bh1, idesc, 1u);
+                                            if (p.passes & 2) tc_mma_f16_pair<0>(d, dah1, desc_hi | bl1, idesc, 1u);
+                                            if (p.passes & 4) tc_mma_f16_pair<0>(d, dah1, desc_hi | bh1, idesc, 1u);
                                         }
                                     }
                                 }
@@ -731,6 +742,9 @@ typedef CUresult (*EigEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// activation tensor maps, keyed by (base pointer, geometry); one cache per context so that eig_destroy drops them
+typedef std::map<std::tuple<const void*, int, int, int, int, int, int, int>, CUtensorMap> TcMapCache;
+
 struct TcState {
     EigEncodeTiledFn encode = nullptr;
     bool probed = false, available = false;
@@ -741,7 +755,7 @@ struct TcState {
     int n_sm = 148, max_pairs = 0;
     bool pdl = true;   // EIG_TC_PDL=0 disables programmatic dependent launch
     std::map<int, bool> smem_attr_set;   // cudaFuncSetAttribute is per device
-    std::map<std::tuple<const void*, int, int, int, int, int, int, int>, CUtensorMap> amaps;
+    TcMapCache amaps;   // only for callers without a context (tests/gpu/tc_check)
 };
 inline TcState& tc_state() { static TcState s; return s; }
 
@@ -900,8 +914,9 @@ inline bool tc_geometry(int B, int H, int W, int Ncta, int gz, bool pooled, int 
 // the TMA maps need 16-byte aligned fp16 channel offsets and pixel pitches; other views stay on the SIMT kernel
 inline bool tc_view_ok(const ConvArgs& a) { return a.in_lo && !(a.in_coff & 7) && !(a.in_pitch & 7); }
 
-inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
+inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream, int passes = 7, TcMapCache* cache = nullptr) {
     TcState& s = tc_state();
+    TcMapCache& amaps = cache ? *cache : s.amaps;
     if (!tc_available()) { s.last_error = s.reason; return -1; }
     if (!w.ok) { s.last_error = "tc_conv: weights not packed"; return -1; }
     if (!a.in_lo) { s.last_error = "tc_conv: the input view must be in split-fp16 storage (in_lo = lo plane)"; return -1; }
@@ -943,8 +958,8 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     for (int pl = 0; pl < 2; ++pl) {
         const h16* base = reinterpret_cast<const h16*>(pl ? a.in_lo : a.in_hi) + a.in_coff;
         auto key = std::make_tuple((const void*)base, a.Cin, a.W, a.H, a.B, a.in_pitch, g.P, box_rows);
-        auto it = s.amaps.find(key);
-        if (it == s.amaps.end()) {
+        auto it = amaps.find(key);
+        if (it == amaps.end()) {
             CUtensorMap map;
             const cuuint64_t gdim[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
             const cuuint64_t gstr[3] = {(cuuint64_t)a.in_pitch * 2, (cuuint64_t)a.W * a.in_pitch * 2, (cuuint64_t)a.H * a.W * a.in_pitch * 2};
@@ -954,7 +969,7 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { s.last_error = "tc_conv: cuTensorMapEncodeTiled(A) failed (" + std::to_string((int)r) + ")"; return -1; }
-            it = s.amaps.emplace(key, map).first;
+            it = amaps.emplace(key, map).first;
         }
         amap[pl] = &it->second;
     }
@@ -967,6 +982,7 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream) {
     p.SA = g.SA; p.SB = g.SB; p.tmem_cols = g.tmem_cols;
     p.egroups = (w.Ncta >= 96 || (pooled && w.Ncta >= 48)) ? 3 : 2;
     p.ksteps = w.ksteps;
+    p.passes = (passes & 7) ? (passes & 7) : 7;
     p.staging_bytes = g.staging; p.stage_ld = g.stage_ld;
     p.inv_scale = 1.0f / (EIG_ACT_SCALE * w.wscale);
     p.ca = a;

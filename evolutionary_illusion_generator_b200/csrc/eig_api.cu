@@ -24,9 +24,29 @@
 using namespace eig;
 #define TO_STREAM(p) ((cudaStream_t)(intptr_t)(p))
 
-static std::string g_err;
+// Optional per-kernel-class device timing (bench.py's roofline pass): every launch is bracketed by a pair of
+// CUDA events on the launching stream; eig_profile_end sums them per class.
+enum { CLS_RENDER = 0, CLS_CONV_SIMT = 1, CLS_CONV_TC = 2, CLS_ELEMENTWISE = 3, CLS_FLOW = 4, CLS_SCORE = 5, CLS_L0 = 6, CLS_COUNT = 8 };
+struct Profiler {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> cls;
+};
+
+// Error text and launch instrumentation belong to the context an entry point was called with: every extern "C" function
+// that takes a context opens a Scope, and fail() / the launch macros reach the context through it.  g_err keeps the
+// most recent message of the calling thread for eig_last_error() (failures before a context exists: eig_create).
+struct CtxCommon { std::string err; Profiler prof; };
+static thread_local std::string g_err;
+static thread_local CtxCommon* g_cur = nullptr;
+struct Scope {
+    CtxCommon* prev;
+    explicit Scope(CtxCommon* c) : prev(g_cur) { g_cur = c; }
+    ~Scope() { g_cur = prev; }
+};
 static int fail(int code, const std::string& msg) {
     g_err = msg;
+    if (g_cur) g_cur->err = msg;
     return code;
 }
 #define CK(expr)                                                                                      \
@@ -41,25 +61,18 @@ static int fail(int code, const std::string& msg) {
         if (e_ != cudaSuccess) return fail(EIG_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
     } while (0)
 
-// Optional per-kernel-class device timing (bench.py's roofline pass): every launch is bracketed by a pair of
-// CUDA events on the launching stream; eig_profile_end sums them per class.
-enum { CLS_RENDER = 0, CLS_CONV_SIMT = 1, CLS_CONV_TC = 2, CLS_ELEMENTWISE = 3, CLS_FLOW = 4, CLS_SCORE = 5, CLS_L0 = 6, CLS_COUNT = 8 };
-struct Profiler {
-    bool on = false;
-    std::vector<cudaEvent_t> ev;
-    std::vector<int> cls;
-};
-static Profiler g_prof;
+static bool prof_on() { return g_cur && g_cur->prof.on; }
 static void prof_pre(int cls, cudaStream_t s) {
-    if (!g_prof.on) return;
+    if (!prof_on()) return;
+    Profiler& pr = g_cur->prof;
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, s);
-    g_prof.ev.push_back(a); g_prof.ev.push_back(b); g_prof.cls.push_back(cls);
+    pr.ev.push_back(a); pr.ev.push_back(b); pr.cls.push_back(cls);
 }
 static void prof_post(cudaStream_t s) {
-    if (!g_prof.on) return;
-    cudaEventRecord(g_prof.ev.back(), s);
+    if (!prof_on()) return;
+    cudaEventRecord(g_cur->prof.ev.back(), s);
 }
 #define LAUNCH_K(cls, kernel, grid, block, smem, s, ...)              \
     do {                                                              \
@@ -87,7 +100,7 @@ struct LayerW {            // repacked weights of one PredNet layer (device)
 #endif
 };
 
-struct eig_ctx {
+struct eig_ctx : CtxCommon {
     int device = 0, w = 0, h = 0, c_dim = 0, ch[4] = {0, 0, 0, 0}, cap = 0;
     int H[4], W[4], ctot[4];
     int conv_mode = EIG_CONV_SIMT;
@@ -130,8 +143,22 @@ struct eig_ctx {
     struct GraphEntry { int seen = 0; long long launches = 0; void* exec = nullptr; };
     std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
     bool use_graphs = true;
+    // tensor-core numerics: MMA products per k-step for each convolution (kind 0 ConvA, 1 ConvP, 2 ConvLSTM) x layer, as a
+    // 3-bit mask (conv_tc.cuh TcParams::passes; 7 = a_lo*w_hi + a_hi*w_lo + a_hi*w_hi).  Steps t < early_until use
+    // (mask & early_mask) instead.  Set through eig_set_option; the defaults are what the parity tests pin.
+    int passes[3][4] = {{7, 7, 7, 7}, {7, 7, 7, 7}, {7, 7, 7, 7}};
+    int early_until = 0, early_mask = 7;
+#ifndef EIG_EMU
+    TcMapCache amaps;   // activation tensor maps of this context's buffers
+#endif
     std::vector<void*> allocs;
 };
+enum { KIND_A = 0, KIND_P = 1, KIND_L = 2 };
+static int passes_for(const eig_ctx* c, int kind, int layer, int t) {
+    int m = c->passes[kind][layer];
+    if (t < c->early_until && (m & c->early_mask)) m &= c->early_mask;
+    return m;
+}
 
 template <class T>
 static cudaError_t dalloc(eig_ctx* c, T** p, size_t count) {
@@ -150,6 +177,7 @@ static void drop_graphs(eig_ctx* c) {
 }
 
 extern "C" const char* eig_last_error(void) { return g_err.c_str(); }
+extern "C" const char* eig_error(const eig_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
 extern "C" int eig_version(void) { return 100; }
 extern "C" int64_t eig_launch_count(void) { return launch_counter().n; }
 
@@ -167,9 +195,10 @@ extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, co
     if (device < 0 || device >= ndev) return fail(EIG_E_INVALID, "eig_create: bad device index");
     CK(cudaSetDevice(device));
     eig_ctx* c = new eig_ctx();
+    Scope sc(c);
     c->device = device;
     const int rc = create_buffers(c, w, h, c_dim, channels, max_genomes);
-    if (rc != EIG_OK) { eig_destroy(c); return rc; }   // nothing of a half-built context survives (e.g. out of memory)
+    if (rc != EIG_OK) { g_cur = sc.prev; eig_destroy(c); return rc; }   // nothing of a half-built context survives (e.g. out of memory)
     *out = c;
     return EIG_OK;
 }
@@ -251,6 +280,7 @@ extern "C" void eig_destroy(eig_ctx* c) {
     if (c->side) cudaStreamDestroy(c->side);
     if (c->stream) cudaStreamDestroy(c->stream);
 #endif
+    for (cudaEvent_t e : c->prof.ev) cudaEventDestroy(e);
     for (void* p : c->allocs) cudaFree(p);
     if (c->d_blob) cudaFree(c->d_blob);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -258,6 +288,7 @@ extern "C" void eig_destroy(eig_ctx* c) {
 }
 
 extern "C" int eig_set_conv_mode(eig_ctx* c, int mode) {
+    Scope sc(c);
     if (!c) return fail(EIG_E_INVALID, "null ctx");
     if (mode != EIG_CONV_SIMT && mode != EIG_CONV_TC) return fail(EIG_E_INVALID, "unknown conv mode");
 #ifdef EIG_EMU
@@ -269,7 +300,32 @@ extern "C" int eig_set_conv_mode(eig_ctx* c, int mode) {
     return EIG_OK;
 }
 
+extern "C" int eig_set_option(eig_ctx* c, const char* key, int value) {
+    if (!c || !key) return fail(EIG_E_INVALID, "eig_set_option: null argument");
+    Scope sc(c);
+    const std::string k = key;
+    bool ok = false;
+    if (k == "early_until") { c->early_until = value; ok = true; }
+    else if (k == "early_mask") { if (!(value & 7)) return fail(EIG_E_INVALID, "eig_set_option: empty pass mask"); c->early_mask = value & 7; ok = true; }
+    else if (k == "graphs") { c->use_graphs = value != 0; ok = true; }
+    else if (k == "overlap") { c->overlap = value != 0; ok = true; }
+    else if (k.compare(0, 7, "passes.") == 0) {
+        if (!(value & 7)) return fail(EIG_E_INVALID, "eig_set_option: empty pass mask");
+        const std::string t = k.substr(7);
+        const char kinds[3] = {'A', 'P', 'L'};
+        for (int kd = 0; kd < 3; ++kd)
+            for (int n = 1; n < 4; ++n)
+                if (t == "all" || (t.size() == 1 && t[0] == kinds[kd]) || (t.size() == 2 && t[0] == kinds[kd] && t[1] == '0' + n)) { c->passes[kd][n] = value & 7; ok = true; }
+    }
+    if (!ok) return fail(EIG_E_INVALID, "eig_set_option: unknown key " + k);
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    drop_graphs(c);   // captured graphs bake the launch parameters in
+    return EIG_OK;
+}
+
 extern "C" int eig_set_grid(eig_ctx* c, const double* hx, const double* hy) {
+    Scope sc(c);
     if (!c || !hx || !hy) return fail(EIG_E_INVALID, "eig_set_grid: null argument");
     CK(cudaSetDevice(c->device));
     CK(cudaMemcpy(c->xmat, hx, sizeof(double) * c->w * c->h, cudaMemcpyHostToDevice));
@@ -339,6 +395,7 @@ void build_z_weights(std::vector<float>& dst, int npad, int C1, const std::vecto
 }  // namespace
 
 extern "C" int eig_load_weights(eig_ctx* c, int nt, const char* const* names, const float* const* ptrs, const int64_t* shapes) {
+    Scope sc(c);
     if (!c || !names || !ptrs || !shapes || nt <= 0) return fail(EIG_E_INVALID, "eig_load_weights: null argument");
     CK(cudaSetDevice(c->device));
     CK(cudaDeviceSynchronize());   // no evaluation may still be reading the old weights
@@ -491,7 +548,7 @@ static L0Args l0_args(eig_ctx* c, const float* x, int B, int cur, int nxt) {
 static int prednet_step(eig_ctx* c, const float* x, int B, int t, bool last, cudaStream_t s) {
     const int cur = t & 1, nxt = cur ^ 1;
     const bool tc = c->conv_mode == EIG_CONV_TC;
-    const bool side_ok = c->overlap && !g_prof.on;   // the per-class profiler times launches on one stream
+    const bool side_ok = c->overlap && !prof_on();   // the per-class profiler times launches on one stream
     int rc;
     const L0Args l0 = l0_args(c, x, B, cur, nxt);
     const int l0_tiles = ((c->w + L0_TW - 1) / L0_TW) * ((c->h + L0_TH - 1) / L0_TH);
@@ -509,7 +566,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, bool last, cud
         a.wgt = nullptr; a.bias = c->lw[1].convA_b; a.N = c->ch[1]; a.Npad = (c->ch[1] + 3) & ~3;
         a.epi = EPI_CONVA; a.P = c->P[1];
         a.dstE = mkview(c->X[1][cur], lo_plane(c, 1, c->X[1][cur]), c->ctot[1], 0, 2 * c->ch[1]);
-        prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[1].tcA, a, s); prof_post(s); EIG_COUNT_LAUNCH();
+        prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[1].tcA, a, s, passes_for(c, KIND_A, 1, t), &c->amaps); prof_post(s); EIG_COUNT_LAUNCH();
         if (rc) return fail(EIG_E_CUDA, "tc_conv ConvA1: " + tc_last_error());
     } else
 #endif
@@ -547,7 +604,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, bool last, cud
         a.epi = EPI_CONVA; a.P = c->P[n];
         a.dstE = mkview(c->X[n][cur], lo_plane(c, n, c->X[n][cur]), c->ctot[n], 0, 2 * c->ch[n]);
 #ifndef EIG_EMU
-        if (tc && c->lw[n].tcA.ok && tc_view_ok(a)) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcA, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvA: " + tc_last_error()); continue; }
+        if (tc && c->lw[n].tcA.ok && tc_view_ok(a)) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcA, a, s, passes_for(c, KIND_A, n, t), &c->amaps); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvA: " + tc_last_error()); continue; }
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }
@@ -563,7 +620,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, bool last, cud
         a.epi = EPI_CONVP; a.outP = c->P[n]; a.clip = 0;
         if (n == 1) { a.nP = c->ch[1]; a.outZ = c->Z; }
 #ifndef EIG_EMU
-        if (tc && c->lw[n].tcP.ok && tc_view_ok(a)) { prof_pre(CLS_CONV_TC, s); const int r2 = tc_conv(c->lw[n].tcP, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (r2) return fail(EIG_E_CUDA, "tc_conv ConvP: " + tc_last_error()); return EIG_OK; }
+        if (tc && c->lw[n].tcP.ok && tc_view_ok(a)) { prof_pre(CLS_CONV_TC, s); const int r2 = tc_conv(c->lw[n].tcP, a, s, passes_for(c, KIND_P, n, t), &c->amaps); prof_post(s); EIG_COUNT_LAUNCH(); if (r2) return fail(EIG_E_CUDA, "tc_conv ConvP: " + tc_last_error()); return EIG_OK; }
 #endif
         return launch_conv(c, a, s);
     };
@@ -580,7 +637,7 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, bool last, cud
         // R_n up-sampled x2 into the concat buffer of layer n-1 (layer 0 gets R_1 through Z instead)
         if (n >= 2) a.dstUp = mkview(c->X[n - 1][cur], lo_plane(c, n - 1, c->X[n - 1][cur]), c->ctot[n - 1], 2 * c->ch[n - 1], c->ch[n]);
 #ifndef EIG_EMU
-        if (tc && c->lw[n].tcL.ok && tc_view_ok(a)) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); }
+        if (tc && c->lw[n].tcL.ok && tc_view_ok(a)) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s, passes_for(c, KIND_L, n, t), &c->amaps); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); }
         else
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
@@ -687,6 +744,7 @@ static int check_ready(eig_ctx* c, int n, bool need_w, bool need_grid) {
 
 extern "C" int eig_cppn_render(eig_ctx* c, const void* d_blob, const int64_t* d_offsets, int n, int max_slots,
                                int max_blob_bytes, int mode, double bg, uint8_t* d_img, float* d_x, void* stream) {
+    Scope sc(c);
     int rc;
     if ((rc = check_ready(c, n, false, true))) return rc;
     if (!d_blob || !d_offsets || !d_img) return fail(EIG_E_INVALID, "eig_cppn_render: null pointer");
@@ -709,6 +767,7 @@ extern "C" int eig_cppn_render(eig_ctx* c, const void* d_blob, const int64_t* d_
 }
 
 extern "C" int eig_prednet_run(eig_ctx* c, const float* d_x, int n, int n_in, int n_ext, uint8_t* d_frames, void* stream) {
+    Scope sc(c);
     int rc;
     if ((rc = check_ready(c, n, true, false))) return rc;
     if (!d_x || !d_frames || n_in < 1 || n_ext < 0) return fail(EIG_E_INVALID, "eig_prednet_run: bad argument");
@@ -718,6 +777,7 @@ extern "C" int eig_prednet_run(eig_ctx* c, const float* d_x, int n, int n_in, in
 
 // stateful single steps: sequences of distinct frames, every prediction readable (test_image_list, call_prednet.py:129-205)
 extern "C" int eig_prednet_reset(eig_ctx* c, int n, void* stream) {
+    Scope sc(c);
     int rc;
     if ((rc = check_ready(c, n, true, false))) return rc;
     CK(cudaSetDevice(c->device));
@@ -729,6 +789,7 @@ extern "C" int eig_prednet_reset(eig_ctx* c, int n, void* stream) {
 }
 
 extern "C" int eig_prednet_forward(eig_ctx* c, const float* d_x, int n, float* d_pred, uint8_t* d_frame, void* stream) {
+    Scope sc(c);
     int rc;
     if ((rc = check_ready(c, n, true, false))) return rc;
     if (!d_x) return fail(EIG_E_INVALID, "eig_prednet_forward: null input");
@@ -791,6 +852,7 @@ static int flow_from_gray(eig_ctx* c, int B, cudaStream_t s) {
 
 extern "C" int eig_flow(eig_ctx* c, const uint8_t* d_img1, const uint8_t* d_img2, int n, float* d_corners, int* d_ncorners,
                         float* d_vectors, int* d_nvec, void* stream) {
+    Scope sc(c);
     int rc;
     if ((rc = check_ready(c, n, false, false))) return rc;
     if (!d_img1 || !d_img2 || !d_vectors || !d_nvec) return fail(EIG_E_INVALID, "eig_flow: null pointer");
@@ -818,6 +880,7 @@ static int score_launch(eig_ctx* c, const float* vec, const int* nvec, int n, in
 }
 
 extern "C" int eig_score(eig_ctx* c, const float* d_vectors, const int* d_nvec, int n, int structure, double* d_fitness, void* stream) {
+    Scope sc(c);
     int rc;
     if ((rc = check_ready(c, n, false, false))) return rc;
     if (!d_vectors || !d_nvec || !d_fitness) return fail(EIG_E_INVALID, "eig_score: null pointer");
@@ -854,6 +917,7 @@ static int copy_fitness(eig_ctx* c, int n, double* d_fitness, cudaStream_t s) {
 
 extern "C" int eig_eval(eig_ctx* c, const void* d_blob, const int64_t* d_offsets, int n, int max_slots, int max_blob_bytes,
                         int structure, int render_mode, int pair_mode, double* d_fitness, void* stream) {
+    Scope sc(c);
     int rc;
     if ((rc = check_ready(c, n, true, true))) return rc;
     if (!d_fitness) return fail(EIG_E_INVALID, "eig_eval: null fitness pointer");
@@ -862,7 +926,7 @@ extern "C" int eig_eval(eig_ctx* c, const void* d_blob, const int64_t* d_offsets
     cudaStream_t s = TO_STREAM(stream);
     if ((rc = eig_cppn_render(c, d_blob, d_offsets, n, max_slots, max_blob_bytes, render_mode, 1.0, c->img, c->x_in, stream))) return rc;
 #ifndef EIG_EMU
-    if (c->use_graphs && !g_prof.on) {
+    if (c->use_graphs && !prof_on()) {
         auto key = std::make_tuple(n, structure, pair_mode, c->conv_mode);
         eig_ctx::GraphEntry& ge = c->graphs[key];
         if (ge.exec) {
@@ -888,7 +952,8 @@ extern "C" int eig_eval(eig_ctx* c, const void* d_blob, const int64_t* d_offsets
                 cudaGetLastError();
                 launch_counter().n = before;
             }
-            c->use_graphs = false;   // capture is not possible here (e.g. the caller's stream is already capturing): run directly
+            cudaGetLastError();      // a refused capture (legacy stream, caller already capturing) must not surface as a launch error below
+            c->use_graphs = false;   // capture is not possible here: run directly
         }
     }
 #endif
@@ -897,6 +962,7 @@ extern "C" int eig_eval(eig_ctx* c, const void* d_blob, const int64_t* d_offsets
 }
 
 extern "C" int eig_range_check(eig_ctx* c, void* stream) {
+    Scope sc(c);
     if (!c) return fail(EIG_E_INVALID, "null ctx");
     CK(cudaSetDevice(c->device));
     cudaStream_t s = TO_STREAM(stream);
@@ -912,6 +978,7 @@ extern "C" int eig_range_check(eig_ctx* c, void* stream) {
 
 extern "C" int eig_eval_host(eig_ctx* c, const void* h_blob, const int64_t* h_offsets, int n, int max_slots, int structure,
                              int render_mode, int pair_mode, double* h_fitness) {
+    Scope sc(c);
     int rc;
     if ((rc = check_ready(c, n, true, true))) return rc;
     if (!h_blob || !h_offsets || !h_fitness) return fail(EIG_E_INVALID, "eig_eval_host: null pointer");
@@ -937,6 +1004,7 @@ extern "C" int eig_eval_host(eig_ctx* c, const void* h_blob, const int64_t* h_of
 
 extern "C" int eig_debug_buffers(eig_ctx* c, uint8_t** d_img, uint8_t** d_frames, float** d_vectors, int** d_nvec,
                                  float** d_corners, int** d_ncorners) {
+    Scope sc(c);
     if (!c) return fail(EIG_E_INVALID, "null ctx");
     if (d_img) *d_img = c->img;
     if (d_frames) *d_frames = c->frames;
@@ -955,24 +1023,29 @@ extern "C" int eig_memcpy_d2h(void* h_dst, const void* d_src, int64_t bytes) {
 
 extern "C" int eig_profile_begin(eig_ctx* c) {
     if (!c) return fail(EIG_E_INVALID, "null ctx");
-    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
-    g_prof.ev.clear(); g_prof.cls.clear();
-    g_prof.on = true;
+    Scope sc(c);
+    Profiler& pr = c->prof;
+    for (cudaEvent_t e : pr.ev) cudaEventDestroy(e);
+    pr.ev.clear(); pr.cls.clear();
+    pr.on = true;
     return EIG_OK;
 }
 
 extern "C" int eig_profile_end(eig_ctx* c, double* ms_per_class, int64_t* launches_per_class) {
     if (!c || !ms_per_class || !launches_per_class) return fail(EIG_E_INVALID, "eig_profile_end: null pointer");
-    g_prof.on = false;
+    Scope sc(c);
+    Profiler& pr = c->prof;
+    pr.on = false;
+    CK(cudaSetDevice(c->device));
     CK(cudaDeviceSynchronize());
     for (int i = 0; i < CLS_COUNT; ++i) { ms_per_class[i] = 0.0; launches_per_class[i] = 0; }
-    for (size_t i = 0; i < g_prof.cls.size(); ++i) {
+    for (size_t i = 0; i < pr.cls.size(); ++i) {
         float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
-        ms_per_class[g_prof.cls[i]] += ms;
-        launches_per_class[g_prof.cls[i]] += 1;
+        CK(cudaEventElapsedTime(&ms, pr.ev[2 * i], pr.ev[2 * i + 1]));
+        ms_per_class[pr.cls[i]] += ms;
+        launches_per_class[pr.cls[i]] += 1;
     }
-    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
-    g_prof.ev.clear(); g_prof.cls.clear();
+    for (cudaEvent_t e : pr.ev) cudaEventDestroy(e);
+    pr.ev.clear(); pr.cls.clear();
     return EIG_OK;
 }

@@ -77,6 +77,10 @@ class Engine:
     def set_conv_mode(self, mode):
         self.lib.check(self.lib.eig_set_conv_mode(self.ctx, int(mode)))
 
+    def set_option(self, key, value):
+        """Tuning / diagnostic knob of the library (include/eig.h: eig_set_option)."""
+        self.lib.check(self.lib.eig_set_option(self.ctx, key.encode(), int(value)))
+
     def load_weights(self, weights):
         """weights: path to a Chainer npz (`serializers.save_npz` layout) or a dict name -> ndarray."""
         if isinstance(weights, str):

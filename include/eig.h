@@ -37,7 +37,10 @@ enum { EIG_PAIR_POPULATION = 0, EIG_PAIR_SINGLE_IMAGE = 1 };
 /* convolution engine for PredNet layers 1..3: exact-fp32 SIMT kernels, or tcgen05 tensor cores (CTA pairs, 3-pass split fp16 with fp32 accumulation) */
 enum { EIG_CONV_SIMT = 0, EIG_CONV_TC = 1 };
 
+/* message of the most recent failure on the calling thread (any context; also failures of eig_create) */
 const char* eig_last_error(void);
+/* message of the most recent failure of THIS context (two contexts in one process do not overwrite each other) */
+const char* eig_error(const eig_ctx* ctx);
 int eig_version(void);
 /* number of CUDA kernels this library has launched so far (bench.py's `gpu_launches`) */
 int64_t eig_launch_count(void);
@@ -49,6 +52,15 @@ void eig_destroy(eig_ctx* ctx);
 
 /* conv_mode: EIG_CONV_SIMT / EIG_CONV_TC.  Returns EIG_E_INVALID if the mode is not compiled in. */
 int eig_set_conv_mode(eig_ctx* ctx, int conv_mode);
+
+/* Tuning / diagnostic knobs (no reference counterpart).  Keys:
+ *   "passes.all" | "passes.A" | "passes.P" | "passes.L" | "passes.<A|P|L><1..3>" : which of the three split-fp16 MMA products
+ *        a convolution issues per k-step (bit 0 a_lo*w_hi, bit 1 a_hi*w_lo, bit 2 a_hi*w_hi; default 7 = all, the setting
+ *        the parity tests pin; profiles/r2/pass_ablation.md has the measured cost of every cheaper mix);
+ *   "early_until" = T, "early_mask" = m : PredNet steps t < T use (mask & m);
+ *   "graphs" 0/1 : CUDA-graph replay of everything after the render; "overlap" 0/1 : ConvP2/3 on the side stream.
+ * Synchronises the device and drops captured graphs. */
+int eig_set_option(eig_ctx* ctx, const char* key, int value);
 
 /* Replaces `serializers.load_npz(initmodel, model)` (call_prednet.py:231).  names[i] use the Chainer npz keys
  * ("predictor/ConvLSTM2/x_i0/W", ...); host_ptrs[i] is contiguous fp32; shapes is n_tensors x 4 (unused
