@@ -1,16 +1,27 @@
 #!/usr/bin/env python
-"""bench.py - genome fitness evaluations per second on N B200s (BASELINE.json metric).  `--workload c4|c5`: the per-GPU shares of the 320x240 / 512x512 configs (not 160x120; informational).
+"""bench.py - genome fitness evaluations per second on N B200s (BASELINE.json metric).
 
-One "step" = one pass of the hot path (CPPN render -> PredNet 20+1 steps -> Shi-Tomasi/LK flow -> score) over
-one synthetic population shard per GPU.  Default workload = BASELINE.json configs[1] ("c2": pop 32,
-neat_configs/circles_bw.txt, 160x120 gray, PredNet channels 1,16,32,64); `--workload c3` is configs[2]
-(circles.txt colour, 3,48,96,192).  Weak scaling: every GPU owns `pop` genomes, the fitness slices are
-all-gathered (NCCL) inside every step.
+One "step" = one pass of the hot path (CPPN render -> PredNet 20+1 steps -> Shi-Tomasi/LK flow -> score) over one
+synthetic population shard per GPU, with one all-gather (NCCL) of the fitness slices inside every step when N > 1.
 
-  value : evals/s with the flattened genomes already resident in HBM; device time from CUDA events per step
-          (L2 flushed between steps, untimed), max over ranks.
-  e2e   : the same through the host entry point `eig_eval_host` (what get_fitnesses_neat calls): pinned host
-          genome blob -> H2D -> kernels -> D2H fitness, wall clock with a device sync, max over ranks.
+The contract line is BASELINE.json configs[2] ("c3": pop 128, neat_configs/circles.txt colour, 160x120, PredNet
+channels 3,48,96,192 = the reference's `--channels` default, /root/reference/generate_illusion.py:734) - the config the
+metric's "1/2/4/8 B200" sweep is quoted on - weak scaling with 128 genomes per GPU.  The same JSON line carries, under
+"also", one sub-record per further configuration, each measured the same way on the same box:
+  c2           BASELINE configs[1]: pop 32 gray 160x120 (channels 1,16,32,64), per GPU
+  c3_strong    configs[2] split over the ranks (pop 128 / N per GPU); N > 1 only
+  c4, c5       configs[3] (pop 256, bands, 320x240) and configs[4] (pop 1024, free, 512x512) - their "8xB200" shape,
+               i.e. pop / 8 genomes per GPU; measured when N = 8 (or with --also c4,c5)
+
+  value    : evals/s with the flattened genomes already resident in HBM; CUDA events per step on the launching stream
+             (L2 flushed between steps, untimed), max over ranks.
+  e2e      : the same through the host entry point `eig_eval_host` (pinned host genome blob -> H2D -> kernels -> D2H
+             fitness), wall clock with a device sync, max over ranks.  `e2e_from_genomes` (rank 0, N = 1) starts one
+             level higher, at the genome objects `get_fitnesses_neat` receives (flatten + pack + eig_eval_host).
+  parity   : BEFORE anything is timed, the first k genomes of rank 0's shard are evaluated by the CPU oracle and
+             compared with the GPU fitness (1e-3 relative, the `north_star` tolerance).  A failing gate aborts the run.
+  gathered_check : N > 1: rank 0 re-evaluates the WHOLE global population on its own GPU and compares the all-gathered
+             vector bit for bit.
   roofline : per-kernel-class CUDA-event times of an instrumented pass of the same step (eig_profile_*).
   cpu_baseline : the oracle (port of the reference's path; Chainer is not installable) on a bounded sample.
 
@@ -37,14 +48,16 @@ WORKLOADS = {
     "c4": ("bands", 3, (3, 48, 96, 192), 320, 240, 0, 32, 335421),
     "c5": ("free", 3, (3, 48, 96, 192), 512, 512, 2, 128, 335421),
 }
+BASELINE_CONFIG = {"c2": "configs[1]", "c3": "configs[2]", "c4": "configs[3] (pop 256 / 8 GPUs)", "c5": "configs[4] (pop 1024 / 8 GPUs)"}
 STRUCTURE_NAMES = {0: "Bands", 1: "Circles", 2: "Free", 3: "CirclesFree"}
+MIN_TIMED_S = 1.0   # every point is timed for at least this long (steps are raised internally for the short workloads)
 
 
 def tc_kernel_macs(ch):
     """Algorithmic MACs per layer-0 pixel per PredNet step that the tcgen05 kernel covers (SURVEY.md §8 a-7 counts):
     everything except ConvA1, ConvP0 and the E0/h0 taps of ConvLSTM0, which run on the layer-0 SIMT kernels.
-    ConvLSTM0's up-sampled-R1 taps are counted at their reference cost 9*C1*4*C0 (the kernel evaluates them folded to
-    half resolution)."""
+    The up-sampled-R taps of every ConvLSTM are counted at their reference cost (9 taps at full resolution), however the
+    kernel evaluates them (folded to half resolution)."""
     c0, c1, c2, c3 = ch
     total = 0.0
     total += 9 * 2 * c1 * c2 / 4.0 + 9 * 2 * c2 * c3 / 16.0                      # ConvA2, ConvA3
@@ -60,6 +73,8 @@ def tc_kernel_macs(ch):
 def tc_dead_macs(ch):
     """ConvP2 / ConvP3 of the final step feed nothing (no next step): not launched, not counted."""
     return 9 * ch[2] * ch[2] / 16.0 + 9 * ch[3] * ch[3] / 64.0
+
+
 USEFUL_STEPS = 21  # 20 static frames + 1 self-fed (the reference's 22nd forward is never read)
 METRIC = "NEAT genome fitness evals/sec (CPPN+PredNet+flow) @160x120"
 
@@ -104,18 +119,18 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
                 for nme, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def build_population(preset, c_dim, n, start):
@@ -127,20 +142,50 @@ def build_population(preset, c_dim, n, start):
     return cfg, pop, progs
 
 
-def oracle_evals_per_s(workload, n_sample, threads, flow_impl="cv2"):
-    """The reference's CPU path (oracle port) on `n_sample` genomes of the workload."""
-    import torch
+_weights_cache = {}
+
+
+def workload_weights(workload):
     from evolutionary_illusion_generator_b200 import weights as W
+    preset, c_dim, ch, w, h = WORKLOADS[workload][:5]
+    key = (w, h, ch)
+    if key not in _weights_cache:
+        _weights_cache.clear()          # one set at a time: the 512x512 peephole maps are large
+        _weights_cache[key] = W.synthetic_predictor_weights(w, h, ch, seed=0)
+    return _weights_cache[key]
+
+
+def oracle_fitness(workload, genomes_from, n, threads, flow_impl="cv2"):
+    """The reference's CPU path (oracle port) on `n` genomes of the workload -> (fitness vector, seconds)."""
+    import torch
     from oracle import pipeline as OPL
     preset, c_dim, ch, w, h, structure, _, _ = WORKLOADS[workload]
     torch.set_num_threads(threads)
-    wts = W.synthetic_predictor_weights(w, h, ch, seed=0)
-    cfg, pop, _ = build_population(preset, c_dim, n_sample, 0)
+    wts = workload_weights(workload)
+    cfg, pop, _ = build_population(preset, c_dim, n, genomes_from)
     gc = cfg.genome_config
     t0 = time.perf_counter()
-    OPL.evaluate_population(pop, gc.input_keys, gc.output_keys, structure, wts, w, h, ch, c_dim, flow_impl=flow_impl)
-    dt = time.perf_counter() - t0
+    fit = OPL.evaluate_population(pop, gc.input_keys, gc.output_keys, structure, wts, w, h, ch, c_dim, flow_impl=flow_impl)
+    return np.asarray(fit, dtype=np.float64), time.perf_counter() - t0
+
+
+def oracle_evals_per_s(workload, n_sample, threads, flow_impl="cv2"):
+    _, dt = oracle_fitness(workload, 0, n_sample, threads, flow_impl)
     return n_sample / dt, dt
+
+
+def default_ref_sample(workload):
+    return {"c2": 8, "c3": 2, "c4": 1, "c5": 1}[workload]
+
+
+def workload_config(workload, pop, world, scaling, conv):
+    preset, c_dim, ch, w, h, structure, _, _ = WORKLOADS[workload]
+    return {"workload": workload, "baseline_config": BASELINE_CONFIG[workload], "pop_per_gpu": pop, "global_pop": world * pop,
+            "resolution": "%dx%d" % (w, h), "channels": list(ch), "neat_config": preset,
+            "structure": STRUCTURE_NAMES[structure], "prednet_steps": USEFUL_STEPS, "conv": conv,
+            "weights": "synthetic_predictor_weights seed 0 (LeCun-normal, layer 0 shaped as an error integrator)",
+            "l2": "flushed between steps (256 MiB memset, untimed)",
+            "parallelism": "genome-sharded dp%d + 1 all-gather/step" % world, "scaling": scaling}
 
 
 def run_reference(args):
@@ -149,54 +194,71 @@ def run_reference(args):
         return
     preset, c_dim, ch, w, h, structure, pop, _ = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    n_sample = args.ref_sample
-    for _ in range(max(args.warmup, 1) if args.warmup < 2 else 1):
-        oracle_evals_per_s(args.workload, 1, cores)
-    vals, secs = [], 0.0
+    n_sample = args.ref_sample or default_ref_sample(args.workload)
+    oracle_evals_per_s(args.workload, 1, cores)          # warm-up (thread pools, grids)
+    secs = 0.0
     for _ in range(args.steps):
-        v, dt = oracle_evals_per_s(args.workload, n_sample, cores)
-        vals.append(v); secs += dt
+        _, dt = oracle_evals_per_s(args.workload, n_sample, cores)
+        secs += dt
     value = args.steps * n_sample / secs
-    sample = ("%d genomes per step of workload %s (render + 22 PredNet forwards + cv2 LK + scoring, in memory), "
+    sample = ("%d genomes per step of workload %s (render + 22 PredNet forwards + cv2 LK + scoring, in memory; genomes are "
+              "evaluated one after the other exactly as the reference does, so evals/s does not depend on the sample size), "
               "torch-CPU fp32 oracle port of the Chainer path, %d threads" % (n_sample, args.workload, cores))
+    cfg = workload_config(args.workload, pop, args.gpus, "weak", "cpu")
+    cfg["sample_genomes_per_step"] = n_sample
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": args.workload, "pop_per_step": n_sample, "resolution": "%dx%d" % (w, h),
-                       "channels": list(ch), "neat_config": preset},
+            "config": cfg,
             "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def run_ours(args):
+class Dist:
+    def __init__(self):
+        import torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def close(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+def measure(D, workload, pop, steps, warmup, scaling, conv, flush, main, parity_k, cpu_sample, from_genomes):
+    """One configuration, measured on every rank; rank 0 returns the record (other ranks None)."""
+    import ctypes as C
     import torch
     import torch.distributed as dist
-    from evolutionary_illusion_generator_b200 import _lib, engine as E, genome as G, weights as W
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    preset, c_dim, ch, w, h, structure, pop, macs = WORKLOADS[args.workload]
-    if args.pop:
-        pop = args.pop
-    if args.scaling == "strong":   # SURVEY.md §8 d sweep (i): the workload's population split over the ranks
-        pop = -(-pop // world)
-    dev = torch.device("cuda", local)
-    eng = E.Engine(w, h, ch, pop, device=local)
-    eng.set_conv_mode(_lib.CONV_TC if args.conv == "tc" else _lib.CONV_SIMT)
+    from evolutionary_illusion_generator_b200 import _lib, engine as E, genome as G
+    preset, c_dim, ch, w, h, structure, _, macs = WORKLOADS[workload]
+    rank, world, dev = D.rank, D.world, D.dev
+    eng = E.Engine(w, h, ch, pop, device=D.local)
+    eng.set_conv_mode(_lib.CONV_TC if conv == "tc" else _lib.CONV_SIMT)
     eng.set_grid(structure)
-    eng.load_weights(W.synthetic_predictor_weights(w, h, ch, seed=0))
-    _, _, progs = build_population(preset, c_dim, pop, rank * pop)
+    eng.load_weights(workload_weights(workload))
+    cfg, genomes, progs = build_population(preset, c_dim, pop, rank * pop)
     blob, offsets, max_slots = G.pack_population(progs)
     resident = eng.upload_programs(progs)
     fit_dev = torch.empty((pop,), dtype=torch.float64, device=dev)
     gathered = torch.empty((world * pop,), dtype=torch.float64, device=dev)
-    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)   # > 126 MB L2
     pin_blob = torch.from_numpy(blob).pin_memory()
     pin_off = torch.from_numpy(offsets).pin_memory()
     pin_fit = torch.empty((pop,), dtype=torch.float64).pin_memory()
@@ -214,47 +276,99 @@ def run_ours(args):
             dist.all_gather_into_tensor(gathered, fit_dev)
             torch.cuda.synchronize()
 
-    def barrier():
+    # ---- parity gate, before anything is timed (rank 0)
+    parity = None
+    if parity_k > 0:
+        ok = True
+        if rank == 0:
+            k = min(parity_k, pop)
+            eng.evaluate_resident(resident, structure, out=fit_dev)
+            torch.cuda.synchronize()
+            got = fit_dev[:k].cpu().numpy()
+            want, dt = oracle_fitness(workload, 0, k, os.cpu_count() or 1)
+            rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-9)
+            within = int(np.sum((rel <= 1e-3) | (np.abs(got - want) <= 1e-9)))
+            parity = {"checked": k, "within_1e-3": within, "ok": within == k, "max_rel_err": float(rel.max()),
+                      "against": "CPU oracle (oracle/pipeline.py, torch-CPU fp32 PredNet port + cv2 LK), same genomes and weights, %.1f s" % dt,
+                      "nonzero": int((want > 0).sum())}
+            ok = within == k
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.broadcast(flag, 0)
+            ok = bool(flag.item())
+        if not ok and main:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "parity gate failed before timing", "parity": parity,
+                                  "config": workload_config(workload, pop, world, scaling, conv)}))
+            eng.close()
+            D.close()
+            sys.exit(1)
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step_resident()
         flush.zero_()
-    barrier()
-    sampler = ClockSampler(local)
+    D.barrier()
+    # raise the step count so that the timed region lasts >= MIN_TIMED_S (the contract line keeps the driver's K)
+    if not main:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step_resident(); b.record(); torch.cuda.synchronize()
+        est = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(est, op=dist.ReduceOp.MAX)
+        steps = max(steps, int(np.ceil(1e3 * MIN_TIMED_S / max(float(est[0]), 1e-3))))
+    sampler = ClockSampler(D.local)
     if rank == 0:
         sampler.start()
     launches0 = eng.lib.eig_launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    D.barrier()
     for a, b in ev:
         a.record()
         step_resident()
         b.record()
         flush.zero_()          # L2 flush between timed steps (not inside any event pair)
-    barrier()
+    D.barrier()
     launches = eng.lib.eig_launch_count() - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     # end-to-end through the host entry point
+    e2e_steps = steps
     for _ in range(2):
         step_host()
-    barrier()
+    D.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         step_host()
-    barrier()
+    D.barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     tmax = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(tmax[0]), float(tmax[1])
+    step_resident()
+    torch.cuda.synchronize()
     fit_host = fit_dev.cpu().numpy()
 
-    # instrumented pass: per-kernel-class device time of the same step (rank 0 reports)
-    import ctypes as C
+    # ---- N > 1: the gathered vector against a single-GPU evaluation of the same global population (rank 0)
+    gathered_check = None
+    if world > 1:
+        all_host = gathered.cpu().numpy()
+        if rank == 0:
+            single = np.empty_like(all_host)
+            for r in range(world):
+                _, _, pr = build_population(preset, c_dim, pop, r * pop)
+                single[r * pop:(r + 1) * pop] = eng.evaluate(pr, structure)
+            same = np.array_equal(single, all_host, equal_nan=True)
+            gathered_check = {"genomes": int(all_host.size), "bit_equal_to_single_gpu": bool(same),
+                              "max_abs_diff": float(np.nanmax(np.abs(single - all_host))) if not same else 0.0}
+        D.barrier()
+
+    # ---- genome objects -> fitness (what get_fitnesses_neat does per generation), rank 0, N = 1
+    e2e_genomes = None
+    if from_genomes and rank == 0 and world == 1:
+        e2e_genomes = time_from_genomes(eng, genomes, cfg, c_dim, structure, steps)
+
+    # ---- instrumented pass: per-kernel-class device time of the same step (rank 0 reports)
     ms = (C.c_double * 8)()
     cnt = (C.c_int64 * 8)()
     prof_steps = 2
@@ -265,76 +379,148 @@ def run_ours(args):
     cls_names = ["render", "conv_simt", "conv_tcgen05", "elementwise", "flow", "score", "layer0_fused"]
     cls_ms = {cls_names[i]: ms[i] / prof_steps for i in range(7)}
     cls_n = {cls_names[i]: int(cnt[i] // prof_steps) for i in range(7)}
-
-    if rank == 0:
-        peaks = measured_peaks()
-        total = world * pop * args.steps
-        value = total / (dev_ms / 1e3)
-        e2e = total / (e2e_ms / 1e3)
-        flop_step = 2.0 * (tc_kernel_macs(ch) * USEFUL_STEPS - tc_dead_macs(ch)) * w * h * pop   # algorithmic FLOP of the tcgen05 launches, one GPU
-        conv_ms = cls_ms["conv_simt"] + cls_ms["conv_tcgen05"]
-        conv_n = cls_n["conv_simt"] + cls_n["conv_tcgen05"]
-        achieved = flop_step / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1", "tc_traffic.json")
-        if args.conv == "tc" and os.path.isfile(tpath) and not args.pop:
-            traffic = json.load(open(tpath)).get(args.workload, {}).get("mean_dram_bytes_per_launch")
-        roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (%s)" % ("tcgen05 cta_group::2, 3-pass split fp16" if args.conv == "tc" else "fp32 SIMT"),
-                    "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": achieved / peaks["tf"],
-                    "traffic": traffic, "traffic_source": "ncu --set full, profiles/r1/tc_traffic.json (mean over the 8 launch shapes of one PredNet step)" if traffic else None,
-                    "peak_source": peaks["source"] + " bf16 dense (sustained)",
-                    "flop_per_launch": flop_step / max(conv_n, 1), "launches_per_step": conv_n,
-                    "avg_launch_us": 1e3 * conv_ms / max(conv_n, 1),
-                    "mma_passes": 3 if args.conv == "tc" else None,
-                    "frac_of_3pass_ceiling": 3.0 * achieved / peaks["tf"] if args.conv == "tc" else None,
-                    "class_ms_per_step": cls_ms, "class_launches_per_step": cls_n,
-                    "whole_path_gflop_per_genome": 2.0 * macs * w * h * USEFUL_STEPS / 1e9,
-                    "timing": "per-launch CUDA events of an instrumented pass of the same step (library launch instrumentation; "
-                              "graph replay, side-stream overlap and programmatic dependent launch are off in that pass, "
-                              "so the class times are upper bounds of their share of ms_per_step)",
-                    "note": "achieved counts each algorithmic MAC once; fp32-grade accuracy needs 3 fp16 MMAs per MAC "
-                            "(hi*hi + hi*lo + lo*hi), so 1/3 of the dense 16-bit peak is the ceiling of this kernel"}
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            n_s = args.ref_sample
-            oracle_evals_per_s(args.workload, 1, cores)
-            v, dt = oracle_evals_per_s(args.workload, n_s, cores)
-            cpu = {"value": v, "unit": "evals/s", "cores": cores, "kind": "port",
-                   "sample": "%d genomes of workload %s through the oracle (torch-CPU fp32 PredNet port, cv2 LK), "
-                             "%.1f s" % (n_s, args.workload, dt)}
-        line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-                "scaling": args.scaling, "vs_baseline": None, "dtype": "fp32 (3-pass split-fp16 tcgen05, fp32 accumulate)" if args.conv == "tc" else "fp32",
-                "data": "synthetic",
-                "config": {"workload": args.workload, "pop_per_gpu": pop, "global_pop": world * pop,
-                           "resolution": "%dx%d" % (w, h), "channels": list(ch), "neat_config": preset,
-                           "structure": STRUCTURE_NAMES[structure], "prednet_steps": USEFUL_STEPS, "conv": args.conv,
-                           "weights": "synthetic_predictor_weights seed 0 (LeCun-normal, layer 0 shaped as an error integrator)", "l2": "flushed between steps (256 MiB memset, untimed)",
-                           "parallelism": "genome-sharded dp%d + 1 all-gather/step" % world},
-                "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": int(blob.nbytes + offsets.nbytes),
-                        "d2h_bytes_per_step": int(8 * pop), "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-                "fitness_checksum": float(np.nansum(fit_host)), "nonzero_fitness_frac": float((fit_host > 0).mean())}
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     eng.close()
+    if rank != 0:
+        return None
+
+    peaks = measured_peaks()
+    total = world * pop * steps
+    value = total / (dev_ms / 1e3)
+    e2e = world * pop * e2e_steps / (e2e_ms / 1e3)
+    flop_step = 2.0 * (tc_kernel_macs(ch) * USEFUL_STEPS - tc_dead_macs(ch)) * w * h * pop   # algorithmic FLOP of the tcgen05 launches, one GPU
+    conv_ms = cls_ms["conv_simt"] + cls_ms["conv_tcgen05"]
+    conv_n = cls_n["conv_simt"] + cls_n["conv_tcgen05"]
+    achieved = flop_step / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    traffic, tsrc = None, None
+    for rel in ("profiles/r2/tc_traffic.json", "profiles/r1/tc_traffic.json"):
+        tpath = os.path.join(ROOT, rel)
+        if conv == "tc" and os.path.isfile(tpath) and pop == WORKLOADS[workload][6]:
+            t = json.load(open(tpath)).get(workload, {}).get("mean_dram_bytes_per_launch")
+            if t:
+                traffic, tsrc = t, "ncu --set full, %s (mean over the conv launches of one PredNet step)" % rel
+                break
+    roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (%s)" % ("tcgen05 cta_group::2, 3-pass split fp16" if conv == "tc" else "fp32 SIMT"),
+                "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": achieved / peaks["tf"],
+                "traffic": traffic, "traffic_source": tsrc,
+                "peak_source": peaks["source"] + " bf16 dense (sustained)",
+                "flop_per_launch": flop_step / max(conv_n, 1), "launches_per_step": conv_n,
+                "avg_launch_us": 1e3 * conv_ms / max(conv_n, 1),
+                "mma_passes": 3 if conv == "tc" else None,
+                "frac_of_3pass_ceiling": 3.0 * achieved / peaks["tf"] if conv == "tc" else None,
+                "class_ms_per_step": cls_ms, "class_launches_per_step": cls_n,
+                "whole_path_gflop_per_genome": 2.0 * macs * w * h * USEFUL_STEPS / 1e9,
+                "whole_path_tflops": 2.0 * macs * w * h * USEFUL_STEPS * world * pop * steps / (dev_ms / 1e3) / 1e12,
+                "timing": "per-launch CUDA events of an instrumented pass of the same step (library launch instrumentation; "
+                          "graph replay, side-stream overlap and programmatic dependent launch are off in that pass, "
+                          "so the class times are upper bounds of their share of ms_per_step)",
+                "note": "achieved counts each algorithmic MAC once (up-sampled taps at their reference cost); fp32-grade accuracy "
+                        "needs 3 fp16 MMAs per MAC (hi*hi + hi*lo + lo*hi), so 1/3 of the dense 16-bit peak is the ceiling of this kernel"}
+    cpu = None
+    if cpu_sample > 0 and world == 1:
+        cores = os.cpu_count() or 1
+        oracle_evals_per_s(workload, 1, cores)
+        v, dt = oracle_evals_per_s(workload, cpu_sample, cores)
+        cpu = {"value": v, "unit": "evals/s", "cores": cores, "kind": "port",
+               "sample": "%d genomes of workload %s through the oracle (torch-CPU fp32 PredNet port, cv2 LK), "
+                         "%.1f s" % (cpu_sample, workload, dt)}
+    rec = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": steps,
+           "warmup": max(warmup, 3), "ms_per_step": dev_ms / steps, "higher_is_better": True,
+           "scaling": scaling, "vs_baseline": None,
+           "dtype": "fp32 (3-pass split-fp16 tcgen05, fp32 accumulate)" if conv == "tc" else "fp32",
+           "data": "synthetic", "config": workload_config(workload, pop, world, scaling, conv),
+           "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": int(blob.nbytes + offsets.nbytes),
+                   "d2h_bytes_per_step": int(8 * pop), "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
+           "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "roofline": roofline, "cpu_baseline": cpu,
+           "fitness_checksum": float(np.nansum(fit_host)), "nonzero_fitness_frac": float((fit_host > 0).mean())}
+    if gathered_check is not None:
+        rec["gathered_check"] = gathered_check
+    if e2e_genomes is not None:
+        rec["e2e_from_genomes"] = e2e_genomes
+    return rec
+
+
+def time_from_genomes(eng, genomes, cfg, c_dim, structure, steps):
+    """Wall clock from genome OBJECTS to the host fitness vector (flatten + pack + H2D + kernels + D2H), the level at which
+    `get_fitnesses_neat` is called: cold = every genome flattened, warm = every genome a program-cache hit."""
+    import torch
+    from evolutionary_illusion_generator_b200 import genome as G, runtime
+    n_out = c_dim if c_dim > 1 else 1
+    items = list(enumerate(genomes))
+    out = {}
+    for mode in ("cold", "warm"):
+        cache = G.ProgramCache()
+
+        def flatten(gid, g):
+            return cache.get(gid, g, cfg, n_out)
+
+        def once():
+            if mode == "cold":
+                cache._entries.clear()
+            return runtime.evaluate_genomes(eng, items, flatten, structure)
+
+        once(); once()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            once()
+        dt = time.perf_counter() - t0
+        out[mode] = {"value": len(items) * steps / dt, "unit": "evals/s", "ms_per_step": 1e3 * dt / steps}
+    out["path"] = "runtime.evaluate_genomes: genome objects -> flatten (program cache) -> pack -> pinned H2D -> eig_eval -> D2H"
+    return out
+
+
+def run_ours(args):
+    import torch
+    D = Dist()
+    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=D.dev)   # > 126 MB L2
+    wl = args.workload
+    pop = args.pop or WORKLOADS[wl][6]
+    scaling = args.scaling
+    if scaling == "strong":   # SURVEY.md §8 d sweep (i): the workload's population split over the ranks
+        pop = -(-pop // D.world)
+    main = measure(D, wl, pop, args.steps, args.warmup, scaling, args.conv, flush, True, args.parity,
+                   0 if args.no_cpu_baseline else (args.ref_sample or default_ref_sample(wl) * 4), True)
+    also = []
+    wanted = [a for a in args.also.split(",") if a] if args.also != "auto" else None
+    if wanted is None:
+        wanted = []
+        if wl == "c3" and scaling == "weak" and not args.pop:
+            wanted.append("c2")
+            if D.world > 1:
+                wanted.append("c3_strong")
+            if D.world == 8:
+                wanted += ["c4", "c5"]
+    for name in wanted:
+        if name == "c3_strong":
+            rec = measure(D, "c3", -(-WORKLOADS["c3"][6] // D.world), args.steps, args.warmup, "strong", args.conv, flush,
+                          False, 0, 0, False)
+        else:
+            short = name == "c5"      # 1.4 s per step: keep the sub-record to a few seconds
+            rec = measure(D, name, WORKLOADS[name][6], 3 if short else args.steps, 3 if short else args.warmup, "weak",
+                          args.conv, flush, False, 2 if name in ("c2", "c4") else 0, 0, False)
+        if rec is not None:
+            rec["name"] = name
+            also.append(rec)
+    if D.rank == 0:
+        main["also"] = also
+        print(json.dumps(main))
+    D.close()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--conv", default=os.environ.get("EIG_BENCH_CONV", "auto"), choices=["auto", "simt", "tc"])
     ap.add_argument("--pop", type=int, default=0, help="genomes per GPU (default: the workload's)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: fixed genomes per GPU (default, the driver's contract); strong: the population is split over the GPUs")
-    ap.add_argument("--ref-sample", type=int, default=8, help="genomes per CPU-baseline sample")
+    ap.add_argument("--also", default="auto", help="comma list of sub-records (c2,c3_strong,c4,c5), '' for none; auto = by N")
+    ap.add_argument("--parity", type=int, default=4, help="genomes of the pre-timing parity gate (0 = off)")
+    ap.add_argument("--ref-sample", type=int, default=0, help="genomes per CPU-baseline sample (default: by workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

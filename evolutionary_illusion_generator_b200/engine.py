@@ -16,11 +16,11 @@ RENDER_GRADIENT, RENDER_GRAY_ROUND, RENDER_PALETTE = 0, 1, 2
 
 
 def render_mode_for(c_dim, gradient):
-    """generate_illusion.py:391-458: colour+gradient / gray+gradient -> 0, gray without gradient -> 1,
-    colour without gradient -> 2 (palette)."""
-    if gradient == 1:
-        return RENDER_GRADIENT
-    return RENDER_PALETTE if c_dim > 1 else RENDER_GRAY_ROUND
+    """generate_illusion.py:391-458: colour takes the gradient branch only for `gradient == 1` and the palette branch
+    otherwise (line 391/405); gray rounds only for `gradient == 0` (line 450) and is a plain gradient for any other value."""
+    if c_dim > 1:
+        return RENDER_GRADIENT if gradient == 1 else RENDER_PALETTE
+    return RENDER_GRAY_ROUND if gradient == 0 else RENDER_GRADIENT
 
 
 class Engine:

@@ -12,6 +12,7 @@ from . import engine as engine_mod, runtime
 from .grid import StructureType  # noqa: F401
 
 REPEAT, EXTENSION = 20, 2
+_score_engines = {}
 
 
 def _load_image(image_path, c_dim, w, h):
@@ -44,9 +45,14 @@ def calculate_fitness(structure, vectors, image_path, w, h, engine=None):
         return 0.0
     eng = engine
     if eng is None:
-        if not runtime._engines:
-            raise RuntimeError("calculate_fitness needs an engine: call get_vectors first or pass engine=")
-        eng = next(e for e in runtime._engines.values() if (e.w, e.h) == (w, h))
+        eng = next((e for e in runtime._engines.values() if (e.w, e.h) == (w, h)), None)
+        if eng is None:   # scoring needs no PredNet weights: a cached score-only context of this image size
+            eng = _score_engines.get((w, h))
+            if eng is None:
+                eng = _score_engines[(w, h)] = runtime.engine_factory(w, h, (1, 4, 4, 4), 1)
+    if len(vectors) > engine_mod.MAX_CORNERS:
+        raise ValueError("calculate_fitness: %d vectors, the flow stage never yields more than %d (maxCorners, "
+                         "optical_flow.py:51)" % (len(vectors), engine_mod.MAX_CORNERS))
     v = np.zeros((1, engine_mod.MAX_CORNERS, 4), dtype=np.float32)
     arr = np.asarray(vectors, dtype=np.float32)[:engine_mod.MAX_CORNERS]
     v[0, :len(arr)] = arr

@@ -15,7 +15,8 @@ _flow_engines = {}
 def _engine_for(w, h, c_dim):
     key = (w, h, c_dim)
     if key not in _flow_engines:
-        _flow_engines[key] = runtime.engine_factory(w, h, (c_dim, 16 * c_dim, 32 * c_dim, 64 * c_dim), 8)
+        # flow-only context: the PredNet buffers are never used, so the channels are minimal and one image pair fits
+        _flow_engines[key] = runtime.engine_factory(w, h, (c_dim, 4, 4, 4), 1)
     return _flow_engines[key]
 
 

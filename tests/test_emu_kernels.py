@@ -4,7 +4,7 @@ container; the B200 run of the same comparisons is tests/test_gpu_parity.py."""
 import numpy as np
 import torch
 
-from evolutionary_illusion_generator_b200 import engine as E, genome as G, weights as W
+from evolutionary_illusion_generator_b200 import _lib as _lib_mod, engine as E, genome as G, weights as W
 from oracle import cppn as OC, flow as OF, grid as OG, pipeline as OPL, prednet as OP, scoring as OS
 
 
@@ -271,3 +271,19 @@ def test_single_image_rating_on_the_host_compiled_library_vs_the_reference(emu_l
     assert FC.calculate_fitness(GI.StructureType.Circles, [None], path, w, h) == 0.0
     for eng in runtime._engines.values():
         eng.close()
+
+
+def test_error_text_and_options_belong_to_the_context(emu_lib):
+    """two contexts in one process (the main engine and the render-only engine of enhanced.png) keep
+    their own error text; eig_set_option validates its keys and masks."""
+    a = E.Engine(64, 64, (1, 4, 8, 8), 2, lib=emu_lib)
+    b = E.Engine(64, 64, (1, 4, 8, 8), 2, lib=emu_lib)
+    assert emu_lib.eig_set_option(a.ctx, b"passes.L7", 7) == _lib_mod.EIG_E_INVALID
+    assert b"unknown key passes.L7" in emu_lib.eig_error(a.ctx)
+    assert emu_lib.eig_set_option(b.ctx, b"passes.all", 0) == _lib_mod.EIG_E_INVALID
+    assert b"empty pass mask" in emu_lib.eig_error(b.ctx)
+    assert b"unknown key" in emu_lib.eig_error(a.ctx)                 # untouched by b's failure
+    assert b"empty pass mask" in emu_lib.eig_last_error()              # the thread's most recent message
+    for key, v in ((b"passes.all", 7), (b"passes.L", 6), (b"passes.A2", 5), (b"early_until", 3), (b"early_mask", 4), (b"graphs", 0)):
+        assert emu_lib.eig_set_option(a.ctx, key, v) == 0, key
+    a.close(); b.close()

@@ -159,6 +159,9 @@ def test_engine_cache_grows_geometrically(monkeypatch):
         def load_weights(self, weights):
             self.weights = weights
 
+        def set_conv_mode(self, mode):
+            self.mode = mode
+
         def close(self):
             self.closed = True
 
@@ -171,6 +174,63 @@ def test_engine_cache_grows_geometrically(monkeypatch):
     assert runtime.get_engine(64, 64, (1, 4, 8, 8), "m.npz", 12) is b
     assert runtime.get_engine(64, 64, (1, 4, 8, 8), "m.npz", 40).max_genomes == 40
     assert runtime.get_engine(64, 64, (1, 4, 8, 8), "other.npz", 3) is not made[2] and len(made) == 4
+    assert all(e.mode == _lib.CONV_TC and e.conv_mode == "tc" for e in made)   # EIG_CONV=auto: the tensor-core path
+
+
+def test_conv_policy_of_the_drop_in_entry_points(monkeypatch):
+    """get_engine picks the convolution engine (EIG_CONV=auto|tc|simt), re-applies it when the engine is
+    re-created, falls back to the exact-fp32 path where the tensor-core path is missing, and after an EIG_E_RANGE."""
+    class FakeEngine:
+        tc_ok = True
+
+        def __init__(self, w, h, channels, max_genomes):
+            self.max_genomes, self.calls = max_genomes, 0
+
+        def load_weights(self, weights):
+            pass
+
+        def set_conv_mode(self, mode):
+            if mode == _lib.CONV_TC and not self.tc_ok:
+                raise _lib.EigError(_lib.EIG_E_INVALID, "tensor-core path unavailable")
+            self.mode = mode
+
+        def close(self):
+            pass
+
+        def evaluate(self, programs, structure, render_mode, pair_mode):
+            self.calls += 1
+            if self.mode == _lib.CONV_TC:
+                raise _lib.EigError(_lib.EIG_E_RANGE, "range")
+            return np.zeros(len(programs))
+
+    monkeypatch.setattr(runtime, "engine_factory", FakeEngine)
+    monkeypatch.setattr(runtime, "_engines", {})
+    monkeypatch.delenv("EIG_CONV", raising=False)
+    e = runtime.get_engine(64, 64, (1, 4, 8, 8), "m.npz", 4)
+    assert e.conv_mode == "tc"
+    with pytest.warns(UserWarning, match="split-fp16 range"):
+        out = runtime.evaluate_population(e, [object()] * 3, 1)
+    assert out.shape == (3,) and e.conv_mode == "simt" and e.calls == 2
+    e2 = runtime.get_engine(64, 64, (1, 4, 8, 8), "m.npz", 100)        # re-created: the fallback sticks
+    assert e2 is not e and e2.conv_mode == "simt"
+    monkeypatch.setattr(runtime, "_engines", {})
+    monkeypatch.setenv("EIG_CONV", "simt")
+    assert runtime.get_engine(64, 64, (1, 4, 8, 8), "m.npz", 4).mode == _lib.CONV_SIMT
+    monkeypatch.setattr(runtime, "_engines", {})
+    FakeEngine.tc_ok = False
+    monkeypatch.setenv("EIG_CONV", "auto")
+    assert runtime.get_engine(64, 64, (1, 4, 8, 8), "m.npz", 4).conv_mode == "simt"
+    monkeypatch.setattr(runtime, "_engines", {})
+    monkeypatch.setenv("EIG_CONV", "tc")
+    with pytest.raises(_lib.EigError):
+        runtime.get_engine(64, 64, (1, 4, 8, 8), "m.npz", 4)
+
+
+def test_render_mode_follows_the_reference_branches():
+    """generate_illusion.py:391,405,450: colour is a gradient only for gradient == 1, gray rounds only for gradient == 0."""
+    from evolutionary_illusion_generator_b200 import engine as E
+    assert [E.render_mode_for(3, g) for g in (1, 0, 2)] == [E.RENDER_GRADIENT, E.RENDER_PALETTE, E.RENDER_PALETTE]
+    assert [E.render_mode_for(1, g) for g in (1, 0, 2)] == [E.RENDER_GRADIENT, E.RENDER_GRAY_ROUND, E.RENDER_GRADIENT]
 
 
 def test_libeig_exports_every_symbol_of_the_header():
@@ -222,7 +282,7 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["higher_is_better"] is True
-    assert d["config"]["workload"] == "c2" and d["n_gpus"] == 1 and d["value"] > 0
+    assert d["config"]["workload"] == "c3" and d["n_gpus"] == 1 and d["value"] > 0   # the contract line is BASELINE configs[2]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "NEAT genome fitness evals/sec" in d["metric"]
