@@ -65,7 +65,10 @@ __device__ __forceinline__ float lstm_cell(float gi, float gf, float gc, float g
     return __fmul_rn(o, tanhf(cn));
 }
 
-template <int TN>
+// REV = true walks the nine taps of every input channel backwards: same products, another fp32 summation order - the
+// yardstick for "what a different but equally exact fp32 implementation does to the frames"
+// (profiles/experiments/pass_ablation.py; eig_set_option "simt_reverse_taps").
+template <int TN, bool REV = false>
 __global__ void __launch_bounds__(256) conv3x3_simt_kernel(ConvArgs a) {
     constexpr int CK = 8, TW = 16, TH = 8, SROW = 20;  // SROW: padded smem row (bank-conflict free half-warps)
     EIG_DYN_SMEM(smem);
@@ -122,9 +125,10 @@ __global__ void __launch_bounds__(256) conv3x3_simt_kernel(ConvArgs a) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) in[r][c] = sIn[(ck * (TH + 2) + ty * 4 + r) * SROW + tx + c];
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
+            for (int ky0 = 0; ky0 < 3; ++ky0)
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
+                for (int kx0 = 0; kx0 < 3; ++kx0) {
+                    const int ky = REV ? 2 - ky0 : ky0, kx = REV ? 2 - kx0 : kx0;
                     const float* wrow = sW + ((ky * 3 + kx) * CK + ck) * ncta + warp * TN;
                     float wv[TN];
 #pragma unroll

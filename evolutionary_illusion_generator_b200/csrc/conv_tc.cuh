@@ -370,14 +370,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
             int s = 0;            // ring position and phase are carried, not divided out of a counter (a runtime
             uint32_t ph = 0;      // division costs the single producer / issuer thread ~400 cycles per use)
             const uint32_t fullA_leader = map_to_cta(fullA, 0);
+            const bool need_alo = (p.passes & 1) != 0;
             for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
                 const TcRegion r = tc_region(p, grp, crank);
                 for (int kb = 0; kb < p.KBn; ++kb) {
                     mbar_wait(emptyA + 8 * s, ph ^ 1);
-                    if (crank == 0) mbar_expect_tx(fullA + 8 * s, 4 * p.a_box_bytes);   // 2 planes x 2 CTAs
+                    // 2 CTAs x (hi plane + lo plane); a convolution that does not issue a_lo * w_hi never reads the lo plane
+                    if (crank == 0) mbar_expect_tx(fullA + 8 * s, (need_alo ? 4 : 2) * p.a_box_bytes);
                     const uint32_t dst = sA + s * a_stage_bytes;
                     tma_load_4d_pair(dst, &mAh, fullA_leader + 8 * s, kb * TC_KB, r.x0 - 1, r.y0 - 1, r.b);
-                    tma_load_4d_pair(dst + p.a_plane_bytes, &mAl, fullA_leader + 8 * s, kb * TC_KB, r.x0 - 1, r.y0 - 1, r.b);
+                    if (need_alo) tma_load_4d_pair(dst + p.a_plane_bytes, &mAl, fullA_leader + 8 * s, kb * TC_KB, r.x0 - 1, r.y0 - 1, r.b);
                     if (++s == p.SA) { s = 0; ph ^= 1; }
                 }
             }
@@ -390,6 +392,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
             long long b_wait = 0, b0 = TC_CLK(), bq;
             const int half_rows = p.Ncta >> 1;
             const uint32_t fullB_leader = map_to_cta(fullB, 0);
+            const bool need_wlo = (p.passes & 2) != 0;
             for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
                 const int nbase = (grp / p.groups_per_nz) * p.Ncta, n0 = nbase + crank * half_rows;
                 for (int kb = 0; kb < p.KBn; ++kb) {
@@ -399,9 +402,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                         b_wait += TC_CLK() - bq;
                         const uint32_t dst = sB + s * b_stage_bytes;
                         const int row_hi = (tap * p.KBn + kb) * p.N, row_lo = ((9 + tap) * p.KBn + kb) * p.N;
-                        if (crank == 0) mbar_expect_tx(fullB + 8 * s, 4 * p.b_plane_bytes);   // 2 planes x 2 CTAs
+                        if (crank == 0) mbar_expect_tx(fullB + 8 * s, (need_wlo ? 4 : 2) * p.b_plane_bytes);   // 2 CTAs x (hi + lo plane)
                         tma_load_2d_pair(dst, &mB, fullB_leader + 8 * s, 0, row_hi + n0);
-                        tma_load_2d_pair(dst + p.b_plane_bytes, &mB, fullB_leader + 8 * s, 0, row_lo + n0);
+                        if (need_wlo) tma_load_2d_pair(dst + p.b_plane_bytes, &mB, fullB_leader + 8 * s, 0, row_lo + n0);
                         if (++s == p.SB) { s = 0; ph ^= 1; }
                     }
                 }

@@ -148,12 +148,25 @@ struct eig_ctx : CtxCommon {
     // (mask & early_mask) instead.  Set through eig_set_option; the defaults are what the parity tests pin.
     int passes[3][4] = {{7, 7, 7, 7}, {7, 7, 7, 7}, {7, 7, 7, 7}};
     int early_until = 0, early_mask = 7;
+    int precision = 0;
+    int simt_reverse_taps = 0;   // diagnostic: the exact-fp32 kernel sums the taps in reverse order (ConvArgs::rev_taps)
 #ifndef EIG_EMU
     TcMapCache amaps;   // activation tensor maps of this context's buffers
 #endif
     std::vector<void*> allocs;
 };
 enum { KIND_A = 0, KIND_P = 1, KIND_L = 2 };
+// Precision profiles of the tensor-core path (eig_set_option "precision"; measured in profiles/r2/pass_ablation_*.md):
+//   0 exact    : three products (a_lo*w_hi + a_hi*w_lo + a_hi*w_hi) in every convolution - fp32-grade, 2^-22 per product
+//   1 balanced : single fp16 product in the convolutions of layers 2 and 3 (ConvA2/3, ConvP2/3, ConvLSTM2/3), whose
+//                rounding never reaches the uint8 frames (frame bytes that differ from the exact-fp32 path: unchanged),
+//                three products in layer 1 (ConvA1, ConvLSTM1, ConvP1 + the ConvLSTM0 partial sums), which drive P0 directly
+//   2 fast     : single product everywhere (frames still within 1 LSB; ~15x more bytes differ than in profile 0)
+static void apply_precision(eig_ctx* c, int profile) {
+    for (int kd = 0; kd < 3; ++kd)
+        for (int n = 1; n < 4; ++n) c->passes[kd][n] = profile == 0 ? 7 : profile == 2 ? 4 : (n == 1 ? 7 : 4);
+    c->precision = profile;
+}
 static int passes_for(const eig_ctx* c, int kind, int layer, int t) {
     int m = c->passes[kind][layer];
     if (t < c->early_until && (m & c->early_mask)) m &= c->early_mask;
@@ -258,6 +271,7 @@ static int create_buffers(eig_ctx* c, int w, int h, int c_dim, const int channel
         CK(cudaEventCreateWithFlags(&c->ev_lstm[n], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_p[n], cudaEventDisableTiming));
     }
+    if (const char* e = getenv("EIG_PRECISION")) { const int v = atoi(e); if (v >= 0 && v <= 2) apply_precision(c, v); }
     if (const char* e = getenv("EIG_NO_OVERLAP")) c->overlap = atoi(e) == 0;
     if (const char* e = getenv("EIG_NO_GRAPH")) c->use_graphs = atoi(e) == 0;
 #else
@@ -307,6 +321,11 @@ extern "C" int eig_set_option(eig_ctx* c, const char* key, int value) {
     bool ok = false;
     if (k == "early_until") { c->early_until = value; ok = true; }
     else if (k == "early_mask") { if (!(value & 7)) return fail(EIG_E_INVALID, "eig_set_option: empty pass mask"); c->early_mask = value & 7; ok = true; }
+    else if (k == "precision") {
+        if (value < 0 || value > 2) return fail(EIG_E_INVALID, "eig_set_option: precision must be 0 (exact), 1 (balanced) or 2 (fast)");
+        apply_precision(c, value); ok = true;
+    }
+    else if (k == "simt_reverse_taps") { c->simt_reverse_taps = value != 0; ok = true; }
     else if (k == "graphs") { c->use_graphs = value != 0; ok = true; }
     else if (k == "overlap") { c->overlap = value != 0; ok = true; }
     else if (k.compare(0, 7, "passes.") == 0) {
@@ -502,17 +521,16 @@ static int launch_conv(eig_ctx* c, const ConvArgs& a, cudaStream_t s) {
     if (a.N <= 16) {
         const int nw = (a.N + 3) / 4;
         const size_t smem = (8 * 10 * 20 + 9 * 8 * nw * 4) * sizeof(float);
-        auto k = conv3x3_simt_kernel<4>;
+        auto k = c->simt_reverse_taps ? conv3x3_simt_kernel<4, true> : conv3x3_simt_kernel<4, false>;
         LAUNCH_K(CLS_CONV_SIMT, k, dim3(tiles, a.B, 1), dim3(32 * nw), smem, s, a);
     } else {
         int nw = (a.N + 15) / 16;
         if (nw > 4) nw = 4;
         const int gz = (a.N + nw * 16 - 1) / (nw * 16);
         const size_t smem = (8 * 10 * 20 + 9 * 8 * nw * 16) * sizeof(float);
-        auto k = conv3x3_simt_kernel<16>;
+        auto k = c->simt_reverse_taps ? conv3x3_simt_kernel<16, true> : conv3x3_simt_kernel<16, false>;
         LAUNCH_K(CLS_CONV_SIMT, k, dim3(tiles, a.B, gz), dim3(32 * nw), smem, s, a);
     }
-    (void)c;
     CKL();
     return EIG_OK;
 }
