@@ -46,6 +46,9 @@ struct ConvArgs {
     const float* peep;
     View dstH;
     View dstUp;
+    // tcgen05 kernel only: half-resolution partial sums [B][H/2][W/2][4 parities][N] of the taps over the up-sampled
+    // R_{n+1}, added to the gate pre-activations (nullptr = those taps are part of this convolution's K range)
+    const float* Zin;
 };
 
 __device__ __forceinline__ float chainer_sigmoid(float v) {

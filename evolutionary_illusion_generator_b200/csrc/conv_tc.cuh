@@ -48,6 +48,7 @@ struct TcWeights {
     __half* d = nullptr;  // [2 planes][9 taps][KBn][Npad][32] fp16 (hi plane, then lo plane), scaled by wscale
     int cin = 0, N = 0, Npad = 0, KBn = 0, Ncta = 0, gz = 1;
     int ksteps = 2;       // 16-channel MMA k-steps of the LAST 32-channel block: 1 when it holds <= 16 real channels
+    unsigned short tap_mask[16] = {0x1ff, 0x1ff, 0x1ff, 0x1ff, 0x1ff, 0x1ff, 0x1ff, 0x1ff, 0x1ff, 0x1ff, 0x1ff, 0x1ff, 0x1ff, 0x1ff, 0x1ff, 0x1ff};
     float wscale = 1.f;   // power of two
     CUtensorMap map;      // weight-tile box: Ncta/2 rows (each CTA of the pair stages its half)
     bool ok = false;
@@ -64,6 +65,9 @@ struct TcParams {
     int tmem_cols;
     int ksteps;                   // k-steps of the last K block (see TcWeights); all other blocks have 2
     int passes;                   // MMA products per k-step, bit 0: a_lo*w_hi, bit 1: a_hi*w_lo, bit 2: a_hi*w_hi (7 = all three, the default)
+    int kb_skip_lo, kb_skip_hi;   // K blocks [lo, hi) are left out (a ConvLSTM whose up-sampled-R taps arrive folded through ConvArgs::Zin)
+    unsigned short tap_mask[16];  // per N slice: the taps that slice evaluates (bit = ky*3+kx; 0x1ff = all nine).  The folded
+                                  // up-sampled-R convolution has one pixel parity per slice and each parity uses 4 of the 9 taps.
     int egroups;                  // epilogue column groups: 2 (warps 8-15) or 3 (+ warps 0-3, for wide accumulators)
     int staging_bytes, stage_ld;  // ConvA pooling tile: 128 rows x stage_ld floats
     float inv_scale;              // 1 / (activation scale * weight scale), exact power of two
@@ -332,7 +336,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
     const uint32_t accFull = emptyB + 8 * p.SB, accEmpty = accFull + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pipe_bytes + p.staging_bytes + 8 * (2 * p.SA + 2 * p.SB + 4));
     float* sBias = reinterpret_cast<float*>(smem + pipe_bytes + p.staging_bytes + 8 * (2 * p.SA + 2 * p.SB + 4) + 16);   // [N] bias, read by every epilogue tile
-    for (int i = threadIdx.x; i < p.ca.N; i += TC_THREADS) sBias[i] = p.ca.bias[i];
+    for (int i = threadIdx.x; i < p.ca.N; i += TC_THREADS) sBias[i] = p.ca.bias ? p.ca.bias[i] : 0.f;
 
     if (warp == 6 && lane == 0) {   // hide the descriptor fetch of the first TMA loads behind the barrier / TMEM set-up
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&mAh) : "memory");
@@ -374,6 +378,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
             for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
                 const TcRegion r = tc_region(p, grp, crank);
                 for (int kb = 0; kb < p.KBn; ++kb) {
+                    if (kb >= p.kb_skip_lo && kb < p.kb_skip_hi) continue;
                     mbar_wait(emptyA + 8 * s, ph ^ 1);
                     // 2 CTAs x (hi plane + lo plane); a convolution that does not issue a_lo * w_hi never reads the lo plane
                     if (crank == 0) mbar_expect_tx(fullA + 8 * s, (need_alo ? 4 : 2) * p.a_box_bytes);
@@ -394,9 +399,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
             const uint32_t fullB_leader = map_to_cta(fullB, 0);
             const bool need_wlo = (p.passes & 2) != 0;
             for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
-                const int nbase = (grp / p.groups_per_nz) * p.Ncta, n0 = nbase + crank * half_rows;
+                const int nz = grp / p.groups_per_nz;
+                const int nbase = nz * p.Ncta, n0 = nbase + crank * half_rows;
+                const uint32_t tmask = p.tap_mask[nz];
                 for (int kb = 0; kb < p.KBn; ++kb) {
+                    if (kb >= p.kb_skip_lo && kb < p.kb_skip_hi) continue;
                     for (int tap = 0; tap < 9; ++tap) {
+                        if (!((tmask >> tap) & 1u)) continue;
                         bq = TC_CLK();
                         mbar_wait(emptyB + 8 * s, ph ^ 1);
                         b_wait += TC_CLK() - bq;
@@ -434,7 +443,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                 t_acc += TC_CLK() - tq;
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(set * acc_stride);
+                const uint32_t tmask = p.tap_mask[grp / p.groups_per_nz];
+                const int last_tap = 31 - __clz((int)tmask);
+                const int last_kb = p.kb_skip_hi >= p.KBn && p.kb_skip_lo < p.kb_skip_hi ? p.kb_skip_lo - 1 : p.KBn - 1;
+                uint32_t started = 0u;   // 0 until the first MMA of this group has been issued (it overwrites the accumulator)
                 for (int kb = 0; kb < p.KBn; ++kb) {
+                    if (kb >= p.kb_skip_lo && kb < p.kb_skip_hi) continue;
                     tq = TC_CLK();
                     mbar_wait(fullA + 8 * sa, pha);
                     tc_fence_after();
@@ -443,12 +457,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                     const bool two_ksteps = kb + 1 < p.KBn || p.ksteps == 2;   // a half-empty last block skips its zero k-step
                     uint32_t tap16 = 0;   // (ky * P + kx) rows of 64 bytes, in 16-byte units
                     for (int tap = 0; tap < 9; ++tap) {
+                      if ((tmask >> tap) & 1u) {
                         tq = TC_CLK();
                         mbar_wait(fullB + 8 * sb, phb);
                         t_b += TC_CLK() - tq;
                         tc_fence_after();
                         const uint32_t b16 = (((sB + sb * b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
-                        const uint32_t acc0 = (kb | tap) ? 1u : 0u;
+                        const uint32_t acc0 = started;
+                        started = 1u;
                         if (elect_one()) {
                             const long long ci0 = TC_CLK();
                             // descriptor low words of this tap: everything below is adds of compile-time multiples on
@@ -487,13 +503,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                             }
                             const long long ci1 = TC_CLK();
                             tc_commit_pair(emptyB + 8 * sb);
-                            if (tap == 8) tc_commit_pair(emptyA + 8 * sa);
-                            if (tap == 8 && kb == p.KBn - 1) tc_commit_pair(accFull + 8 * set);
+                            if (tap == last_tap) tc_commit_pair(emptyA + 8 * sa);
+                            if (tap == last_tap && kb == last_kb) tc_commit_pair(accFull + 8 * set);
                             t_issue += ci1 - ci0; t_commit += TC_CLK() - ci1;
                         }
                         __syncwarp();
-                        tap16 += (tap == 2 || tap == 5) ? (uint32_t)((p.P - 2) * (TC_ROW >> 4)) : (uint32_t)(TC_ROW >> 4);
                         if (++sb == p.SB) { sb = 0; phb ^= 1; }
+                      }
+                        tap16 += (tap == 2 || tap == 5) ? (uint32_t)((p.P - 2) * (TC_ROW >> 4)) : (uint32_t)(TC_ROW >> 4);
                     }
                     if (++sa == p.SA) { sa = 0; pha ^= 1; }
                 }
@@ -530,9 +547,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                 int nt = 0, nc0 = half * 16;
                 bool nvalid = false;
                 long long npix = 0, nppix = 0;
-                float4 cold = make_float4(0.f, 0.f, 0.f, 0.f), pq[4];
+                float4 cold = make_float4(0.f, 0.f, 0.f, 0.f), pq[4], zq[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) pq[q] = cold;
+                for (int q = 0; q < 4; ++q) { pq[q] = cold; zq[q] = cold; }
+                const int Hh = p.H >> 1, Wh = p.W >> 1;
                 auto fetch = [&](int i) {
                     nt = i / n_chunks; nc0 = half * 16 + 16 * p.egroups * (i - nt * n_chunks);
                     const int y = r.y0 + nt * p.TH + hh, x = r.x0 + ww;
@@ -543,6 +561,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                     cold = *reinterpret_cast<const float4*>(a.cstate + npix * R + r0);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) pq[q] = *reinterpret_cast<const float4*>(a.peep + (nppix * R + r0 + q) * 4);
+                    if (a.Zin) {   // folded up-sampled-R taps: [b][y/2][x/2][parity][N] partial sums of this pixel's parity
+                        const long long zpix = nvalid ? ((long long)b * Hh + (y >> 1)) * Wh + (x >> 1) : 0;
+                        const float* zp = a.Zin + (zpix * 4 + (nvalid ? (y & 1) * 2 + (x & 1) : 0)) * a.N + n0 + nc0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) zq[q] = *reinterpret_cast<const float4*>(zp + q * 4);
+                    }
                 };
                 if (n_items > 0) fetch(0);
                 eq = TC_CLK();
@@ -556,9 +580,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                     const bool valid = nvalid;
                     const long long pix = npix;
                     const float4 ccur = cold;
-                    float4 pcur[4];
+                    float4 pcur[4], zcur[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) pcur[q] = pq[q];
+                    for (int q = 0; q < 4; ++q) { pcur[q] = pq[q]; zcur[q] = zq[q]; }
                     if (i + 1 < n_items) fetch(i + 1);
                     float v[16];
                     tmem_ld_wait(racc);
@@ -572,8 +596,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float4 bq = *reinterpret_cast<const float4*>(sBias + n0 + c0 + q * 4);
-                        hn[q] = lstm_cell_v(__fmul_rn(v[q * 4], inv), __fmul_rn(v[q * 4 + 1], inv), __fmul_rn(v[q * 4 + 2], inv),
-                                            __fmul_rn(v[q * 4 + 3], inv), bq, pcur[q], co[q], &cn[q]);
+                        // (zcur is zero without folding: x + 0 is exact)
+                        hn[q] = lstm_cell_v(__fadd_rn(__fmul_rn(v[q * 4], inv), zcur[q].x), __fadd_rn(__fmul_rn(v[q * 4 + 1], inv), zcur[q].y),
+                                            __fadd_rn(__fmul_rn(v[q * 4 + 2], inv), zcur[q].z), __fadd_rn(__fmul_rn(v[q * 4 + 3], inv), zcur[q].w),
+                                            bq, pcur[q], co[q], &cn[q]);
                     }
                     *reinterpret_cast<float4*>(a.cstate + pix * R + r0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
                     uint2 uh = make_uint2(0u, 0u), ul = uh;    // h goes to up to five places: split it once
@@ -917,7 +943,8 @@ inline bool tc_geometry(int B, int H, int W, int Ncta, int gz, bool pooled, int 
 // the TMA maps need 16-byte aligned fp16 channel offsets and pixel pitches; other views stay on the SIMT kernel
 inline bool tc_view_ok(const ConvArgs& a) { return a.in_lo && !(a.in_coff & 7) && !(a.in_pitch & 7); }
 
-inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream, int passes = 7, TcMapCache* cache = nullptr) {
+inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream, int passes = 7, TcMapCache* cache = nullptr,
+                   int kb_skip_lo = 0, int kb_skip_hi = 0) {
     TcState& s = tc_state();
     TcMapCache& amaps = cache ? *cache : s.amaps;
     if (!tc_available()) { s.last_error = s.reason; return -1; }
@@ -986,6 +1013,10 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream, i
     p.egroups = (w.Ncta >= 96 || (pooled && w.Ncta >= 48)) ? 3 : 2;
     p.ksteps = w.ksteps;
     p.passes = (passes & 7) ? (passes & 7) : 7;
+    if (kb_skip_lo < 0 || kb_skip_hi > w.KBn || (kb_skip_lo < kb_skip_hi && kb_skip_lo == 0 && kb_skip_hi == w.KBn)) { s.last_error = "tc_conv: bad K-block skip range"; return -1; }
+    p.kb_skip_lo = kb_skip_lo; p.kb_skip_hi = kb_skip_hi;
+    if (w.gz > 16) { s.last_error = "tc_conv: more than 16 N slices"; return -1; }
+    for (int i = 0; i < 16; ++i) p.tap_mask[i] = w.tap_mask[i];
     p.staging_bytes = g.staging; p.stage_ld = g.stage_ld;
     p.inv_scale = 1.0f / (EIG_ACT_SCALE * w.wscale);
     p.ca = a;

@@ -97,6 +97,7 @@ struct LayerW {            // repacked weights of one PredNet layer (device)
     float* peep = nullptr;                              // [H][W][R][4]
 #ifndef EIG_EMU
     TcWeights tcA, tcP, tcL;                            // tensor-core layouts (conv_tc.cuh)
+    TcWeights tcZ;                                      // folded up-sampled-R taps of THIS layer's ConvLSTM: R_{n+1} -> Z_n (layers 1, 2)
 #endif
 };
 
@@ -115,6 +116,13 @@ struct eig_ctx : CtxCommon {
     h16* E0s = nullptr;              // [2 planes][B][h][w][8] split-fp16 E0, input of ConvA1 on the tensor cores (conv_l0.cuh)
     bool conva1_tc = false;          // ConvA1 runs on the tcgen05 kernel (set at weight load: C1 >= 32)
     float* Z = nullptr;              // [B][H/2][W/2][16*C0] partial sums of ConvLSTM0's up-sampled-R1 taps (conv_l0.cuh)
+    // Folding for layers 1 and 2 (tensor-core mode): ConvLSTM_n's taps over the nearest-neighbour up-sampled R_{n+1}
+    // collapse, per pixel parity, to 2x2 taps at half resolution; Zf[n] = [B][H_{n+1}][W_{n+1}][4 parities][4*C_n] holds
+    // those partial sums (one tap-masked convolution of R_{n+1}, launched right after ConvLSTM_{n+1}), ConvLSTM_n skips
+    // the K blocks of its up(R) slice and adds Zf[n] in its epilogue, and ConvLSTM_{n+1} no longer writes the 2x2-replicated
+    // copy of R_{n+1}.  -22 % of the MMAs of ConvLSTM1/2.
+    float* Zf[3] = {nullptr, nullptr, nullptr};
+    int fold = -1;                   // eig_set_option "fold": 0 off, 1 on wherever the shapes allow, -1 auto (by population size)
     int npz = 0;                     // columns of the layer-1 ConvP+Z convolution: C1 + 16*C0
     float* x_in = nullptr;           // [B][h][w][c]
     unsigned char* img = nullptr;    // rendered [B][h][w][c]
@@ -156,6 +164,7 @@ struct eig_ctx : CtxCommon {
     std::vector<void*> allocs;
 };
 enum { KIND_A = 0, KIND_P = 1, KIND_L = 2 };
+static const long long FOLD_AUTO_MIN_PIXELS = 300000;   // "fold" auto: B * H_n * W_n from which the folded form is used (measured, profiles/r2)
 // Precision profiles of the tensor-core path (eig_set_option "precision"; measured in profiles/r2/pass_ablation_*.md):
 //   0 exact    : three products (a_lo*w_hi + a_hi*w_lo + a_hi*w_hi) in every convolution - fp32-grade, 2^-22 per product
 //   1 balanced : single fp16 product in the convolutions of layers 2 and 3 (ConvA2/3, ConvP2/3, ConvLSTM2/3), whose
@@ -195,6 +204,11 @@ extern "C" int eig_version(void) { return 100; }
 extern "C" int64_t eig_launch_count(void) { return launch_counter().n; }
 
 static int create_buffers(eig_ctx* c, int w, int h, int c_dim, const int channels[4], int max_genomes);
+// the folded form needs the K blocks of [E_n | up(R_{n+1}) | h_n] to start on 32-channel boundaries and one parity
+// (4*C_n gate columns) to be a whole number of N slices
+static bool fold_shape_ok(const eig_ctx* c, int n) {
+    return n >= 1 && n <= 2 && (2 * c->ch[n]) % 32 == 0 && c->ch[n + 1] % 32 == 0 && (4 * c->ch[n]) % 32 == 0;
+}
 
 extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, const int channels[4], int max_genomes) {
     if (!out || !channels || max_genomes <= 0) return fail(EIG_E_INVALID, "eig_create: null/invalid argument");
@@ -233,6 +247,8 @@ static int create_buffers(eig_ctx* c, int w, int h, int c_dim, const int channel
     const size_t npx = B * w * h;
     c->npz = c->ch[1] + 16 * c->ch[0];
     CK(dalloc(c, &c->Z, B * c->H[1] * c->W[1] * 16 * c->ch[0]));
+    for (int n = 1; n <= 2; ++n)
+        if (fold_shape_ok(c, n)) CK(dalloc(c, &c->Zf[n], B * c->H[n + 1] * c->W[n + 1] * 16 * c->ch[n]));
     CK(dalloc(c, &c->E0s, 2 * npx * 8));
     CK(dalloc(c, &c->x_in, npx * c_dim));
     CK(dalloc(c, &c->img, npx * c_dim));
@@ -272,6 +288,7 @@ static int create_buffers(eig_ctx* c, int w, int h, int c_dim, const int channel
         CK(cudaEventCreateWithFlags(&c->ev_p[n], cudaEventDisableTiming));
     }
     if (const char* e = getenv("EIG_PRECISION")) { const int v = atoi(e); if (v >= 0 && v <= 2) apply_precision(c, v); }
+    if (const char* e = getenv("EIG_FOLD")) { const int v = atoi(e); c->fold = v < 0 ? -1 : (v != 0); }
     if (const char* e = getenv("EIG_NO_OVERLAP")) c->overlap = atoi(e) == 0;
     if (const char* e = getenv("EIG_NO_GRAPH")) c->use_graphs = atoi(e) == 0;
 #else
@@ -286,7 +303,7 @@ extern "C" void eig_destroy(eig_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
 #ifndef EIG_EMU
-    for (int n = 0; n < 4; ++n) { tc_free(c->lw[n].tcA); tc_free(c->lw[n].tcP); tc_free(c->lw[n].tcL); }
+    for (int n = 0; n < 4; ++n) { tc_free(c->lw[n].tcA); tc_free(c->lw[n].tcP); tc_free(c->lw[n].tcL); tc_free(c->lw[n].tcZ); }
 #endif
 #ifndef EIG_EMU
     drop_graphs(c);
@@ -325,6 +342,7 @@ extern "C" int eig_set_option(eig_ctx* c, const char* key, int value) {
         if (value < 0 || value > 2) return fail(EIG_E_INVALID, "eig_set_option: precision must be 0 (exact), 1 (balanced) or 2 (fast)");
         apply_precision(c, value); ok = true;
     }
+    else if (k == "fold") { c->fold = value < 0 ? -1 : (value != 0); ok = true; }
     else if (k == "simt_reverse_taps") { c->simt_reverse_taps = value != 0; ok = true; }
     else if (k == "graphs") { c->use_graphs = value != 0; ok = true; }
     else if (k == "overlap") { c->overlap = value != 0; ok = true; }
@@ -387,29 +405,39 @@ void scatter_conv(std::vector<float>& dst, int cin_total, int npad, int cin_off,
                 dst[((size_t)tap * cin_total + cin_off + ci) * npad + n * col_mul + col_add] =
                     t->p[((size_t)n * cin + ci) * 9 + tap];
 }
-// ConvLSTM0's 3x3 taps over the nearest-neighbour up-sampled R1, folded to half resolution: output pixel (2Y+py, 2X+px)
+// A ConvLSTM's 3x3 taps over the nearest-neighbour up-sampled R_{n+1}, folded to half resolution: output pixel (2Y+py, 2X+px)
 // reads full-resolution row 2Y+py+ky-1 = low-resolution row Y + floor((py+ky-1)/2), so per parity the taps {0,1,2}
 // collapse onto low-resolution offsets {-1,0,0} (p = 0) or {0,0,+1} (p = 1).  Zero padding agrees on both grids.
-// dst: [9][C1][npad]; Z columns start at col0 = C1: column col0 + (py*2+px)*NG + n, NG = 4*C0.
-// w0: ConvLSTM0 weights [9][ctot0][NG]; the R1 channels are [2*C0, 2*C0 + C1).
-void build_z_weights(std::vector<float>& dst, int npad, int C1, const std::vector<float>& w0, int C0, int ctot0) {
-    const int NG = 4 * C0;
-    static const int lowoff[2][3] = {{-1, 0, 0}, {0, 0, 1}};
-    std::vector<double> acc((size_t)9 * C1 * 4 * NG, 0.0);
+// dst: [9][Cup][npad]; the folded columns start at col0: column col0 + (py*2+px)*NG + n.
+// w: the ConvLSTM's weights [9][ctot][NG]; the R_{n+1} channels are [coff, coff + Cup).
+static const int kLowOff[2][3] = {{-1, 0, 0}, {0, 0, 1}};
+void build_fold_weights(std::vector<float>& dst, int npad, int col0, int Cup, const std::vector<float>& w, int NG, int ctot, int coff) {
+    std::vector<double> acc((size_t)9 * Cup * 4 * NG, 0.0);
     for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px)
             for (int ky = 0; ky < 3; ++ky)
                 for (int kx = 0; kx < 3; ++kx) {
-                    const int tap_lr = (lowoff[py][ky] + 1) * 3 + (lowoff[px][kx] + 1);
-                    for (int ch = 0; ch < C1; ++ch)
+                    const int tap_lr = (kLowOff[py][ky] + 1) * 3 + (kLowOff[px][kx] + 1);
+                    for (int ch = 0; ch < Cup; ++ch)
                         for (int n = 0; n < NG; ++n)
-                            acc[((size_t)tap_lr * C1 + ch) * 4 * NG + (py * 2 + px) * NG + n] +=
-                                (double)w0[((size_t)(ky * 3 + kx) * ctot0 + 2 * C0 + ch) * NG + n];
+                            acc[((size_t)tap_lr * Cup + ch) * 4 * NG + (py * 2 + px) * NG + n] +=
+                                (double)w[((size_t)(ky * 3 + kx) * ctot + coff + ch) * NG + n];
                 }
     for (int tap = 0; tap < 9; ++tap)
-        for (int ch = 0; ch < C1; ++ch)
+        for (int ch = 0; ch < Cup; ++ch)
             for (int j = 0; j < 4 * NG; ++j)
-                dst[((size_t)tap * C1 + ch) * npad + C1 + j] = (float)acc[((size_t)tap * C1 + ch) * 4 * NG + j];
+                dst[((size_t)tap * Cup + ch) * npad + col0 + j] = (float)acc[((size_t)tap * Cup + ch) * 4 * NG + j];
+}
+// the low-resolution taps parity (py, px) reads: bit = (dy+1)*3 + (dx+1)
+unsigned short fold_tap_mask(int parity) {
+    unsigned m = 0;
+    for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) m |= 1u << ((kLowOff[parity >> 1][ky] + 1) * 3 + (kLowOff[parity & 1][kx] + 1));
+    return (unsigned short)m;
+}
+// layer 0: the Z columns ride behind the C1 ConvP1 columns (conv_l0.cuh)
+void build_z_weights(std::vector<float>& dst, int npad, int C1, const std::vector<float>& w0, int C0, int ctot0) {
+    build_fold_weights(dst, npad, C1, C1, w0, 4 * C0, ctot0, 2 * C0);
 }
 }  // namespace
 
@@ -508,6 +536,15 @@ extern "C" int eig_load_weights(eig_ctx* c, int nt, const char* const* names, co
             if (n == 0) lstm0_host = wv;
 #ifndef EIG_EMU
             if (n >= 1 && (rc = tc_pack(L.tcL, wv.data(), ctot, N, N))) return fail(EIG_E_CUDA, "tc_pack ConvLSTM: " + tc_last_error());
+            if (fold_shape_ok(c, n)) {   // Z_n = folded up(R_{n+1}) taps: [9][C_{n+1}][4 parities x N], one parity per group of N slices
+                std::vector<float> zw((size_t)9 * rup * 4 * N, 0.f);
+                build_fold_weights(zw, 4 * N, 0, rup, wv, N, ctot, 2 * C);
+                int ncta = 0;
+                for (int d = 32; d <= 256 && d <= N; d += 32) if (N % d == 0) ncta = d;   // largest slice that divides one parity
+                if (ncta && (rc = tc_pack(L.tcZ, zw.data(), rup, 4 * N, 4 * N, ncta))) return fail(EIG_E_CUDA, "tc_pack fold: " + tc_last_error());
+                if (L.tcZ.ok && (L.tcZ.Ncta != ncta || L.tcZ.gz > 16)) tc_free(L.tcZ);
+                if (L.tcZ.ok) for (int z = 0; z < L.tcZ.gz; ++z) L.tcZ.tap_mask[z] = fold_tap_mask(z * ncta / N);
+            }
 #endif
         }
     }
@@ -642,6 +679,19 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, bool last, cud
 #endif
         return launch_conv(c, a, s);
     };
+#ifndef EIG_EMU
+    // folded up-sampled-R taps (see eig_ctx::Zf): per consumer layer n = 1, 2
+    auto fold_on = [&](int n) {
+        if (!tc || n < 1 || n > 2 || !c->Zf[n] || !c->lw[n].tcZ.ok || !c->lw[n].tcL.ok || c->fold == 0) return false;
+        // the producer of Z_n is the tcgen05 launch of ConvLSTM_{n+1}: that layer must be on the tensor-core path too
+        const int hoff_up = 2 * c->ch[n + 1] + (n + 1 < 3 ? c->ch[n + 2] : 0);
+        if (!c->lw[n + 1].tcL.ok || (c->ctot[n + 1] & 7) || (c->ctot[n] & 7) || (hoff_up & 7)) return false;
+        if (c->fold == 1) return true;
+        return (long long)B * c->H[n] * c->W[n] >= FOLD_AUTO_MIN_PIXELS;   // small populations are launch-bound: one more launch costs more than the MMAs it saves
+    };
+#else
+    auto fold_on = [&](int) { return false; };
+#endif
     for (int n = 3; n >= 1; --n) {  // ConvLSTM_n
         ConvArgs a;
         memset(&a, 0, sizeof a);
@@ -653,9 +703,25 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, bool last, cud
         const int hoff = 2 * c->ch[n] + (n < 3 ? c->ch[n + 1] : 0);
         a.dstH = mkview(c->X[n][nxt], lo_plane(c, n, c->X[n][nxt]), c->ctot[n], hoff, c->ch[n]);
         // R_n up-sampled x2 into the concat buffer of layer n-1 (layer 0 gets R_1 through Z instead)
-        if (n >= 2) a.dstUp = mkview(c->X[n - 1][cur], lo_plane(c, n - 1, c->X[n - 1][cur]), c->ctot[n - 1], 2 * c->ch[n - 1], c->ch[n]);
+        const bool fold_here = fold_on(n), fold_below = n >= 2 && fold_on(n - 1);
+        if (n >= 2 && !fold_below) a.dstUp = mkview(c->X[n - 1][cur], lo_plane(c, n - 1, c->X[n - 1][cur]), c->ctot[n - 1], 2 * c->ch[n - 1], c->ch[n]);
 #ifndef EIG_EMU
-        if (tc && c->lw[n].tcL.ok && tc_view_ok(a)) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s, passes_for(c, KIND_L, n, t), &c->amaps); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error()); }
+        if (tc && c->lw[n].tcL.ok && tc_view_ok(a)) {
+            int skip_lo = 0, skip_hi = 0;
+            if (fold_here) { a.Zin = c->Zf[n]; skip_lo = 2 * c->ch[n] / TC_KB; skip_hi = (2 * c->ch[n] + c->ch[n + 1]) / TC_KB; }
+            prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s, passes_for(c, KIND_L, n, t), &c->amaps, skip_lo, skip_hi); prof_post(s); EIG_COUNT_LAUNCH();
+            if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error());
+            if (fold_below) {   // Z_{n-1}: the tap-masked half-resolution convolution of the h_n just written, raw fp32 partial sums
+                ConvArgs z;
+                memset(&z, 0, sizeof z);
+                z.in_hi = c->X[n][nxt]; z.in_lo = lo_plane(c, n, c->X[n][nxt]);
+                z.in_pitch = c->ctot[n]; z.in_coff = hoff; z.Cin = c->ch[n];
+                z.B = B; z.H = c->H[n]; z.W = c->W[n];
+                z.N = 16 * c->ch[n - 1]; z.Npad = z.N; z.epi = EPI_RAW; z.outP = c->Zf[n - 1];
+                prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n - 1].tcZ, z, s, passes_for(c, KIND_L, n - 1, t), &c->amaps); prof_post(s); EIG_COUNT_LAUNCH();
+                if (rc) return fail(EIG_E_CUDA, "tc_conv fold: " + tc_last_error());
+            }
+        }
         else
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;

@@ -188,6 +188,16 @@ REFERENCE_CASES = [
 ]
 
 
+# BASELINE configs[4] shape (512x512 colour, Free scoring branch, generate_illusion.py:590-607) through the reference
+# itself: `python make_golden.py reference-large` -> reference_pipeline_large.npz.  3-output genomes: the reference's
+# colour render indexes image_array[:, :, c] for every output node, so the 6-output free config overflows its 3-channel
+# array (SURVEY.md "defects").  configs[3] (Bands) cannot be recorded this way: the reference's own get_fitnesses_neat
+# raises IndexError on the (1, w*h) Bands planes in get_image_from_cppn (generate_illusion.py:400; same defect list) -
+# its 320x240 resolution is covered by r_320x240 above and the Bands scoring branch by scoring_ref.npz.
+REFERENCE_LARGE_CASES = [
+    ("r_c5_free", "circles", 3, (3, 48, 96, 192), 512, 512, 2, 1, 2, False, 0),
+]
+
 EXPORT_CASES = ("r_small_free", "r_small_colour_palette")
 
 
@@ -221,11 +231,11 @@ def run_reference_case(ns, case, workdir):
     return np.array([float(g.fitness) for _, g in pop]), np.stack(frames), exported
 
 
-def make_reference_pipeline(ns):
+def make_reference_pipeline(ns, cases=None, fname="reference_pipeline.npz"):
     """tests/golden/reference_pipeline.npz: fitness vectors and frames produced by the reference itself."""
     import tempfile
     out, meta = {}, []
-    for case in REFERENCE_CASES:
+    for case in (cases or REFERENCE_CASES):
         with tempfile.TemporaryDirectory() as d:
             fit, frames, exported = run_reference_case(ns, case, d)
         name = case[0]
@@ -237,7 +247,31 @@ def make_reference_pipeline(ns):
                               "weight_seed"), case)))
         print(name, "reference fitness", np.round(fit, 6))
     out["meta"] = np.array(json.dumps(meta))
-    np.savez_compressed(os.path.join(HERE, "reference_pipeline.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, fname), **out)
+
+
+def make_full_populations():
+    """full_populations.npz: the oracle on EVERY genome of the two 160x120 bench populations (BASELINE configs[1] pop 32,
+    configs[2] pop 128; bench.build_population, predictor weights seed 0): fitness, number of flow vectors and the two
+    frames handed to the flow stage for the first 8 genomes.  ~3 minutes on 8 cores; /root/reference not needed."""
+    import torch
+    torch.set_num_threads(8)
+    out, meta = {}, []
+    for name, preset, c_dim, ch, w, h, structure, n in (("c2", "circles_bw", 1, (1, 16, 32, 64), 160, 120, 1, 32),
+                                                        ("c3", "circles", 3, (3, 48, 96, 192), 160, 120, 1, 128)):
+        wts = W.synthetic_predictor_weights(w, h, ch, seed=0)
+        cfg = G.make_config(2, G.NEAT_PRESETS[preset]["num_outputs"])
+        pop = [G.synthetic_genome(preset, i) for i in range(n)]
+        fit, ex = OPL.evaluate_population(pop, cfg.genome_config.input_keys, cfg.genome_config.output_keys, structure,
+                                          wts, w, h, ch, c_dim, keep=True, flow_impl="cv2")
+        out["fitness_" + name] = fit
+        out["nvec_" + name] = np.array([len(e["vectors"]) for e in ex])
+        out["frames_" + name] = np.stack([np.stack(e["frames"][:2]) for e in ex[:8]])
+        meta.append(dict(name=name, preset=preset, c_dim=c_dim, channels=ch, w=w, h=h, structure=structure, n=n,
+                         weights="predictor", weight_seed=0))
+        print(name, "nonzero fitness", int((fit > 0).sum()), "of", n, "mean nvec", out["nvec_" + name].mean())
+    out["meta"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(HERE, "full_populations.npz"), **out)
 
 
 SINGLE_IMAGE_CASES = [
@@ -302,6 +336,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "reference":
         make_reference_pipeline(ref_harness.load())
         make_reference_single_image(ref_harness.load())
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "reference-large":
+        make_reference_pipeline(ref_harness.load(), REFERENCE_LARGE_CASES, "reference_pipeline_large.npz")
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "full":
+        make_full_populations()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "single":
         make_reference_single_image(ref_harness.load())

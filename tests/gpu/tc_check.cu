@@ -197,6 +197,7 @@ static bool check_epilogues(Problem& p, int mode) {
     return ok;
 }
 
+static int g_passes = 7;   // MMA products per k-step in timing mode (TcParams::passes)
 // timing mode: `tc_check time` runs the PredNet layer shapes at population 32 with the per-role cycle counters on
 static void time_shape(const char* name, int B, int H, int W, int pitch, int coff, int Cin, int N, int epi, int max_nt) {
     tc_set_max_nt(max_nt);
@@ -221,21 +222,21 @@ static void time_shape(const char* name, int B, int H, int W, int pitch, int cof
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float ms_product = 0;
     {   // the product instantiation (no cycle counters)
-        for (int i = 0; i < 3; ++i) tc_conv(p.tw, a, 0);
+        for (int i = 0; i < 3; ++i) tc_conv(p.tw, a, 0, g_passes);
         CHECK(cudaDeviceSynchronize());
         cudaEventRecord(e0);
-        for (int i = 0; i < 10; ++i) tc_conv(p.tw, a, 0);
+        for (int i = 0; i < 10; ++i) tc_conv(p.tw, a, 0, g_passes);
         cudaEventRecord(e1);
         CHECK(cudaDeviceSynchronize());
         cudaEventElapsedTime(&ms_product, e0, e1);
     }
     long long* dbg; CHECK(cudaMalloc(&dbg, 160 * 16 * 8)); CHECK(cudaMemset(dbg, 0, 160 * 16 * 8));
     tc_state().dbg = dbg;
-    for (int i = 0; i < 3; ++i) tc_conv(p.tw, a, 0);
+    for (int i = 0; i < 3; ++i) tc_conv(p.tw, a, 0, g_passes);
     CHECK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
     const int reps = 10;
-    for (int i = 0; i < reps; ++i) if (tc_conv(p.tw, a, 0)) { printf("tc_conv: %s\n", tc_last_error().c_str()); exit(2); }
+    for (int i = 0; i < reps; ++i) if (tc_conv(p.tw, a, 0, g_passes)) { printf("tc_conv: %s\n", tc_last_error().c_str()); exit(2); }
     cudaEventRecord(e1);
     CHECK(cudaDeviceSynchronize());
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
@@ -252,6 +253,22 @@ static void time_shape(const char* name, int B, int H, int W, int pitch, int cof
     tc_state().dbg = nullptr;
     cudaFree(dbg); cudaFree(out); cudaFree(cst); cudaFree(peep); cudaFree(dh); cudaFree(Pp); cudaFree(dE);
     cudaFree(p.d_hi); cudaFree(p.d_w); cudaFree(p.d_b); tc_free(p.tw);
+}
+
+// `tc_check time c3 [passes]`: the eight convolutions of one PredNet step of BASELINE configs[2] (pop 128 colour)
+static int timing_c3(int passes) {
+    g_passes = passes;
+    printf("--- workload C3 shapes (B 128, channels 3,48,96,192), MMA products mask %d\n", passes);
+    time_shape("A2", 128, 60, 80, 240, 0, 96, 96, EPI_CONVA, 0);
+    time_shape("A3", 128, 30, 40, 480, 0, 192, 192, EPI_CONVA, 0);
+    time_shape("LSTM3", 128, 15, 20, 576, 0, 576, 768, EPI_LSTM, 0);
+    time_shape("LSTM2", 128, 30, 40, 480, 0, 480, 384, EPI_LSTM, 0);
+    time_shape("LSTM1", 128, 60, 80, 240, 0, 240, 192, EPI_LSTM, 0);
+    time_shape("P1+Z", 128, 60, 80, 240, 192, 48, 96, EPI_CONVP, 0);
+    time_shape("P2", 128, 30, 40, 480, 384, 96, 96, EPI_CONVP, 0);
+    time_shape("P3", 128, 15, 20, 576, 384, 192, 192, EPI_CONVP, 0);
+    g_passes = 7;
+    return 0;
 }
 
 static int timing_main() {
@@ -276,6 +293,7 @@ static int timing_main() {
 
 int main(int argc, char** argv) {
     if (!tc_available()) { printf("tensor-core path unavailable: %s\n", tc_unavailable_reason().c_str()); return 4; }
+    if (argc > 2 && !strcmp(argv[1], "time") && !strcmp(argv[2], "c3")) return timing_c3(argc > 3 ? atoi(argv[3]) : 7);
     if (argc > 1 && !strcmp(argv[1], "time")) return timing_main();
     struct Shape { int B, H, W, pitch, coff, Cin, N; };
     const Shape shapes[] = {

@@ -206,9 +206,10 @@ def test_whole_path_fitness_vs_oracle_golden(gpu_engine_factory, mode):
         report.append((m["name"], float((rel <= 1e-3).mean()), rel.max(), list(dbg["nvec"]), list(z["nvec_" + m["name"]])))
     for r in report:
         print("whole path %s %s: within 1e-3: %.2f  worst rel %.2e  nvec %s vs %s" % ((mode,) + r))
-    # tolerance stated by north_star: 1e-3 relative; fitness is discontinuous in the uint8 frames, so a genome
-    # whose frames differ by one LSB somewhere may land outside - report the fraction, require the bulk
-    assert np.mean([r[1] for r in report]) >= 0.8
+    # tolerance stated by north_star: 1e-3 relative, for EVERY genome of every golden case.  (Fitness is discontinuous in
+    # the uint8 frames, so a genome whose frames carry an LSB flip may land outside; such a genome would have to be named
+    # here with its flip - measured on the B200: none, profiles/r2/parity_report_*.txt.)
+    assert all(r[1] == 1.0 for r in report), [(r[0], r[1], r[2]) for r in report if r[1] < 1.0]
 
 
 @pytest.mark.parametrize("mode", ["simt", "tc"])
@@ -219,8 +220,6 @@ def test_whole_path_fitness_vs_the_reference_itself(gpu_engine_factory, mode):
     z = np.load(os.path.join(GOLDEN, "reference_pipeline.npz"))
     worst = 0.0
     for m in json.loads(str(z["meta"])):
-        if m["name"] == "r_320x240":
-            continue      # recorded after the last B200 session of round 1 (CPU oracle test covers it); enable once run on a GPU
         w, h, ch, c = m["w"], m["h"], tuple(m["channels"]), m["c_dim"]
         cfg = G.make_config(2, G.NEAT_PRESETS[m["preset"]]["num_outputs"])
         pop = G.synthetic_population(m["preset"], m["n"], evolved=m["evolved"])
@@ -294,7 +293,7 @@ def test_full_size_properties_c2(gpu_engine_factory):
     rel = np.abs(full[:8] - want) / np.maximum(np.abs(want), 1e-12)
     rel[(full[:8] == 0) & (want == 0)] = 0
     print("C2 first 8 genomes rel err vs oracle:", np.array2string(rel, precision=2))
-    assert (rel <= 1e-3).mean() >= 0.75
+    assert (rel <= 1e-3).all(), rel
     assert (full > 0).mean() > 0.5
 
 
@@ -323,7 +322,7 @@ def test_largest_baseline_configs(gpu_engine_factory, name, preset, structure, w
     def close(a, b):
         return (a == b) or abs(a - b) <= 1e-3 * max(abs(b), 1e-12) or (np.isnan(a) and np.isnan(b))
     assert close(fits["simt"][0], ref[0])
-    assert sum(close(a, b) for a, b in zip(fits["tc"], fits["simt"])) >= n - 1
+    assert all(close(a, b) for a, b in zip(fits["tc"], fits["simt"])), (fits["tc"], fits["simt"])
 
 
 @pytest.mark.parametrize("c", [1, 3])
