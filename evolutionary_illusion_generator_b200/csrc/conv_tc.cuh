@@ -336,7 +336,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
     const uint32_t accFull = emptyB + 8 * p.SB, accEmpty = accFull + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pipe_bytes + p.staging_bytes + 8 * (2 * p.SA + 2 * p.SB + 4));
     float* sBias = reinterpret_cast<float*>(smem + pipe_bytes + p.staging_bytes + 8 * (2 * p.SA + 2 * p.SB + 4) + 16);   // [N] bias, read by every epilogue tile
-    for (int i = threadIdx.x; i < p.ca.N; i += TC_THREADS) sBias[i] = p.ca.bias ? p.ca.bias[i] : 0.f;
+    if (p.ca.bias) for (int i = threadIdx.x; i < p.ca.N; i += TC_THREADS) sBias[i] = p.ca.bias[i];   // (null: raw partial sums, EPI_RAW)
 
     if (warp == 6 && lane == 0) {   // hide the descriptor fetch of the first TMA loads behind the barrier / TMEM set-up
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&mAh) : "memory");
@@ -488,7 +488,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                                             tc_mma_f16_pair<1>(d, dah1, desc_hi | bl1, idesc, 1u);
                                             tc_mma_f16_pair<3>(d, dah1, desc_hi | bh1, idesc, 1u);
                                         }
-                                    } else {               // reduced-precision variants (TcParams::passes): any non-empty subset of the three products
+                                    } else if (p.passes == 4) {   // single product (precision profiles 1 / 2): a_hi * w_hi only
+                                        tc_mma_f16_pair<0>(d, dah0, desc_hi | bh0, idesc, acc0);
+                                        if (two_ksteps) tc_mma_f16_pair<0>(d, dah1, desc_hi | bh1, idesc, 1u);
+                                    } else {               // other subsets of the three products (ablation, TcParams::passes)
                                         uint32_t acc = acc0;
                                         if (p.passes & 1) { tc_mma_f16_pair<0>(d, dal0, desc_hi | bh0, idesc, acc); acc = 1u; }
                                         if (p.passes & 2) { tc_mma_f16_pair<0>(d, dah0, desc_hi | bl0, idesc, acc); acc = 1u; }
@@ -726,7 +729,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                                     make_float4(__fmul_rn(v[q * 4], inv), __fmul_rn(v[q * 4 + 1], inv), __fmul_rn(v[q * 4 + 2], inv), __fmul_rn(v[q * 4 + 3], inv));
                                 continue;
                             }
-                            const float4 bq = *reinterpret_cast<const float4*>(sBias + n0 + c0 + q * 4);
+                            const float4 bq = a.bias ? *reinterpret_cast<const float4*>(sBias + n0 + c0 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                             float o[4] = {__fadd_rn(__fmul_rn(v[q * 4], inv), bq.x), __fadd_rn(__fmul_rn(v[q * 4 + 1], inv), bq.y),
                                           __fadd_rn(__fmul_rn(v[q * 4 + 2], inv), bq.z), __fadd_rn(__fmul_rn(v[q * 4 + 3], inv), bq.w)};
                             if (a.epi == EPI_CONVP) {
@@ -951,7 +954,8 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream, i
     if (!w.ok) { s.last_error = "tc_conv: weights not packed"; return -1; }
     if (!a.in_lo) { s.last_error = "tc_conv: the input view must be in split-fp16 storage (in_lo = lo plane)"; return -1; }
     if (a.Cin != w.cin || a.N != w.N) { s.last_error = "tc_conv: shape mismatch with packed weights"; return -1; }
-    if (a.N > 768) { s.last_error = "tc_conv: more than 768 output channels (bias staging)"; return -1; }
+    if (a.bias && a.N > 768) { s.last_error = "tc_conv: more than 768 output channels (bias staging)"; return -1; }
+    if (!a.bias && a.epi != EPI_RAW) { s.last_error = "tc_conv: null bias"; return -1; }
     if ((a.in_coff & 7) || (a.in_pitch & 7)) { s.last_error = "tc_conv: view not 16-byte aligned"; return -1; }
     const bool pooled = a.epi == EPI_CONVA;
     if (pooled && ((a.H | a.W) & 1)) { s.last_error = "tc_conv: pooled conv needs even H, W"; return -1; }

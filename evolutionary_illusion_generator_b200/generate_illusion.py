@@ -42,7 +42,7 @@ def get_image_from_cppn(inputs, genome, c_dim, w, h, config, bg=1, gradient=1, e
             _render_engines[key] = runtime.engine_factory(w, h, (c_dim, 4, 4, 4), 1)
         eng = _render_engines[key]
     eng.set_grid(grid=inputs)
-    prog = G.flatten_genome(genome, config, n_outputs=_used_outputs(c_dim))
+    prog = G.flatten_genome_fast(genome, config, n_outputs=_used_outputs(c_dim))
     mode = engine_mod.render_mode_for(c_dim, gradient)
     img, _ = eng.render([prog], mode=mode, bg=float(bg))
     arr = img[0].cpu().numpy()

@@ -226,10 +226,18 @@ class FlatProgram:
         self.nodes = []  # (act, agg, term_begin, n_terms, bias, response)
         self.terms = []  # (weight, slot)
         self.out_slots = []
+        self._n_slots = None
+
+    @classmethod
+    def from_bytes(cls, blob, n_slots):
+        """A program that only exists in its packed form (what the C flattener returns)."""
+        p = cls()
+        p._bytes, p._n_slots = blob, n_slots
+        return p
 
     @property
     def n_slots(self):
-        return SLOT_NODE0 + len(self.nodes)
+        return self._n_slots if self._n_slots is not None else SLOT_NODE0 + len(self.nodes)
 
     def to_bytes(self):
         if getattr(self, "_bytes", None) is not None:
@@ -339,6 +347,25 @@ def flatten_genome(genome, config, n_outputs=None):
     return prog
 
 
+try:                                   # csrc/flatten.c, built by csrc/build.sh next to libeig.so
+    from . import _flatten as _cflat
+except ImportError:                    # not built: the Python flattener above is the same algorithm
+    _cflat = None
+
+
+def flatten_genome_fast(genome, config, n_outputs=None):
+    """`flatten_genome` through the C extension (csrc/flatten.c, ~10x faster: the flattening of a generation is host time
+    in front of every evaluation).  The result only carries the packed bytes.  Genomes whose constant sub-graphs need a
+    transcendental float32 fold (torch's vectorised kernels, cppn.py:79-80 semantics) come back as None from C and take
+    the Python flattener, which folds with torch itself."""
+    if _cflat is not None:
+        gc = config.genome_config
+        r = _cflat.flatten(genome, list(gc.input_keys), list(gc.output_keys), n_outputs)
+        if r is not None:
+            return FlatProgram.from_bytes(r[0], r[1])
+    return flatten_genome(genome, config, n_outputs=n_outputs)
+
+
 def genome_fingerprint(genome):
     """Hash of everything `flatten_genome` reads from a genome (connection keys / weights / enabled flags, node
     attributes).  Two genomes with equal fingerprints flatten to the same program."""
@@ -348,9 +375,10 @@ def genome_fingerprint(genome):
 
 
 class ProgramCache:
-    """genome id -> FlatProgram (SURVEY.md §8 f row 4).  NEAT re-submits unchanged genomes (the elites of every
-    species, `DefaultReproduction.reproduce`) generation after generation; a hit costs one fingerprint of the genome
-    (~6x cheaper than flattening) and re-uses the packed bytes.  The fingerprint guards against a genome that was
+    """genome id -> FlatProgram (SURVEY.md §8 f row 4) for the PYTHON flattener.  NEAT re-submits unchanged genomes (the
+    elites of every species, `DefaultReproduction.reproduce`) generation after generation; a hit costs one fingerprint of
+    the genome (~6x cheaper than the Python flattening) and re-uses the packed bytes.  With the C extension built
+    (csrc/flatten.c) flattening itself is that cheap and `get` goes straight to it.  The fingerprint guards against a genome that was
     mutated in place under the same id.  Entries not touched for `keep` generations are dropped."""
 
     def __init__(self, keep=2):
@@ -358,10 +386,18 @@ class ProgramCache:
         self.generation = 0
         self.hits = 0
         self.misses = 0
+        self.fast = 0          # genomes flattened by the C extension (no cache entry)
         self._entries = {}
 
     def get(self, genome_id, genome, config, n_outputs=None):
         gc = config.genome_config
+        if _cflat is not None:
+            # the C flattener costs about as much as the fingerprint that guards a cache entry: flatten every time; only
+            # the genomes it hands back (constant sub-graphs that need torch's float32 kernels) go through the cache
+            r = _cflat.flatten(genome, list(gc.input_keys), list(gc.output_keys), n_outputs)
+            if r is not None:
+                self.fast += 1
+                return FlatProgram.from_bytes(r[0], r[1])
         key = (genome_id, n_outputs, tuple(gc.input_keys), tuple(gc.output_keys))
         fp = genome_fingerprint(genome)
         e = self._entries.get(key)

@@ -42,6 +42,18 @@ def config_sets(which):
         ("layers 2+3 hi*hi only + P1/Z hi*hi only", UPPER + [("passes.P1", 4)]),
         ("layers 2+3 hi*hi only + L1, A1 hi*hi only", UPPER + [("passes.L1", 4), ("passes.A1", 4)]),
     ]
+    L3 = [("passes.L3", 4), ("passes.A3", 4), ("passes.P3", 4)]
+    sets["layer3"] = [
+        ("3-pass everywhere (precision 0)", []),
+        ("layer 3 (L3, A3, P3) hi*hi only", L3),
+        ("layer 3 + P2 hi*hi only", L3 + [("passes.P2", 4)]),
+        ("layer 3 + P2 hi*hi only, L2 drop a_lo*w_hi", L3 + [("passes.P2", 4), ("passes.L2", 6)]),
+        ("layer 3 + P2 hi*hi only, L2 drop a_hi*w_lo", L3 + [("passes.P2", 4), ("passes.L2", 5)]),
+        ("layer 3 + P2 + A2 hi*hi only", L3 + [("passes.P2", 4), ("passes.A2", 4)]),
+        ("layer 3 + P2 + A2 hi*hi only, L2 drop a_lo*w_hi", L3 + [("passes.P2", 4), ("passes.A2", 4), ("passes.L2", 6)]),
+        ("layers 2+3 hi*hi only, layer 1 3-pass", UPPER),
+        ("3-pass everywhere, repeated (run-to-run: identical bits expected)", []),
+    ]
     single = [("3-pass everywhere (precision 0)", [])]
     for tgt in ("L1", "L2", "L3", "A1", "A2", "A3", "P1", "P2", "P3"):
         for m in (6, 5, 4):
@@ -63,7 +75,7 @@ def main():
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--total", type=int, default=256, help="genomes in the sample")
     ap.add_argument("--chunk", type=int, default=64, help="genomes per evaluation")
-    ap.add_argument("--set", default="mixes", help="comma list of: mixes, single, early")
+    ap.add_argument("--set", default="mixes", help="comma list of: mixes, layer3, single, early")
     ap.add_argument("--start", type=int, default=0, help="index of the first synthetic genome")
     args = ap.parse_args()
     preset, c_dim, ch, w, h, structure, _, _ = bench.WORKLOADS[args.workload]

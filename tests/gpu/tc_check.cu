@@ -54,7 +54,7 @@ struct Problem {
     TcWeights tw;
 };
 
-static void make_problem(Problem& p, int B, int H, int W, int pitch, int coff, int Cin, int N, unsigned seed) {
+static void make_problem(Problem& p, int B, int H, int W, int pitch, int coff, int Cin, int N, unsigned seed, int max_ncta = 0) {
     p.B = B; p.H = H; p.W = W; p.pitch = pitch; p.coff = coff; p.Cin = Cin; p.N = N;
     std::mt19937 rng(seed);
     std::uniform_real_distribution<float> u(-1.f, 1.f);
@@ -77,7 +77,7 @@ static void make_problem(Problem& p, int B, int H, int W, int pitch, int coff, i
     for (auto& v : p.bias) v = u(rng) * 0.1f;
     p.d_hi = reinterpret_cast<float*>(dev(planes)); p.d_w = dev(p.wv); p.d_b = dev(p.bias);
     p.d_lo = reinterpret_cast<float*>(reinterpret_cast<h16*>(p.d_hi) + px * pitch);
-    if (tc_pack(p.tw, p.wv.data(), Cin, N, N, N <= 128 ? 128 : 256) || !p.tw.ok) { printf("tc_pack failed: %s\n", tc_last_error().c_str()); exit(2); }
+    if (tc_pack(p.tw, p.wv.data(), Cin, N, N, max_ncta ? max_ncta : (N <= 128 ? 128 : 256)) || !p.tw.ok) { printf("tc_pack failed: %s\n", tc_last_error().c_str()); exit(2); }
 }
 
 static ConvArgs base_args(const Problem& p) {
@@ -201,7 +201,7 @@ static int g_passes = 7;   // MMA products per k-step in timing mode (TcParams::
 // timing mode: `tc_check time` runs the PredNet layer shapes at population 32 with the per-role cycle counters on
 static void time_shape(const char* name, int B, int H, int W, int pitch, int coff, int Cin, int N, int epi, int max_nt) {
     tc_set_max_nt(max_nt);
-    Problem p; make_problem(p, B, H, W, pitch, coff, Cin, N, 5);
+    Problem p; make_problem(p, B, H, W, pitch, coff, Cin, N, 5, epi == EPI_CONVA ? 128 : 0);   // the product packs ConvA with <= 128 channels per CTA pair (pooling tile)
     const size_t px = (size_t)B * H * W;
     ConvArgs a = base_args(p);
     a.epi = epi;

@@ -38,7 +38,7 @@ def _worker(rank, world, port, n, out_dir):
     cache = G.ProgramCache()
     pop = [(i, G.synthetic_genome("circles_bw", i)) for i in range(n)]
     streamed = runtime.evaluate_genomes(eng, pop, lambda gid, g: cache.get(gid, g, cfg, 1), 2, chunk=1)
-    assert cache.misses == hi - lo
+    assert cache.misses + cache.fast == hi - lo     # this rank flattened its own shard only
     np.save(os.path.join(out_dir, "fit_streamed_%d.npy" % rank), streamed)
     np.save(os.path.join(out_dir, "shard_%d.npy" % rank), np.array([lo, hi, per]))
     # the whole drop-in call under torch.distributed: every rank ends with the same genome.fitness, rank 0 alone writes files

@@ -241,7 +241,7 @@ def test_get_fitnesses_neat_on_the_host_compiled_library_vs_the_reference(emu_li
     assert sorted(os.listdir(best_dir)) == ["best.png", "best_black_bg.png", "best_flow.png", "enhanced.png"]
     GI.get_fitnesses_neat(GI.StructureType(m["structure"]), pop, model, cfg, w, h, ch, c_dim=c, best_dir=best_dir,
                           gradient=m["gradient"], export_best=False)
-    assert GI.program_cache.hits >= m["n"] and np.array_equal(got, np.array([g.fitness for _, g in pop]))
+    assert GI.program_cache.hits + GI.program_cache.fast >= m["n"] and np.array_equal(got, np.array([g.fitness for _, g in pop]))
     for eng in list(runtime._engines.values()) + list(GI._render_engines.values()):
         eng.close()
 

@@ -45,7 +45,9 @@ def _frame_diff(a, b):
 # 1e-3 against the CPU oracle (mode -> workload -> ids); measured on the B200, see the printed report of the test
 FULL_POP_ALLOW = {
     "simt": {"c2": [], "c3": []},
-    "tc": {"c2": [], "c3": []},
+    # c3 genome 29: one LSB flip in its extension frame changes the status of a tracked corner; 1.4e-2 (it is an outlier of the
+    # exact 3-product path against the exact-fp32 GPU path too: profiles/r2/pass_ablation_c3_mixes512.md, ids 13 29 113 ...)
+    "tc": {"c2": [], "c3": [29]},
 }
 
 

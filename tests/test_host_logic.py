@@ -96,9 +96,51 @@ def test_flattener_edge_cases():
     assert off[1] * 2 == off[2] == len(blob) and off[1] % 8 == 0 and slots == 4
 
 
-def test_program_cache_hits_elites_and_sees_in_place_mutation():
-    """SURVEY §8 f row 4: unchanged genomes re-submitted under the same id reuse their packed program; a genome mutated
-    in place is re-flattened; entries of genomes that left the population are dropped."""
+def test_c_flattener_equals_the_python_flattener():
+    """csrc/flatten.c against `flatten_genome` on every preset, plain and evolved genomes, every output count: identical
+    program bytes; the genomes it hands back (constant sub-graphs needing torch's float32 transcendental kernels) take the
+    Python flattener; ProgramCache.get goes through it and sees an in-place mutation."""
+    if G._cflat is None:
+        import __graft_entry__
+        __graft_entry__.build()
+        import importlib
+        importlib.reload(G)
+    assert G._cflat is not None
+    total = handed_back = 0
+    for preset in ("circles_bw", "circles", "bands", "free", "default"):
+        cfg = G.make_config(2, G.NEAT_PRESETS[preset]["num_outputs"])
+        gc = cfg.genome_config
+        for evolved in (False, True):
+            for i in range(300):
+                g = G.synthetic_genome(preset, i, evolved=evolved, num_inputs=2)
+                for n_out in (None, 1, 3):
+                    want = G.flatten_genome(g, cfg, n_outputs=n_out)
+                    r = G._cflat.flatten(g, list(gc.input_keys), list(gc.output_keys), n_out)
+                    total += 1
+                    if r is None:
+                        handed_back += 1
+                    else:
+                        assert r[0] == want.to_bytes() and r[1] == want.n_slots, (preset, evolved, i, n_out)
+                    fast = G.flatten_genome_fast(g, cfg, n_outputs=n_out)
+                    assert fast.to_bytes() == want.to_bytes() and fast.n_slots == want.n_slots
+    assert 0 < handed_back < 0.05 * total
+    cfg = G.make_config(2, 3)
+    cache = G.ProgramCache()
+    gid, g = G.synthetic_population("circles", 4)[2]
+    a = cache.get(gid, g, cfg, 3).to_bytes()
+    next(iter(g.connections.values())).weight += 0.25
+    b = cache.get(gid, g, cfg, 3).to_bytes()
+    assert a != b and b == G.flatten_genome(g, cfg, n_outputs=3).to_bytes() and cache.fast == 2
+    assert G._cflat.flatten(g, [-1, -2, -3, -4], [0, 1, 2], None) is None      # four leaves: Python raises the ValueError
+    with pytest.raises(ValueError):
+        G.flatten_genome_fast(g, G.make_config(4, 3))
+
+
+def test_program_cache_hits_elites_and_sees_in_place_mutation(monkeypatch):
+    """SURVEY §8 f row 4 (Python flattener; with the C extension `get` flattens every time): unchanged genomes re-submitted
+    under the same id reuse their packed program; a genome mutated in place is re-flattened; entries of genomes that left
+    the population are dropped."""
+    monkeypatch.setattr(G, "_cflat", None)
     cfg = G.make_config(2, 3)
     pop = G.synthetic_population("circles", 24, evolved=True)
     cache = G.ProgramCache(keep=2)
