@@ -72,6 +72,8 @@ struct TcParams {
     int staging_bytes, stage_ld;  // ConvA pooling tile: 128 rows x stage_ld floats
     float inv_scale;              // 1 / (activation scale * weight scale), exact power of two
     long long* dbg;               // optional [grid][16] cycle counters per role (tests/gpu/tc_check timing mode), else null
+    int dbg_flags;                // tests/gpu/tc_check timing mode only (0 in the product): 1 = no operand loads (the MMAs run on whatever
+                                  // is in shared memory: issue + tensor-pipe pacing alone), 2 = the epilogue only hands the accumulators back
     ConvArgs ca;
 };
 
@@ -370,7 +372,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
 
     if (warp == 6) {
         // ===== activation (A) producer: hi and lo halo boxes of this CTA's region; the leader's barrier counts both CTAs =====
-        if (lane == 0) {
+        if (lane == 0 && !(p.dbg_flags & 1)) {
             int s = 0;            // ring position and phase are carried, not divided out of a counter (a runtime
             uint32_t ph = 0;      // division costs the single producer / issuer thread ~400 cycles per use)
             const uint32_t fullA_leader = map_to_cta(fullA, 0);
@@ -391,7 +393,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
         }
     } else if (warp == 4) {
         // ===== weight (B) producer: this CTA's half (Ncta/2 rows) of every tile; the leader's barrier counts both =====
-        if (lane == 0) {
+        if (lane == 0 && !(p.dbg_flags & 1)) {
             int s = 0;
             uint32_t ph = 0;
             long long b_wait = 0, b0 = TC_CLK(), bq;
@@ -450,7 +452,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                 for (int kb = 0; kb < p.KBn; ++kb) {
                     if (kb >= p.kb_skip_lo && kb < p.kb_skip_hi) continue;
                     tq = TC_CLK();
-                    mbar_wait(fullA + 8 * sa, pha);
+                    if (!(p.dbg_flags & 1)) mbar_wait(fullA + 8 * sa, pha);
                     tc_fence_after();
                     t_a += TC_CLK() - tq;
                     const uint32_t a16 = (((sA + sa * a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
@@ -459,7 +461,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                     for (int tap = 0; tap < 9; ++tap) {
                       if ((tmask >> tap) & 1u) {
                         tq = TC_CLK();
-                        mbar_wait(fullB + 8 * sb, phb);
+                        if (!(p.dbg_flags & 1)) mbar_wait(fullB + 8 * sb, phb);
                         t_b += TC_CLK() - tq;
                         tc_fence_after();
                         const uint32_t b16 = (((sB + sb * b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
@@ -540,6 +542,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
             const int set = it & 1, b = r.b, n0 = r.n0;
             const int ncols = min(p.Ncta, a.N - n0);   // the last slice may be padded up to a multiple of 32
             const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(set * acc_stride);
+            if (p.dbg_flags & 2) {
+                mbar_wait(accFull + 8 * set, (it >> 1) & 1);
+                tc_fence_after();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_relaxed(accEmpty_leader + 8 * set);
+                ++it;
+                continue;
+            }
             if (a.epi == EPI_LSTM) {
                 // Work items = (tile t, 16-column chunk c0) of this warp, walked in order.  The cell state / peephole
                 // loads of item i+1 are in flight while item i is computed, and those of the FIRST item are issued
@@ -783,6 +794,7 @@ struct TcState {
     std::string reason, last_error;
     int force_nt = 0;  // EIG_TC_NT: cap on MMA tiles per CTA region
     long long* dbg = nullptr;  // device buffer for the per-role cycle counters (tests only)
+    int dbg_flags = 0;         // TcParams::dbg_flags (tests only)
     int last_grid = 0, last_nt = 0, last_sa = 0, last_sb = 0;
     int n_sm = 148, max_pairs = 0;
     bool pdl = true;   // EIG_TC_PDL=0 disables programmatic dependent launch
@@ -1026,6 +1038,7 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream, i
     p.ca = a;
     if (g.smem > TC_SMEM_LIMIT) { s.last_error = "tc_conv: shared memory budget exceeded"; return -1; }
     p.dbg = s.dbg;
+    p.dbg_flags = s.dbg_flags;
     p.groups_per_nz = (g.regions + 1) / 2;
     p.groups = p.groups_per_nz * w.gz;
     const int n_pairs = std::min(p.groups, s.max_pairs);

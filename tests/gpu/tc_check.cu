@@ -258,7 +258,8 @@ static void time_shape(const char* name, int B, int H, int W, int pitch, int cof
 // `tc_check time c3 [passes]`: the eight convolutions of one PredNet step of BASELINE configs[2] (pop 128 colour)
 static int timing_c3(int passes) {
     g_passes = passes;
-    printf("--- workload C3 shapes (B 128, channels 3,48,96,192), MMA products mask %d\n", passes);
+    if (const char* e = getenv("EIG_TC_DBGFLAGS")) tc_state().dbg_flags = atoi(e);
+    printf("--- workload C3 shapes (B 128, channels 3,48,96,192), MMA products mask %d, debug flags %d (1 = no operand loads, 2 = no epilogue work)\n", passes, tc_state().dbg_flags);
     time_shape("A2", 128, 60, 80, 240, 0, 96, 96, EPI_CONVA, 0);
     time_shape("A3", 128, 30, 40, 480, 0, 192, 192, EPI_CONVA, 0);
     time_shape("LSTM3", 128, 15, 20, 576, 0, 576, 768, EPI_LSTM, 0);
@@ -272,6 +273,9 @@ static int timing_c3(int passes) {
 }
 
 static int timing_main() {
+    if (const char* e = getenv("EIG_TC_DBGFLAGS")) tc_state().dbg_flags = atoi(e);
+    if (const char* e = getenv("EIG_TC_PASSES")) g_passes = atoi(e);
+    printf("--- workload C2 shapes, MMA products mask %d, debug flags %d\n", g_passes, tc_state().dbg_flags);
     {
         for (int max_nt = 0; max_nt <= 0; ++max_nt) {
             printf("--- product kernel: CTA pairs, lo*hi, hi*lo (keep A), hi*hi (re-use A)\n");
