@@ -267,6 +267,32 @@ __device__ __forceinline__ void view_store4(const View& v, long long pix, int c,
     view_store4_pre(v, pix, c, val, uh, ul);
 }
 
+// 4 x 4 transpose of float4 elements across the four lanes of a quad (j = lane & 3): before, lane j holds the four float4
+// F[0..3] of ITS row; after, F[k] holds float4 number j of the row of quad lane k.  The epilogue's natural mapping is
+// lane = pixel (TMEM lane), registers = consecutive channels, so a warp-wide 16-byte access touches 32 different pixels
+// = 32 cache lines; transposed, the four lanes of a quad cover 64 contiguous bytes of one pixel and the same instruction
+// touches 8 lines.  (Measured with ncu --set full, profiles/r2: the raw-partial-sum epilogue was store-issue bound.)
+// The transpose is its own inverse, so loads use it the other way round.
+__device__ __forceinline__ float4 shfl_xor_f4(const float4 v, int m) {
+    float4 r;
+    r.x = __shfl_xor_sync(0xffffffffu, v.x, m); r.y = __shfl_xor_sync(0xffffffffu, v.y, m);
+    r.z = __shfl_xor_sync(0xffffffffu, v.z, m); r.w = __shfl_xor_sync(0xffffffffu, v.w, m);
+    return r;
+}
+__device__ __forceinline__ void quad_transpose4(float4 (&F)[4], int j) {
+    const bool b0 = (j & 1) != 0, b1 = (j & 2) != 0;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const float4 rcv = shfl_xor_f4(b0 ? F[2 * m] : F[2 * m + 1], 1);
+        if (b0) F[2 * m] = rcv; else F[2 * m + 1] = rcv;
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const float4 rcv = shfl_xor_f4(b1 ? F[m] : F[m + 2], 2);
+        if (b1) F[m] = rcv; else F[m + 2] = rcv;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 // K-major SWIZZLE_64B shared-memory matrix descriptor (rows of 64 bytes, 8-row atoms 512 bytes apart).  Measured on
 // B200 (tests/gpu/tc_check): the swizzle XOR is a function of the absolute smem address, so a start address shifted by
@@ -565,6 +591,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { pq[q] = cold; zq[q] = cold; }
                 const int Hh = p.H >> 1, Wh = p.W >> 1;
+                const int j4 = lane & 3, qb = lane & ~3;
                 auto fetch = [&](int i) {
                     nt = i / n_chunks; nc0 = half * 16 + 16 * p.egroups * (i - nt * n_chunks);
                     const int y = r.y0 + nt * p.TH + hh, x = r.x0 + ww;
@@ -573,13 +600,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                     nppix = nvalid ? (long long)y * p.W + x : 0;
                     const int r0 = (n0 + nc0) >> 2;
                     cold = *reinterpret_cast<const float4*>(a.cstate + npix * R + r0);
+                    // peephole weights and folded partial sums: 64 contiguous bytes per pixel and chunk, loaded quad-transposed
+                    // (lane j of a quad fetches float4 number j of each of the quad's four pixels; quad_transpose4 at the
+                    // point of use hands every lane its own pixel's four)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) pq[q] = *reinterpret_cast<const float4*>(a.peep + (nppix * R + r0 + q) * 4);
+                    for (int k = 0; k < 4; ++k) {
+                        const int pp_k = __shfl_sync(0xffffffffu, (int)nppix, qb + k);
+                        pq[k] = *reinterpret_cast<const float4*>(a.peep + ((long long)pp_k * R + r0 + j4) * 4);
+                    }
                     if (a.Zin) {   // folded up-sampled-R taps: [b][y/2][x/2][parity][N] partial sums of this pixel's parity
-                        const long long zpix = nvalid ? ((long long)b * Hh + (y >> 1)) * Wh + (x >> 1) : 0;
-                        const float* zp = a.Zin + (zpix * 4 + (nvalid ? (y & 1) * 2 + (x & 1) : 0)) * a.N + n0 + nc0;
+                        const int zrow = nvalid ? (int)((((long long)b * Hh + (y >> 1)) * Wh + (x >> 1)) * 4 + (y & 1) * 2 + (x & 1)) : 0;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) zq[q] = *reinterpret_cast<const float4*>(zp + q * 4);
+                        for (int k = 0; k < 4; ++k) {
+                            const int zr_k = __shfl_sync(0xffffffffu, zrow, qb + k);
+                            zq[k] = *reinterpret_cast<const float4*>(a.Zin + (long long)zr_k * a.N + n0 + nc0 + 4 * j4);
+                        }
                     }
                 };
                 if (n_items > 0) fetch(0);
@@ -598,6 +633,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
 #pragma unroll
                     for (int q = 0; q < 4; ++q) { pcur[q] = pq[q]; zcur[q] = zq[q]; }
                     if (i + 1 < n_items) fetch(i + 1);
+                    quad_transpose4(pcur, j4);
+                    if (a.Zin) quad_transpose4(zcur, j4);
                     float v[16];
                     tmem_ld_wait(racc);
 #pragma unroll
@@ -727,30 +764,48 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                 const long long pix = valid ? ((long long)b * p.H + y) * p.W + x : 0;
                 const uint32_t tcol = lane_addr + (uint32_t)(t * tile_cols);
                 if (a.epi == EPI_CONVP || a.epi == EPI_RAW) {
+                    // The accumulator chunk of the next column group is in flight while this one is stored; stores go out
+                    // quad-transposed (see quad_transpose4): lane j of a quad writes float4 number j of each of the quad's
+                    // four pixels, 64 contiguous bytes per pixel and instruction.
                     const int nP = a.nP ? a.nP : a.N;
-                    for (int c0 = half * 16; c0 < ncols; c0 += 16 * p.egroups) {
-                        float v[16];
-                        tmem_ld16(tcol + c0, v);
-                        if (!valid) continue;
+                    const int j4 = lane & 3, qb = lane & ~3;
+                    const int nchunks = ncols > half * 16 ? (ncols - half * 16 + 16 * p.egroups - 1) / (16 * p.egroups) : 0;
+                    uint32_t racc[16];
+                    if (nchunks > 0) tmem_ld16_issue(tcol + half * 16, racc);
+                    for (int ci = 0; ci < nchunks; ++ci) {
+                        const int c0 = half * 16 + ci * 16 * p.egroups;
+                        float4 F[4];
+                        tmem_ld_wait(racc);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            F[q] = make_float4(__uint_as_float(racc[q * 4]), __uint_as_float(racc[q * 4 + 1]), __uint_as_float(racc[q * 4 + 2]), __uint_as_float(racc[q * 4 + 3]));
+                        if (ci + 1 < nchunks) tmem_ld16_issue(tcol + c0 + 16 * p.egroups, racc);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int col = n0 + c0 + q * 4;
-                            if (col >= nP) {   // raw partial sums for ConvLSTM0 (see ConvArgs::outZ)
-                                *reinterpret_cast<float4*>(a.outZ + pix * (a.N - nP) + col - nP) =
-                                    make_float4(__fmul_rn(v[q * 4], inv), __fmul_rn(v[q * 4 + 1], inv), __fmul_rn(v[q * 4 + 2], inv), __fmul_rn(v[q * 4 + 3], inv));
-                                continue;
-                            }
-                            const float4 bq = a.bias ? *reinterpret_cast<const float4*>(sBias + n0 + c0 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            float o[4] = {__fadd_rn(__fmul_rn(v[q * 4], inv), bq.x), __fadd_rn(__fmul_rn(v[q * 4 + 1], inv), bq.y),
-                                          __fadd_rn(__fmul_rn(v[q * 4 + 2], inv), bq.z), __fadd_rn(__fmul_rn(v[q * 4 + 3], inv), bq.w)};
-                            if (a.epi == EPI_CONVP) {
+                            float o[4] = {__fmul_rn(F[q].x, inv), __fmul_rn(F[q].y, inv), __fmul_rn(F[q].z, inv), __fmul_rn(F[q].w, inv)};
+                            if (col < nP) {   // (columns >= nP: raw partial sums for ConvLSTM0, see ConvArgs::outZ)
+                                const float4 bq = a.bias ? *reinterpret_cast<const float4*>(sBias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                o[0] = __fadd_rn(o[0], bq.x); o[1] = __fadd_rn(o[1], bq.y); o[2] = __fadd_rn(o[2], bq.z); o[3] = __fadd_rn(o[3], bq.w);
+                                if (a.epi == EPI_CONVP) {
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    o[i] = o[i] > 0.f ? o[i] : 0.f;
-                                    if (a.clip && o[i] > 1.f) o[i] = 1.f;
+                                    for (int i = 0; i < 4; ++i) {
+                                        o[i] = o[i] > 0.f ? o[i] : 0.f;
+                                        if (a.clip && o[i] > 1.f) o[i] = 1.f;
+                                    }
                                 }
                             }
-                            *reinterpret_cast<float4*>(a.outP + pix * nP + col) = make_float4(o[0], o[1], o[2], o[3]);
+                            F[q] = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                        quad_transpose4(F, j4);
+                        const int colj = n0 + c0 + j4 * 4;      // this lane now holds columns colj .. colj+3 of the quad's four pixels
+                        float* const dst = colj >= nP ? a.outZ + (colj - nP) : a.outP + colj;
+                        const long long pitch = colj >= nP ? (long long)(a.N - nP) : (long long)nP;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const long long pix_k = __shfl_sync(0xffffffffu, pix, qb + k);
+                            const int valid_k = __shfl_sync(0xffffffffu, (int)valid, qb + k);
+                            if (valid_k && colj < n0 + ncols) *reinterpret_cast<float4*>(dst + pix_k * pitch) = F[k];
                         }
                     }
                 }
