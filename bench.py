@@ -35,6 +35,15 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU oracle of the parity gate (rank 0) would then take minutes per
+# genome.  Give each rank its share of the host cores instead - before numpy / torch load their thread pools.
+if os.environ.get("OMP_NUM_THREADS") == "1" and os.environ.get("LOCAL_WORLD_SIZE"):
+    _share = max(1, (os.cpu_count() or 1) // max(1, int(os.environ["LOCAL_WORLD_SIZE"])))
+    if os.environ.get("RANK", "0") == "0":
+        _share = max(_share, min(os.cpu_count() or 1, 16))
+    os.environ["OMP_NUM_THREADS"] = str(_share)
+    os.environ["MKL_NUM_THREADS"] = str(_share)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
