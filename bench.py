@@ -251,7 +251,7 @@ class Dist:
             dist.destroy_process_group()
 
 
-def measure(D, workload, pop, steps, warmup, scaling, conv, flush, main, parity_k, cpu_sample, from_genomes):
+def measure(D, workload, pop, steps, warmup, scaling, conv, flush, main, parity_ref, cpu_sample, from_genomes):
     """One configuration, measured on every rank; rank 0 returns the record (other ranks None)."""
     import ctypes as C
     import torch
@@ -287,14 +287,15 @@ def measure(D, workload, pop, steps, warmup, scaling, conv, flush, main, parity_
 
     # ---- parity gate, before anything is timed (rank 0)
     parity = None
-    if parity_k > 0:
+    if parity_ref is not None:
         ok = True
         if rank == 0:
-            k = min(parity_k, pop)
+            want, dt = parity_ref
+            k = min(len(want), pop)
+            want = want[:k]
             eng.evaluate_resident(resident, structure, out=fit_dev)
             torch.cuda.synchronize()
             got = fit_dev[:k].cpu().numpy()
-            want, dt = oracle_fitness(workload, 0, k, os.cpu_count() or 1)
             rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-9)
             within = int(np.sum((rel <= 1e-3) | (np.abs(got - want) <= 1e-9)))
             parity = {"checked": k, "within_1e-3": within, "ok": within == k, "max_rel_err": float(rel.max()),
@@ -480,33 +481,49 @@ def time_from_genomes(eng, genomes, cfg, c_dim, structure, steps):
 
 def run_ours(args):
     import torch
-    D = Dist()
-    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=D.dev)   # > 126 MB L2
     wl = args.workload
-    pop = args.pop or WORKLOADS[wl][6]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     scaling = args.scaling
-    if scaling == "strong":   # SURVEY.md §8 d sweep (i): the workload's population split over the ranks
-        pop = -(-pop // D.world)
-    main = measure(D, wl, pop, args.steps, args.warmup, scaling, args.conv, flush, True, args.parity,
-                   0 if args.no_cpu_baseline else (args.ref_sample or default_ref_sample(wl) * 4), True)
-    also = []
     wanted = [a for a in args.also.split(",") if a] if args.also != "auto" else None
     if wanted is None:
         wanted = []
         if wl == "c3" and scaling == "weak" and not args.pop:
             wanted.append("c2")
-            if D.world > 1:
+            if world > 1:
                 wanted.append("c3_strong")
-            if D.world == 8:
+            if world == 8:
                 wanted += ["c4", "c5"]
+    # The oracle side of every parity gate runs on rank 0 BEFORE the process group exists: NCCL's initialisation narrows
+    # the CPU affinity its caller's later OpenMP workers inherit (measured: the same 4 genomes took 1.6 s at N = 1 and
+    # 218 s at N = 2 when the oracle ran after init_process_group).
+    refs = {}
+    if int(os.environ.get("RANK", "0")) == 0 and args.parity > 0:
+        refs[wl] = oracle_fitness(wl, 0, args.parity, os.cpu_count() or 1)
+        for name in wanted:
+            if name in ("c2", "c4"):
+                refs[name] = oracle_fitness(name, 0, 2, os.cpu_count() or 1)
+    D = Dist()
+    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=D.dev)   # > 126 MB L2
+    pop = args.pop or WORKLOADS[wl][6]
+    if scaling == "strong":   # SURVEY.md §8 d sweep (i): the workload's population split over the ranks
+        pop = -(-pop // D.world)
+
+    def ref_for(name):
+        if args.parity <= 0 or (name not in refs and D.rank == 0):
+            return None
+        return refs.get(name, (None, 0.0))      # ranks > 0 only need to know that a gate runs
+
+    main = measure(D, wl, pop, args.steps, args.warmup, scaling, args.conv, flush, True, ref_for(wl),
+                   0 if args.no_cpu_baseline else (args.ref_sample or default_ref_sample(wl) * 4), True)
+    also = []
     for name in wanted:
         if name == "c3_strong":
             rec = measure(D, "c3", -(-WORKLOADS["c3"][6] // D.world), args.steps, args.warmup, "strong", args.conv, flush,
-                          False, 0, 0, False)
+                          False, None, 0, False)
         else:
             short = name == "c5"      # 1.4 s per step: keep the sub-record to a few seconds
             rec = measure(D, name, WORKLOADS[name][6], 3 if short else args.steps, 3 if short else args.warmup, "weak",
-                          args.conv, flush, False, 2 if name in ("c2", "c4") else 0, 0, False)
+                          args.conv, flush, False, ref_for(name) if name in ("c2", "c4") else None, 0, False)
         if rec is not None:
             rec["name"] = name
             also.append(rec)
