@@ -164,7 +164,7 @@ struct eig_ctx : CtxCommon {
     std::vector<void*> allocs;
 };
 enum { KIND_A = 0, KIND_P = 1, KIND_L = 2 };
-static const long long FOLD_AUTO_MIN_PIXELS = 300000;   // "fold" auto: B * H_n * W_n from which the folded form is used (measured, profiles/r2)
+static const long long FOLD_AUTO_MIN_PIXELS = 70000;   // "fold" auto: B * H_n * W_n from which the folded form is used (measured: +10 % at 16 colour genomes, neutral for 32 gray ones; profiles/r2/bench_c3_pop16_fold{0,1}_f.json)
 // Precision profiles of the tensor-core path (eig_set_option "precision"; measured in profiles/r2/pass_ablation_*.md):
 //   0 exact    : three products (a_lo*w_hi + a_hi*w_lo + a_hi*w_hi) in every convolution - fp32-grade, 2^-22 per product
 //   1 balanced : single fp16 product in the convolutions of layers 2 and 3 (ConvA2/3, ConvP2/3, ConvLSTM2/3), whose
