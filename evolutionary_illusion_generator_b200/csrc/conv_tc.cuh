@@ -338,7 +338,10 @@ __device__ __forceinline__ TcRegion tc_region(const TcParams& p, int group, int 
 //   (tcgen05.commit multicast to both CTAs), accEmpty (epilogue warps of both CTAs -> leader).
 // per-role cycle counters exist only in the DBG instantiation (tests/gpu/tc_check timing mode)
 #define TC_CLK() (DBG ? clock64() : 0ll)
-template <bool DBG>
+// FOLD: the ConvLSTM epilogue adds the folded partial sums ConvArgs::Zin (and the K-block skip / tap masks are live); the
+// plain instantiation carries none of it - the latency-bound small-population launches are sensitive to every register and
+// shuffle of the epilogue (measured on C2).
+template <bool DBG, bool FOLD = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                   const __grid_constant__ CUtensorMap mB, const TcParams p) {
@@ -406,7 +409,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
             for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
                 const TcRegion r = tc_region(p, grp, crank);
                 for (int kb = 0; kb < p.KBn; ++kb) {
-                    if (kb >= p.kb_skip_lo && kb < p.kb_skip_hi) continue;
+                    if (FOLD && kb >= p.kb_skip_lo && kb < p.kb_skip_hi) continue;
                     mbar_wait(emptyA + 8 * s, ph ^ 1);
                     // 2 CTAs x (hi plane + lo plane); a convolution that does not issue a_lo * w_hi never reads the lo plane
                     if (crank == 0) mbar_expect_tx(fullA + 8 * s, (need_alo ? 4 : 2) * p.a_box_bytes);
@@ -429,11 +432,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
             for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
                 const int nz = grp / p.groups_per_nz;
                 const int nbase = nz * p.Ncta, n0 = nbase + crank * half_rows;
-                const uint32_t tmask = p.tap_mask[nz];
+                const uint32_t tmask = FOLD ? p.tap_mask[nz] : 0x1ffu;
                 for (int kb = 0; kb < p.KBn; ++kb) {
-                    if (kb >= p.kb_skip_lo && kb < p.kb_skip_hi) continue;
+                    if (FOLD && kb >= p.kb_skip_lo && kb < p.kb_skip_hi) continue;
                     for (int tap = 0; tap < 9; ++tap) {
-                        if (!((tmask >> tap) & 1u)) continue;
+                        if (FOLD && !((tmask >> tap) & 1u)) continue;
                         bq = TC_CLK();
                         mbar_wait(emptyB + 8 * s, ph ^ 1);
                         b_wait += TC_CLK() - bq;
@@ -463,6 +466,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
             const uint32_t tile16 = (uint32_t)(p.TH * p.P * TC_ROW) >> 4;
             int sa = 0, sb = 0, it = 0;
             uint32_t pha = 0, phb = 0;
+            const int KBn = p.KBn, skip_lo = p.kb_skip_lo, skip_hi = p.kb_skip_hi;
+            const int first_kb = (FOLD && skip_lo == 0 && skip_hi > 0) ? skip_hi : 0;
+            const int last_kb = (FOLD && skip_hi >= KBn && skip_lo < skip_hi) ? skip_lo - 1 : KBn - 1;
             long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t_commit = 0, t0 = TC_CLK(), tq;
             for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
                 const int set = it & 1;
@@ -471,28 +477,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                 t_acc += TC_CLK() - tq;
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(set * acc_stride);
-                const uint32_t tmask = p.tap_mask[grp / p.groups_per_nz];
-                const int last_tap = 31 - __clz((int)tmask);
-                const int last_kb = p.kb_skip_hi >= p.KBn && p.kb_skip_lo < p.kb_skip_hi ? p.kb_skip_lo - 1 : p.KBn - 1;
-                uint32_t started = 0u;   // 0 until the first MMA of this group has been issued (it overwrites the accumulator)
-                for (int kb = 0; kb < p.KBn; ++kb) {
-                    if (kb >= p.kb_skip_lo && kb < p.kb_skip_hi) continue;
+                const uint32_t tmask = FOLD ? p.tap_mask[grp / p.groups_per_nz] : 0x1ffu;
+                const int last_tap = FOLD ? 31 - __clz((int)tmask) : 8, first_tap = FOLD ? __ffs((int)tmask) - 1 : 0;
+                for (int kb = 0; kb < KBn; ++kb) {
+                    if (FOLD && kb >= skip_lo && kb < skip_hi) continue;
                     tq = TC_CLK();
                     if (!(p.dbg_flags & 1)) mbar_wait(fullA + 8 * sa, pha);
                     tc_fence_after();
                     t_a += TC_CLK() - tq;
                     const uint32_t a16 = (((sA + sa * a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
-                    const bool two_ksteps = kb + 1 < p.KBn || p.ksteps == 2;   // a half-empty last block skips its zero k-step
+                    const bool two_ksteps = kb + 1 < KBn || p.ksteps == 2;   // a half-empty last block skips its zero k-step
                     uint32_t tap16 = 0;   // (ky * P + kx) rows of 64 bytes, in 16-byte units
                     for (int tap = 0; tap < 9; ++tap) {
-                      if ((tmask >> tap) & 1u) {
+                      if (!FOLD || ((tmask >> tap) & 1u)) {
                         tq = TC_CLK();
                         if (!(p.dbg_flags & 1)) mbar_wait(fullB + 8 * sb, phb);
                         t_b += TC_CLK() - tq;
                         tc_fence_after();
                         const uint32_t b16 = (((sB + sb * b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
-                        const uint32_t acc0 = started;
-                        started = 1u;
+                        const uint32_t acc0 = (kb != first_kb || tap != first_tap) ? 1u : 0u;   // the first MMA of a group overwrites the accumulator
                         if (elect_one()) {
                             const long long ci0 = TC_CLK();
                             // descriptor low words of this tap: everything below is adds of compile-time multiples on
@@ -600,15 +603,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                     nppix = nvalid ? (long long)y * p.W + x : 0;
                     const int r0 = (n0 + nc0) >> 2;
                     cold = *reinterpret_cast<const float4*>(a.cstate + npix * R + r0);
-                    // peephole weights and folded partial sums: 64 contiguous bytes per pixel and chunk, loaded quad-transposed
-                    // (lane j of a quad fetches float4 number j of each of the quad's four pixels; quad_transpose4 at the
-                    // point of use hands every lane its own pixel's four)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int pp_k = __shfl_sync(0xffffffffu, (int)nppix, qb + k);
-                        pq[k] = *reinterpret_cast<const float4*>(a.peep + ((long long)pp_k * R + r0 + j4) * 4);
-                    }
-                    if (a.Zin) {   // folded up-sampled-R taps: [b][y/2][x/2][parity][N] partial sums of this pixel's parity
+                    for (int q = 0; q < 4; ++q) pq[q] = *reinterpret_cast<const float4*>(a.peep + (nppix * R + r0 + q) * 4);
+                    // folded partial sums: 64 contiguous bytes per pixel and chunk, loaded quad-transposed (lane j of a quad
+                    // fetches float4 number j of each of the quad's four pixels; quad_transpose4 at the point of use hands
+                    // every lane its own pixel's four).  (The same trick on the peephole loads - L2-resident weights - cost
+                    // the latency-bound C2 epilogues 3 % and gained nothing at C3: measured, reverted.)
+                    if (FOLD && a.Zin) {   // folded up-sampled-R taps: [b][y/2][x/2][parity][N] partial sums of this pixel's parity
                         const int zrow = nvalid ? (int)((((long long)b * Hh + (y >> 1)) * Wh + (x >> 1)) * 4 + (y & 1) * 2 + (x & 1)) : 0;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -633,8 +634,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
 #pragma unroll
                     for (int q = 0; q < 4; ++q) { pcur[q] = pq[q]; zcur[q] = zq[q]; }
                     if (i + 1 < n_items) fetch(i + 1);
-                    quad_transpose4(pcur, j4);
-                    if (a.Zin) quad_transpose4(zcur, j4);
+                    if (FOLD && a.Zin) quad_transpose4(zcur, j4);
                     float v[16];
                     tmem_ld_wait(racc);
 #pragma unroll
@@ -647,10 +647,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float4 bq = *reinterpret_cast<const float4*>(sBias + n0 + c0 + q * 4);
-                        // (zcur is zero without folding: x + 0 is exact)
-                        hn[q] = lstm_cell_v(__fadd_rn(__fmul_rn(v[q * 4], inv), zcur[q].x), __fadd_rn(__fmul_rn(v[q * 4 + 1], inv), zcur[q].y),
-                                            __fadd_rn(__fmul_rn(v[q * 4 + 2], inv), zcur[q].z), __fadd_rn(__fmul_rn(v[q * 4 + 3], inv), zcur[q].w),
-                                            bq, pcur[q], co[q], &cn[q]);
+                        if (FOLD)
+                            hn[q] = lstm_cell_v(__fadd_rn(__fmul_rn(v[q * 4], inv), zcur[q].x), __fadd_rn(__fmul_rn(v[q * 4 + 1], inv), zcur[q].y),
+                                                __fadd_rn(__fmul_rn(v[q * 4 + 2], inv), zcur[q].z), __fadd_rn(__fmul_rn(v[q * 4 + 3], inv), zcur[q].w),
+                                                bq, pcur[q], co[q], &cn[q]);
+                        else
+                            hn[q] = lstm_cell_v(__fmul_rn(v[q * 4], inv), __fmul_rn(v[q * 4 + 1], inv), __fmul_rn(v[q * 4 + 2], inv),
+                                                __fmul_rn(v[q * 4 + 3], inv), bq, pcur[q], co[q], &cn[q]);
                     }
                     *reinterpret_cast<float4*>(a.cstate + pix * R + r0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
                     uint2 uh = make_uint2(0u, 0u), ul = uh;    // h goes to up to five places: split it once
@@ -874,7 +877,7 @@ inline bool tc_available() {
         return false;
     }
     s.encode = (EigEncodeTiledFn)fn;
-    if (cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv3x3_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
         s.reason = "cannot raise the dynamic shared memory limit";
         cudaGetLastError();
         return false;
@@ -1030,8 +1033,9 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream, i
     int dev = 0;
     cudaGetDevice(&dev);
     if (!s.smem_attr_set[dev]) {
-        if (cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess ||
-            cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
+        if (cudaFuncSetAttribute(conv3x3_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess ||
+            cudaFuncSetAttribute(conv3x3_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess ||
+            cudaFuncSetAttribute(conv3x3_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
             s.last_error = "tc_conv: cannot raise the dynamic shared memory limit on this device"; cudaGetLastError(); return -1;
         }
         s.smem_attr_set[dev] = true;
@@ -1048,7 +1052,7 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream, i
         int n = 0;
         cfg.gridDim = dim3(s.n_sm / 2 * 2);
         cfg.dynamicSmemBytes = TC_SMEM_LIMIT;
-        if (cudaOccupancyMaxActiveClusters(&n, conv3x3_tc_kernel<false>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = s.n_sm / 2; }
+        if (cudaOccupancyMaxActiveClusters(&n, conv3x3_tc_kernel<false, true>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = s.n_sm / 2; }
         s.max_pairs = std::min(n, s.n_sm / 2);
     }
     TcGeom g;
@@ -1100,8 +1104,12 @@ inline int tc_conv(const TcWeights& w, const ConvArgs& a, cudaStream_t stream, i
     cfg.gridDim = dim3(n_pairs * 2);
     cfg.dynamicSmemBytes = g.smem;
     s.last_grid = n_pairs * 2; s.last_nt = g.NT; s.last_sa = g.SA; s.last_sb = g.SB;
-    const cudaError_t le = s.dbg ? cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<true>, *amap[0], *amap[1], w.map, p)
-                                 : cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false>, *amap[0], *amap[1], w.map, p);
+    // the plain instantiation serves every launch without folded partial sums, K-block skip and tap masks
+    bool fold = a.Zin != nullptr || kb_skip_lo < kb_skip_hi;
+    for (int i = 0; i < w.gz; ++i) fold = fold || w.tap_mask[i] != 0x1ff;
+    const cudaError_t le = s.dbg ? cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<true, true>, *amap[0], *amap[1], w.map, p)
+                         : fold ? cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false, true>, *amap[0], *amap[1], w.map, p)
+                                : cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false, false>, *amap[0], *amap[1], w.map, p);
     if (le != cudaSuccess) { s.last_error = std::string("tc_conv launch: ") + cudaGetErrorString(le); cudaGetLastError(); return -1; }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { s.last_error = std::string("tc_conv launch: ") + cudaGetErrorString(e); return -1; }
