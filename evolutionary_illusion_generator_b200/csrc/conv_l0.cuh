@@ -270,6 +270,124 @@ __global__ void __launch_bounds__(256) l0_conva1_kernel(L0Args a, int n_items) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------- ConvA1, narrow first layers
+// One CTA per (32x8 pixel tile, genome), no persistence and no register prefetch: for C1 <= 16 (the gray BASELINE network,
+// C0 = 1, C1 = 16) the persistent kernel above needs 161 registers per thread = 3 CTAs of 128 threads per SM, and a
+// ConvA1 that is 10 % of a C2 PredNet step then runs on 12 warps per SM (measured 26-29 us for 177 MFMA).  This variant
+// stays under 80 registers (6+ CTAs per SM) and lets the block scheduler hide the global-memory latency instead.
+// Same arithmetic, same accumulation order (input channel, ky, kx; fused multiply-add) as l0_conva1_kernel.
+template <int CPT>
+__global__ void __launch_bounds__(128, 6) l0_conva1_tile_kernel(L0Args a) {
+    constexpr int SW = L0_TW + 2, SH = L0_TH + 2;
+    EIG_DYN_SMEM(smem);
+    const int cin = 2 * a.C0;
+    float* sE = reinterpret_cast<float*>(smem);                 // [2*C0][SH][SW]
+    float* sW = sE + cin * SH * SW;                             // [9][2*C0][C1pad]
+    float* sOut = sW + 9 * cin * a.C1pad;                       // [64 pooled pixels][C1pad + 1]
+    const int ldo = a.C1pad + 1;
+    const int tiles_x = (a.W + L0_TW - 1) / L0_TW;
+    const int x0 = (blockIdx.x % tiles_x) * L0_TW, y0 = (blockIdx.x / tiles_x) * L0_TH;
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < 9 * cin * a.C1pad; i += blockDim.x) sW[i] = a.wA[i];   // constants: before the wait
+    EIG_PDL_WAIT();
+    {
+        const long long img = (long long)b * a.H * a.W;
+        for (int i = threadIdx.x; i < SH * SW * a.C0; i += blockDim.x) {
+            const int c = i % a.C0, pos = i / a.C0;
+            const int cy = pos / SW, cx = pos - cy * SW;
+            const int gy = y0 + cy - 1, gx = x0 + cx - 1;
+            float ep = 0.f, en = 0.f;
+            if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+                const long long idx = (img + (long long)gy * a.W + gx) * a.C0 + c;
+                const float xv = a.x[idx], pv = a.P0[idx];
+                ep = __fsub_rn(xv, pv); en = __fsub_rn(pv, xv);
+                ep = ep > 0.f ? ep : 0.f; en = en > 0.f ? en : 0.f;
+            }
+            sE[c * SH * SW + pos] = ep;
+            sE[(a.C0 + c) * SH * SW + pos] = en;
+        }
+    }
+    __syncthreads();
+    const int pp = threadIdx.x & 63, grp = threadIdx.x >> 6;    // pooled pixel in the tile, channel group
+    const int px = pp & 15, py = pp >> 4;
+    const int n0 = grp * CPT;
+    float acc[4][CPT];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int n = 0; n < CPT; ++n) acc[j][n] = 0.f;
+    if (n0 < a.C1pad) {
+        for (int c = 0; c < cin; ++c) {
+            float in[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) in[r][q] = sE[(c * SH + 2 * py + r) * SW + 2 * px + q];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float* wrow = sW + ((ky * 3 + kx) * cin + c) * a.C1pad + n0;
+                    float wv[CPT];
+#pragma unroll
+                    for (int n = 0; n < CPT; n += 4) {
+                        const float4 q = *reinterpret_cast<const float4*>(wrow + n);
+                        wv[n] = q.x; wv[n + 1] = q.y; wv[n + 2] = q.z; wv[n + 3] = q.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int n = 0; n < CPT; ++n)
+                            acc[j][n] = __fmaf_rn(in[(j >> 1) + ky][(j & 1) + kx], wv[n], acc[j][n]);
+                }
+        }
+#pragma unroll
+        for (int n = 0; n < CPT; ++n) {
+            if (n0 + n >= a.C1) continue;
+            const float bn = a.bA[n0 + n];
+            const float m = fmaxf(fmaxf(__fadd_rn(acc[0][n], bn), __fadd_rn(acc[1][n], bn)),
+                                  fmaxf(__fadd_rn(acc[2][n], bn), __fadd_rn(acc[3][n], bn)));
+            sOut[pp * ldo + n0 + n] = fmaxf(m, 0.f);  // relu commutes with max
+        }
+    }
+    __syncthreads();
+    // error units: consecutive threads on consecutive channels of one pooled pixel (coalesced rows of the concat buffer)
+    const int Hp = a.H >> 1, Wp = a.W >> 1;
+    const long long prow = ((long long)b * Hp + (y0 >> 1)) * Wp + (x0 >> 1);
+    if ((a.C1 & 3) == 0) {
+        const int g4 = a.C1 >> 2;
+        for (int i = threadIdx.x; i < 64 * g4; i += blockDim.x) {
+            const int q = i / g4, g = i - q * g4;
+            const int gpy = (y0 >> 1) + (q >> 4), gpx = (x0 >> 1) + (q & 15);
+            if (gpy >= Hp || gpx >= Wp) continue;
+            const long long ppos = prow + (long long)(q >> 4) * Wp + (q & 15);
+            const float4 pv = *reinterpret_cast<const float4*>(a.P1 + ppos * a.C1 + 4 * g);
+            const float p4[4] = {pv.x, pv.y, pv.z, pv.w};
+            float ep[4], en[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float m = sOut[q * ldo + 4 * g + k];
+                const float d1 = __fsub_rn(m, p4[k]), d2 = __fsub_rn(p4[k], m);
+                ep[k] = d1 > 0.f ? d1 : 0.f; en[k] = d2 > 0.f ? d2 : 0.f;
+            }
+            view_store_vec4(a.dstE1, ppos, 4 * g, ep);
+            view_store_vec4(a.dstE1, ppos, a.C1 + 4 * g, en);
+        }
+    } else {
+        const int c2 = 2 * a.C1;
+        for (int i = threadIdx.x; i < 64 * c2; i += blockDim.x) {
+            const int q = i / c2, ch = i - q * c2;
+            const int gpy = (y0 >> 1) + (q >> 4), gpx = (x0 >> 1) + (q & 15);
+            if (gpy >= Hp || gpx >= Wp) continue;
+            const long long ppos = prow + (long long)(q >> 4) * Wp + (q & 15);
+            const int n = ch < a.C1 ? ch : ch - a.C1;
+            const float m = sOut[q * ldo + n], pv = a.P1[ppos * a.C1 + n];
+            const float e = ch < a.C1 ? __fsub_rn(m, pv) : __fsub_rn(pv, m);
+            view_store(a.dstE1, ppos, ch, e > 0.f ? e : 0.f);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- ConvLSTM0
 // The 3x3 taps over the nearest-neighbour up-sampled R1 are NOT evaluated here: for the four pixel parities they
 // collapse to 2x2 taps over R1 at half resolution, i.e. to one 3x3 convolution of R1 with 4 * NG output columns

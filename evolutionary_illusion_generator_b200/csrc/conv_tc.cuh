@@ -767,9 +767,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                 const long long pix = valid ? ((long long)b * p.H + y) * p.W + x : 0;
                 const uint32_t tcol = lane_addr + (uint32_t)(t * tile_cols);
                 if (a.epi == EPI_CONVP || a.epi == EPI_RAW) {
-                    // The accumulator chunk of the next column group is in flight while this one is stored; stores go out
-                    // quad-transposed (see quad_transpose4): lane j of a quad writes float4 number j of each of the quad's
-                    // four pixels, 64 contiguous bytes per pixel and instruction.
+                    // The accumulator chunk of the next column group is in flight while this one is stored.  The wide raw
+                    // partial sums (EPI_RAW: 768+ floats per pixel) go out quad-transposed (see quad_transpose4): lane j of a
+                    // quad writes float4 number j of each of the quad's four pixels, 64 contiguous bytes per pixel and
+                    // instruction (Z_1: 375 -> 245 us).  ConvP outputs keep the direct form: the same trick cost the
+                    // latency-bound C2 launches 3 % and gained nothing at C3 (measured).
                     const int nP = a.nP ? a.nP : a.N;
                     const int j4 = lane & 3, qb = lane & ~3;
                     const int nchunks = ncols > half * 16 ? (ncols - half * 16 + 16 * p.egroups - 1) / (16 * p.egroups) : 0;
@@ -799,6 +801,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
                                 }
                             }
                             F[q] = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                        if (a.epi != EPI_RAW) {   // ConvP: narrow rows, latency-bound launches - every lane stores its own pixel
+                            if (valid) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const int col = n0 + c0 + q * 4;
+                                    if (col >= n0 + ncols) continue;
+                                    if (col >= nP) *reinterpret_cast<float4*>(a.outZ + pix * (a.N - nP) + col - nP) = F[q];
+                                    else *reinterpret_cast<float4*>(a.outP + pix * nP + col) = F[q];
+                                }
+                            }
+                            continue;
                         }
                         quad_transpose4(F, j4);
                         const int colj = n0 + c0 + j4 * 4;      // this lane now holds columns colj .. colj+3 of the quad's four pixels

@@ -164,7 +164,7 @@ struct eig_ctx : CtxCommon {
     std::vector<void*> allocs;
 };
 enum { KIND_A = 0, KIND_P = 1, KIND_L = 2 };
-static const long long FOLD_AUTO_MIN_PIXELS = 70000;   // "fold" auto: B * H_n * W_n from which the folded form is used (measured: +10 % at 16 colour genomes, neutral for 32 gray ones; profiles/r2/bench_c3_pop16_fold{0,1}_f.json)
+static const long long FOLD_AUTO_MIN_WORK = 200000000LL;   // "fold" auto: B * H_n * W_n * C_n * C_{n+1} from which the folded form is used (measured: +10 % at 16 colour genomes = 3.5e8, -1.5 % at 32 gray genomes = 7.9e7; profiles/r2/bench_c3_pop16_fold{0,1}_f.json, bench_c3_*_f.json "also")
 // Precision profiles of the tensor-core path (eig_set_option "precision"; measured in profiles/r2/pass_ablation_*.md):
 //   0 exact    : three products (a_lo*w_hi + a_hi*w_lo + a_hi*w_hi) in every convolution - fp32-grade, 2^-22 per product
 //   1 balanced : single fp16 product in the convolutions of layers 2 and 3 (ConvA2/3, ConvP2/3, ConvLSTM2/3), whose
@@ -640,7 +640,11 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, bool last, cud
 #endif
             return dim3((unsigned)std::min(n_items, nsm * per_sm));
         };
-        if (c1pad <= 4) { auto k = l0_conva1_kernel<4>; LAUNCH_K_PDL(CLS_L0, k, grid_of((const void*)k, 64), dim3(64), smem, s, l0, n_items); }
+        // narrow first layers (C1 <= 16, the gray network): one CTA per tile and genome, high occupancy instead of persistence
+        const size_t smem_tile = ((size_t)2 * l0.C0 * (L0_TH + 2) * (L0_TW + 2) + (size_t)9 * 2 * l0.C0 * c1pad + (size_t)64 * (c1pad + 1) + 16) * sizeof(float);
+        if (c1pad <= 4 && smem_tile <= 48 * 1024) { auto k = l0_conva1_tile_kernel<4>; LAUNCH_K_PDL(CLS_L0, k, dim3(l0_tiles, B), dim3(64), smem_tile, s, l0); }
+        else if (c1pad <= 16 && smem_tile <= 48 * 1024) { const int th = 64 * ((c1pad + 7) / 8); auto k = l0_conva1_tile_kernel<8>; LAUNCH_K_PDL(CLS_L0, k, dim3(l0_tiles, B), dim3(th), smem_tile, s, l0); }
+        else if (c1pad <= 4) { auto k = l0_conva1_kernel<4>; LAUNCH_K_PDL(CLS_L0, k, grid_of((const void*)k, 64), dim3(64), smem, s, l0, n_items); }
         else if (c1pad <= 16) { const int th = 64 * ((c1pad + 7) / 8); auto k = l0_conva1_kernel<8>; LAUNCH_K_PDL(CLS_L0, k, grid_of((const void*)k, th), dim3(th), smem, s, l0, n_items); }
         else if (c1pad <= 48) { const int th = 64 * ((c1pad + 11) / 12); auto k = l0_conva1_kernel<12>; LAUNCH_K_PDL(CLS_L0, k, grid_of((const void*)k, th), dim3(th), smem, s, l0, n_items); }
         else { const int th = 64 * ((c1pad + 15) / 16); auto k = l0_conva1_kernel<16>; LAUNCH_K_PDL(CLS_L0, k, grid_of((const void*)k, th), dim3(th), smem, s, l0, n_items); }
@@ -687,7 +691,8 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, bool last, cud
         const int hoff_up = 2 * c->ch[n + 1] + (n + 1 < 3 ? c->ch[n + 2] : 0);
         if (!c->lw[n + 1].tcL.ok || (c->ctot[n + 1] & 7) || (c->ctot[n] & 7) || (hoff_up & 7)) return false;
         if (c->fold == 1) return true;
-        return (long long)B * c->H[n] * c->W[n] >= FOLD_AUTO_MIN_PIXELS;   // small populations are launch-bound: one more launch costs more than the MMAs it saves
+        // small problems are launch-bound: one more launch costs more than the MMAs it saves.  Work saved ~ pixels x C_n x C_{n+1}
+        return (long long)B * c->H[n] * c->W[n] * c->ch[n] * c->ch[n + 1] >= FOLD_AUTO_MIN_WORK;
     };
 #else
     auto fold_on = [&](int) { return false; };
