@@ -326,6 +326,117 @@ __device__ __forceinline__ TcRegion tc_region(const TcParams& p, int group, int 
     return r;
 }
 
+struct TcMmaCtx {
+    uint32_t tmem_base, sA, sB, fullA, emptyA, fullB, emptyB, accFull, accEmpty;
+    int pair_id, n_pairs, a_stage_bytes, b_stage_bytes, lane;
+};
+#define TC_CLK() (DBG ? clock64() : 0ll)
+// The MMA issuer of the leader CTA.  NT = MMA tiles per region, PASSES = products per k-step (7: all three with the a_hi
+// tile kept in the collector, 4: a_hi * w_hi only, 0: any subset, taken from TcParams::passes at run time - ablations).
+template <bool DBG, bool FOLD, int NT, int PASSES>
+__device__ __forceinline__ void tc_mma_role(const TcParams& p, const TcMmaCtx& mc) {
+    // kind::f16: D fp32, A/B fp16 K-major, N = Ncta, M = 256 over the pair
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Ncta >> 3) << 17) | ((256u >> 4) << 24);
+    // descriptor = {hi word: constant, lo word: (address >> 4) | LBO}; offsets are plain adds on the lo word
+    const uint64_t desc_hi = tc_smem_desc(0) & 0xffffffff00000000ull;
+    const uint32_t lo_flag = 1u << 16;
+    const uint32_t plane_a16 = (uint32_t)p.a_plane_bytes >> 4, plane_b16 = (uint32_t)p.b_plane_bytes >> 4;
+    const uint32_t tile16 = (uint32_t)(p.TH * p.P * TC_ROW) >> 4;
+    const uint32_t tile_cols = (uint32_t)p.Ncta;
+    const uint32_t acc_stride = (uint32_t)(NT * p.Ncta);
+    const uint32_t row_step16 = (uint32_t)((p.P - 2) * (TC_ROW >> 4));
+    const uint32_t passes_rt = (uint32_t)p.passes;
+    const bool wait_loads = !(p.dbg_flags & 1);
+    const bool last_block_two = p.ksteps == 2;
+    const int SA = p.SA, SB = p.SB, groups = p.groups, groups_per_nz = p.groups_per_nz;
+    int sa = 0, sb = 0, it = 0;
+    uint32_t pha = 0, phb = 0;
+    const int KBn = p.KBn, skip_lo = p.kb_skip_lo, skip_hi = p.kb_skip_hi;
+    const int first_kb = (FOLD && skip_lo == 0 && skip_hi > 0) ? skip_hi : 0;
+    const int last_kb = (FOLD && skip_hi >= KBn && skip_lo < skip_hi) ? skip_lo - 1 : KBn - 1;
+    long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t_commit = 0, t0 = TC_CLK(), tq;
+    for (int grp = mc.pair_id; grp < groups; grp += mc.n_pairs) {
+        const int set = it & 1;
+        tq = TC_CLK();
+        mbar_wait(mc.accEmpty + 8 * set, ((it >> 1) & 1) ^ 1);
+        t_acc += TC_CLK() - tq;
+        tc_fence_after();
+        const uint32_t d0 = mc.tmem_base + (uint32_t)set * acc_stride;
+        const uint32_t tmask = FOLD ? p.tap_mask[grp / groups_per_nz] : 0x1ffu;
+        const int last_tap = FOLD ? 31 - __clz((int)tmask) : 8, first_tap = FOLD ? __ffs((int)tmask) - 1 : 0;
+        for (int kb = 0; kb < KBn; ++kb) {
+            if (FOLD && kb >= skip_lo && kb < skip_hi) continue;
+            tq = TC_CLK();
+            if (wait_loads) mbar_wait(mc.fullA + 8 * sa, pha);
+            tc_fence_after();
+            t_a += TC_CLK() - tq;
+            const uint32_t a16 = (((mc.sA + sa * mc.a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
+            const bool two_ksteps = kb + 1 < KBn || last_block_two;   // a half-empty last block skips its zero k-step
+            uint32_t tap16 = 0;   // (ky * P + kx) rows of 64 bytes, in 16-byte units
+            for (int tap = 0; tap < 9; ++tap) {
+                if (!FOLD || ((tmask >> tap) & 1u)) {
+                    tq = TC_CLK();
+                    if (wait_loads) mbar_wait(mc.fullB + 8 * sb, phb);
+                    t_b += TC_CLK() - tq;
+                    tc_fence_after();
+                    const uint32_t b16 = (((mc.sB + sb * mc.b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
+                    const uint32_t acc0 = (kb != first_kb || tap != first_tap) ? 1u : 0u;   // the first MMA of a group overwrites the accumulator
+                    if (elect_one()) {
+                        const long long ci0 = TC_CLK();
+                        const uint32_t a_tap = a16 + tap16;
+                        const uint32_t bh0 = b16, bh1 = b16 + 2, bl0 = b16 + plane_b16, bl1 = b16 + plane_b16 + 2;
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) {
+                            const uint32_t at16 = a_tap + (uint32_t)t * tile16;
+                            const uint32_t d = d0 + (uint32_t)t * tile_cols;
+                            const uint64_t dah0 = desc_hi | at16, dah1 = desc_hi | (at16 + 2);
+                            const uint64_t dal0 = desc_hi | (at16 + plane_a16), dal1 = desc_hi | (at16 + plane_a16 + 2);
+                            if (PASSES == 7) {   // a_hi is fetched once per k-step: kept by the first MMA that uses it, re-used by the second
+                                tc_mma_f16_pair<0>(d, dal0, desc_hi | bh0, idesc, acc0);
+                                tc_mma_f16_pair<1>(d, dah0, desc_hi | bl0, idesc, 1u);
+                                tc_mma_f16_pair<3>(d, dah0, desc_hi | bh0, idesc, 1u);
+                                if (two_ksteps) {
+                                    tc_mma_f16_pair<0>(d, dal1, desc_hi | bh1, idesc, 1u);
+                                    tc_mma_f16_pair<1>(d, dah1, desc_hi | bl1, idesc, 1u);
+                                    tc_mma_f16_pair<3>(d, dah1, desc_hi | bh1, idesc, 1u);
+                                }
+                            } else if (PASSES == 4) {   // single product (precision profiles 1 / 2): a_hi * w_hi only
+                                tc_mma_f16_pair<0>(d, dah0, desc_hi | bh0, idesc, acc0);
+                                if (two_ksteps) tc_mma_f16_pair<0>(d, dah1, desc_hi | bh1, idesc, 1u);
+                            } else {               // other subsets of the three products (ablation, TcParams::passes)
+                                uint32_t acc = acc0;
+                                if (passes_rt & 1) { tc_mma_f16_pair<0>(d, dal0, desc_hi | bh0, idesc, acc); acc = 1u; }
+                                if (passes_rt & 2) { tc_mma_f16_pair<0>(d, dah0, desc_hi | bl0, idesc, acc); acc = 1u; }
+                                if (passes_rt & 4) { tc_mma_f16_pair<0>(d, dah0, desc_hi | bh0, idesc, acc); acc = 1u; }
+                                if (two_ksteps) {
+                                    if (passes_rt & 1) tc_mma_f16_pair<0>(d, dal1, desc_hi | bh1, idesc, 1u);
+                                    if (passes_rt & 2) tc_mma_f16_pair<0>(d, dah1, desc_hi | bl1, idesc, 1u);
+                                    if (passes_rt & 4) tc_mma_f16_pair<0>(d, dah1, desc_hi | bh1, idesc, 1u);
+                                }
+                            }
+                        }
+                        const long long ci1 = TC_CLK();
+                        tc_commit_pair(mc.emptyB + 8 * sb);
+                        if (tap == last_tap) tc_commit_pair(mc.emptyA + 8 * sa);
+                        if (tap == last_tap && kb == last_kb) tc_commit_pair(mc.accFull + 8 * set);
+                        t_issue += ci1 - ci0; t_commit += TC_CLK() - ci1;
+                    }
+                    __syncwarp();
+                    if (++sb == SB) { sb = 0; phb ^= 1; }
+                }
+                tap16 += (tap == 2 || tap == 5) ? row_step16 : (uint32_t)(TC_ROW >> 4);
+            }
+            if (++sa == SA) { sa = 0; pha ^= 1; }
+        }
+        ++it;
+    }
+    if (DBG && p.dbg && mc.lane == 0) {
+        long long* d = p.dbg + (long long)blockIdx.x * 16;
+        d[0] = TC_CLK() - t0; d[1] = t_acc; d[2] = t_a; d[3] = t_b; d[4] = it; d[14] = t_issue; d[15] = t_commit;
+    }
+}
+#undef TC_CLK
+
 // Persistent, warp-specialised: grid = 2 * min(groups, #SM / 2) CTAs of 512 threads in clusters of 2.
 //   warp  4     weight producer (one thread): this CTA's half of every per-tap weight tile, hi and lo planes
 //   warp  5     TMEM allocator; in the leader CTA also the MMA issuer (one elected thread) for BOTH CTAs
@@ -457,103 +568,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
     } else if (warp == 5) {
         if (crank == 0) {
             // ===== MMA issuer (leader CTA): the warp walks the loops together, one elected lane issues =====
-            // kind::f16: D fp32, A/B fp16 K-major, N = Ncta, M = 256 over the pair
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Ncta >> 3) << 17) | ((256u >> 4) << 24);
-            // descriptor = {hi word: constant, lo word: (address >> 4) | LBO}; offsets are plain adds on the lo word
-            const uint64_t desc_hi = tc_smem_desc(0) & 0xffffffff00000000ull;
-            const uint32_t lo_flag = 1u << 16;
-            const uint32_t plane_a16 = (uint32_t)p.a_plane_bytes >> 4, plane_b16 = (uint32_t)p.b_plane_bytes >> 4;
-            const uint32_t tile16 = (uint32_t)(p.TH * p.P * TC_ROW) >> 4;
-            int sa = 0, sb = 0, it = 0;
-            uint32_t pha = 0, phb = 0;
-            const int KBn = p.KBn, skip_lo = p.kb_skip_lo, skip_hi = p.kb_skip_hi;
-            const int first_kb = (FOLD && skip_lo == 0 && skip_hi > 0) ? skip_hi : 0;
-            const int last_kb = (FOLD && skip_hi >= KBn && skip_lo < skip_hi) ? skip_lo - 1 : KBn - 1;
-            long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t_commit = 0, t0 = TC_CLK(), tq;
-            for (int grp = pair_id; grp < p.groups; grp += n_pairs) {
-                const int set = it & 1;
-                tq = TC_CLK();
-                mbar_wait(accEmpty + 8 * set, ((it >> 1) & 1) ^ 1);
-                t_acc += TC_CLK() - tq;
-                tc_fence_after();
-                const uint32_t d0 = tmem_base + (uint32_t)(set * acc_stride);
-                const uint32_t tmask = FOLD ? p.tap_mask[grp / p.groups_per_nz] : 0x1ffu;
-                const int last_tap = FOLD ? 31 - __clz((int)tmask) : 8, first_tap = FOLD ? __ffs((int)tmask) - 1 : 0;
-                for (int kb = 0; kb < KBn; ++kb) {
-                    if (FOLD && kb >= skip_lo && kb < skip_hi) continue;
-                    tq = TC_CLK();
-                    if (!(p.dbg_flags & 1)) mbar_wait(fullA + 8 * sa, pha);
-                    tc_fence_after();
-                    t_a += TC_CLK() - tq;
-                    const uint32_t a16 = (((sA + sa * a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
-                    const bool two_ksteps = kb + 1 < KBn || p.ksteps == 2;   // a half-empty last block skips its zero k-step
-                    uint32_t tap16 = 0;   // (ky * P + kx) rows of 64 bytes, in 16-byte units
-                    for (int tap = 0; tap < 9; ++tap) {
-                      if (!FOLD || ((tmask >> tap) & 1u)) {
-                        tq = TC_CLK();
-                        if (!(p.dbg_flags & 1)) mbar_wait(fullB + 8 * sb, phb);
-                        t_b += TC_CLK() - tq;
-                        tc_fence_after();
-                        const uint32_t b16 = (((sB + sb * b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flag;
-                        const uint32_t acc0 = (kb != first_kb || tap != first_tap) ? 1u : 0u;   // the first MMA of a group overwrites the accumulator
-                        if (elect_one()) {
-                            const long long ci0 = TC_CLK();
-                            // descriptor low words of this tap: everything below is adds of compile-time multiples on
-                            // uniform registers (the loops are fully unrolled; a rolled t loop costs ~150 cycles of
-                            // dependent uniform-datapath arithmetic per k-step - measured, profiles/r1)
-                            const uint32_t a_tap = a16 + tap16;
-                            const uint32_t bh0 = b16, bh1 = b16 + 2, bl0 = b16 + plane_b16, bl1 = b16 + plane_b16 + 2;
-#pragma unroll
-                            for (int t = 0; t < TC_MAX_NT; ++t) {
-                                if (t < p.NT) {
-                                    const uint32_t at16 = a_tap + (uint32_t)t * tile16;
-                                    const uint32_t d = d0 + (uint32_t)t * (uint32_t)tile_cols;
-                                    const uint64_t dah0 = desc_hi | at16, dah1 = desc_hi | (at16 + 2);
-                                    const uint64_t dal0 = desc_hi | (at16 + plane_a16), dal1 = desc_hi | (at16 + plane_a16 + 2);
-                                    if (p.passes == 7) {   // a_hi is fetched once per k-step: kept by the first MMA that uses it, re-used by the second
-                                        tc_mma_f16_pair<0>(d, dal0, desc_hi | bh0, idesc, acc0);
-                                        tc_mma_f16_pair<1>(d, dah0, desc_hi | bl0, idesc, 1u);
-                                        tc_mma_f16_pair<3>(d, dah0, desc_hi | bh0, idesc, 1u);
-                                        if (two_ksteps) {
-                                            tc_mma_f16_pair<0>(d, dal1, desc_hi | bh1, idesc, 1u);
-                                            tc_mma_f16_pair<1>(d, dah1, desc_hi | bl1, idesc, 1u);
-                                            tc_mma_f16_pair<3>(d, dah1, desc_hi | bh1, idesc, 1u);
-                                        }
-                                    } else if (p.passes == 4) {   // single product (precision profiles 1 / 2): a_hi * w_hi only
-                                        tc_mma_f16_pair<0>(d, dah0, desc_hi | bh0, idesc, acc0);
-                                        if (two_ksteps) tc_mma_f16_pair<0>(d, dah1, desc_hi | bh1, idesc, 1u);
-                                    } else {               // other subsets of the three products (ablation, TcParams::passes)
-                                        uint32_t acc = acc0;
-                                        if (p.passes & 1) { tc_mma_f16_pair<0>(d, dal0, desc_hi | bh0, idesc, acc); acc = 1u; }
-                                        if (p.passes & 2) { tc_mma_f16_pair<0>(d, dah0, desc_hi | bl0, idesc, acc); acc = 1u; }
-                                        if (p.passes & 4) { tc_mma_f16_pair<0>(d, dah0, desc_hi | bh0, idesc, acc); acc = 1u; }
-                                        if (two_ksteps) {
-                                            if (p.passes & 1) tc_mma_f16_pair<0>(d, dal1, desc_hi | bh1, idesc, 1u);
-                                            if (p.passes & 2) tc_mma_f16_pair<0>(d, dah1, desc_hi | bl1, idesc, 1u);
-                                            if (p.passes & 4) tc_mma_f16_pair<0>(d, dah1, desc_hi | bh1, idesc, 1u);
-                                        }
-                                    }
-                                }
-                            }
-                            const long long ci1 = TC_CLK();
-                            tc_commit_pair(emptyB + 8 * sb);
-                            if (tap == last_tap) tc_commit_pair(emptyA + 8 * sa);
-                            if (tap == last_tap && kb == last_kb) tc_commit_pair(accFull + 8 * set);
-                            t_issue += ci1 - ci0; t_commit += TC_CLK() - ci1;
-                        }
-                        __syncwarp();
-                        if (++sb == p.SB) { sb = 0; phb ^= 1; }
-                      }
-                        tap16 += (tap == 2 || tap == 5) ? (uint32_t)((p.P - 2) * (TC_ROW >> 4)) : (uint32_t)(TC_ROW >> 4);
-                    }
-                    if (++sa == p.SA) { sa = 0; pha ^= 1; }
-                }
-                ++it;
+            // The loop is instantiated per (tiles per region, products per k-step): with both as run-time values ptxas
+            // re-reads the kernel parameters and re-derives predicates inside every tap (a dozen LDCU + branches per tile),
+            // which is most of the ~450 cycles a tap costs the issue thread - more than the MMAs of a tap last when there
+            // are only two of them (single-product profiles) or when N is small (profiles/r2/tc_pacing_breakdown_d.txt).
+            TcMmaCtx mc;
+            mc.tmem_base = tmem_base; mc.sA = sA; mc.sB = sB; mc.fullA = fullA; mc.emptyA = emptyA; mc.fullB = fullB; mc.emptyB = emptyB;
+            mc.accFull = accFull; mc.accEmpty = accEmpty; mc.pair_id = pair_id; mc.n_pairs = n_pairs;
+            mc.a_stage_bytes = a_stage_bytes; mc.b_stage_bytes = b_stage_bytes; mc.lane = lane;
+            const int ps = p.passes;
+#define TC_ROLE(NTV) do { if (ps == 7) tc_mma_role<DBG, FOLD, NTV, 7>(p, mc); else if (ps == 4) tc_mma_role<DBG, FOLD, NTV, 4>(p, mc); else tc_mma_role<DBG, FOLD, NTV, 0>(p, mc); } while (0)
+            switch (p.NT) {
+                case 1: TC_ROLE(1); break;
+                case 2: TC_ROLE(2); break;
+                case 3: TC_ROLE(3); break;
+                default: TC_ROLE(4); break;
             }
-            if (DBG && p.dbg && lane == 0) {
-                long long* d = p.dbg + (long long)blockIdx.x * 16;
-                d[0] = TC_CLK() - t0; d[1] = t_acc; d[2] = t_a; d[3] = t_b; d[4] = it; d[14] = t_issue; d[15] = t_commit;
-            }
+#undef TC_ROLE
         }
     } else if (warp >= 8 || (warp < 4 && p.egroups == 3)) {
         // ===== epilogue warps 8..15 =====
