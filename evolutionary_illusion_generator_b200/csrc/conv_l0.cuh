@@ -276,11 +276,11 @@ __global__ void __launch_bounds__(256) l0_conva1_kernel(L0Args a, int n_items) {
 // ConvA1 that is 10 % of a C2 PredNet step then runs on 12 warps per SM (measured 26-29 us for 177 MFMA).  This variant
 // stays under 80 registers (6+ CTAs per SM) and lets the block scheduler hide the global-memory latency instead.
 // Same arithmetic, same accumulation order (input channel, ky, kx; fused multiply-add) as l0_conva1_kernel.
-template <int CPT>
+template <int CPT, int C0>
 __global__ void __launch_bounds__(128, 6) l0_conva1_tile_kernel(L0Args a) {
-    constexpr int SW = L0_TW + 2, SH = L0_TH + 2;
+    constexpr int SW = L0_TW + 2, SH = L0_TH + 2, NPOS = SH * SW;
     EIG_DYN_SMEM(smem);
-    const int cin = 2 * a.C0;
+    constexpr int cin = 2 * C0;
     float* sE = reinterpret_cast<float*>(smem);                 // [2*C0][SH][SW]
     float* sW = sE + cin * SH * SW;                             // [9][2*C0][C1pad]
     float* sOut = sW + 9 * cin * a.C1pad;                       // [64 pooled pixels][C1pad + 1]
@@ -290,21 +290,33 @@ __global__ void __launch_bounds__(128, 6) l0_conva1_tile_kernel(L0Args a) {
     const int b = blockIdx.y;
     for (int i = threadIdx.x; i < 9 * cin * a.C1pad; i += blockDim.x) sW[i] = a.wA[i];   // constants: before the wait
     EIG_PDL_WAIT();
-    {
+    {   // halo staging, one position (all C0 channels) per thread and round; every global load of a thread is issued before
+        // the first one is used (the round count is a compile-time constant for the thread counts this kernel is launched with)
         const long long img = (long long)b * a.H * a.W;
-        for (int i = threadIdx.x; i < SH * SW * a.C0; i += blockDim.x) {
-            const int c = i % a.C0, pos = i / a.C0;
+        constexpr int ROUNDS = (NPOS + 63) / 64;                // blockDim >= 64
+        float xv[ROUNDS][C0], pv[ROUNDS][C0];
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int pos = (int)threadIdx.x + r * (int)blockDim.x;
             const int cy = pos / SW, cx = pos - cy * SW;
             const int gy = y0 + cy - 1, gx = x0 + cx - 1;
-            float ep = 0.f, en = 0.f;
-            if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-                const long long idx = (img + (long long)gy * a.W + gx) * a.C0 + c;
-                const float xv = a.x[idx], pv = a.P0[idx];
-                ep = __fsub_rn(xv, pv); en = __fsub_rn(pv, xv);
-                ep = ep > 0.f ? ep : 0.f; en = en > 0.f ? en : 0.f;
+            const bool in = pos < NPOS && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+            const long long idx = (img + (long long)gy * a.W + gx) * C0;
+#pragma unroll
+            for (int c = 0; c < C0; ++c) { xv[r][c] = in ? a.x[idx + c] : 0.f; pv[r][c] = in ? a.P0[idx + c] : 0.f; }
+        }
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int pos = (int)threadIdx.x + r * (int)blockDim.x;
+            if (pos < NPOS) {
+#pragma unroll
+                for (int c = 0; c < C0; ++c) {
+                    float ep = __fsub_rn(xv[r][c], pv[r][c]), en = __fsub_rn(pv[r][c], xv[r][c]);
+                    ep = ep > 0.f ? ep : 0.f; en = en > 0.f ? en : 0.f;
+                    sE[c * NPOS + pos] = ep;
+                    sE[(C0 + c) * NPOS + pos] = en;
+                }
             }
-            sE[c * SH * SW + pos] = ep;
-            sE[(a.C0 + c) * SH * SW + pos] = en;
         }
     }
     __syncthreads();
@@ -354,10 +366,10 @@ __global__ void __launch_bounds__(128, 6) l0_conva1_tile_kernel(L0Args a) {
     // error units: consecutive threads on consecutive channels of one pooled pixel (coalesced rows of the concat buffer)
     const int Hp = a.H >> 1, Wp = a.W >> 1;
     const long long prow = ((long long)b * Hp + (y0 >> 1)) * Wp + (x0 >> 1);
-    if ((a.C1 & 3) == 0) {
+    if ((a.C1 & 3) == 0 && (int)blockDim.x % (a.C1 >> 2) == 0) {
         const int g4 = a.C1 >> 2;
-        for (int i = threadIdx.x; i < 64 * g4; i += blockDim.x) {
-            const int q = i / g4, g = i - q * g4;
+        const int g = (int)threadIdx.x % g4, dq = (int)blockDim.x / g4;   // a thread keeps its channel group and strides over pixels
+        for (int q = (int)threadIdx.x / g4; q < 64; q += dq) {
             const int gpy = (y0 >> 1) + (q >> 4), gpx = (x0 >> 1) + (q & 15);
             if (gpy >= Hp || gpx >= Wp) continue;
             const long long ppos = prow + (long long)(q >> 4) * Wp + (q & 15);

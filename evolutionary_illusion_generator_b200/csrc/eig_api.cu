@@ -642,8 +642,14 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, bool last, cud
         };
         // narrow first layers (C1 <= 16, the gray network): one CTA per tile and genome, high occupancy instead of persistence
         const size_t smem_tile = ((size_t)2 * l0.C0 * (L0_TH + 2) * (L0_TW + 2) + (size_t)9 * 2 * l0.C0 * c1pad + (size_t)64 * (c1pad + 1) + 16) * sizeof(float);
-        if (c1pad <= 4 && smem_tile <= 48 * 1024) { auto k = l0_conva1_tile_kernel<4>; LAUNCH_K_PDL(CLS_L0, k, dim3(l0_tiles, B), dim3(64), smem_tile, s, l0); }
-        else if (c1pad <= 16 && smem_tile <= 48 * 1024) { const int th = 64 * ((c1pad + 7) / 8); auto k = l0_conva1_tile_kernel<8>; LAUNCH_K_PDL(CLS_L0, k, dim3(l0_tiles, B), dim3(th), smem_tile, s, l0); }
+        if (c1pad <= 4 && smem_tile <= 48 * 1024) {
+            if (l0.C0 == 1) { auto k = l0_conva1_tile_kernel<4, 1>; LAUNCH_K_PDL(CLS_L0, k, dim3(l0_tiles, B), dim3(64), smem_tile, s, l0); }
+            else { auto k = l0_conva1_tile_kernel<4, 3>; LAUNCH_K_PDL(CLS_L0, k, dim3(l0_tiles, B), dim3(64), smem_tile, s, l0); }
+        } else if (c1pad <= 16 && smem_tile <= 48 * 1024) {
+            const int th = 64 * ((c1pad + 7) / 8);
+            if (l0.C0 == 1) { auto k = l0_conva1_tile_kernel<8, 1>; LAUNCH_K_PDL(CLS_L0, k, dim3(l0_tiles, B), dim3(th), smem_tile, s, l0); }
+            else { auto k = l0_conva1_tile_kernel<8, 3>; LAUNCH_K_PDL(CLS_L0, k, dim3(l0_tiles, B), dim3(th), smem_tile, s, l0); }
+        }
         else if (c1pad <= 4) { auto k = l0_conva1_kernel<4>; LAUNCH_K_PDL(CLS_L0, k, grid_of((const void*)k, 64), dim3(64), smem, s, l0, n_items); }
         else if (c1pad <= 16) { const int th = 64 * ((c1pad + 7) / 8); auto k = l0_conva1_kernel<8>; LAUNCH_K_PDL(CLS_L0, k, grid_of((const void*)k, th), dim3(th), smem, s, l0, n_items); }
         else if (c1pad <= 48) { const int th = 64 * ((c1pad + 11) / 12); auto k = l0_conva1_kernel<12>; LAUNCH_K_PDL(CLS_L0, k, grid_of((const void*)k, th), dim3(th), smem, s, l0, n_items); }
