@@ -12,6 +12,9 @@ metric's "1/2/4/8 B200" sweep is quoted on - weak scaling with 128 genomes per G
   c3_strong    configs[2] split over the ranks (pop 128 / N per GPU); N > 1 only
   c4, c5       configs[3] (pop 256, bands, 320x240) and configs[4] (pop 1024, free, 512x512) - their "8xB200" shape,
                i.e. pop / 8 genomes per GPU; measured when N = 8 (or with --also c4,c5)
+  c3_precision1, c3_precision2   N = 1: the contract workload under the two OPT-IN precision profiles (fewer tensor-core
+               products per MAC; frames stay within 1 LSB, more bytes differ - profiles/r2/pass_ablation_*.md).  The
+               contract line itself always runs the exact default (three products per MAC).
 
   value    : evals/s with the flattened genomes already resident in HBM; CUDA events per step on the launching stream
              (L2 flushed between steps, untimed), max over ranks.
@@ -251,7 +254,7 @@ class Dist:
             dist.destroy_process_group()
 
 
-def measure(D, workload, pop, steps, warmup, scaling, conv, flush, main, parity_ref, cpu_sample, from_genomes):
+def measure(D, workload, pop, steps, warmup, scaling, conv, flush, main, parity_ref, cpu_sample, from_genomes, precision=None):
     """One configuration, measured on every rank; rank 0 returns the record (other ranks None)."""
     import ctypes as C
     import torch
@@ -261,6 +264,8 @@ def measure(D, workload, pop, steps, warmup, scaling, conv, flush, main, parity_
     rank, world, dev = D.rank, D.world, D.dev
     eng = E.Engine(w, h, ch, pop, device=D.local)
     eng.set_conv_mode(_lib.CONV_TC if conv == "tc" else _lib.CONV_SIMT)
+    if precision is not None:
+        eng.set_option("precision", precision)
     eng.set_grid(structure)
     eng.load_weights(workload_weights(workload))
     cfg, genomes, progs = build_population(preset, c_dim, pop, rank * pop)
@@ -442,6 +447,14 @@ def measure(D, workload, pop, steps, warmup, scaling, conv, flush, main, parity_
                    "d2h_bytes_per_step": int(8 * pop), "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
            "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "roofline": roofline, "cpu_baseline": cpu,
            "fitness_checksum": float(np.nansum(fit_host)), "nonzero_fitness_frac": float((fit_host > 0).mean())}
+    if precision is None:
+        rec["config"]["precision_profile"] = int(os.environ.get("EIG_PRECISION", "0") or 0)
+    if precision is not None:
+        rec["config"]["precision_profile"] = precision
+        rec["dtype"] = ("fp32-grade (3 split-fp16 products per MAC)", "mixed: single fp16 product in PredNet layers 2+3, 3 products in layer 1",
+                        "single fp16 product per MAC, fp32 accumulate")[precision]
+        rec["roofline"]["mma_passes"] = (3, "3 (layer 1) / 1 (layers 2, 3)", 1)[precision]
+        rec["roofline"]["frac_of_3pass_ceiling"] = None if precision else rec["roofline"]["frac_of_3pass_ceiling"]
     if gathered_check is not None:
         rec["gathered_check"] = gathered_check
     if e2e_genomes is not None:
@@ -493,6 +506,8 @@ def run_ours(args):
                 wanted.append("c3_strong")
             if world == 8:
                 wanted += ["c4", "c5"]
+            if world == 1 and args.conv == "tc":
+                wanted += ["c3_precision1", "c3_precision2"]
     # The oracle side of every parity gate runs on rank 0 BEFORE the process group exists: NCCL's initialisation narrows
     # the CPU affinity its caller's later OpenMP workers inherit (measured: the same 4 genomes took 1.6 s at N = 1 and
     # 218 s at N = 2 when the oracle ran after init_process_group).
@@ -520,6 +535,9 @@ def run_ours(args):
         if name == "c3_strong":
             rec = measure(D, "c3", -(-WORKLOADS["c3"][6] // D.world), args.steps, args.warmup, "strong", args.conv, flush,
                           False, None, 0, False)
+        elif name.startswith("c3_precision"):   # the opt-in precision profiles, same population and gate as the contract line
+            rec = measure(D, "c3", WORKLOADS["c3"][6], args.steps, args.warmup, "weak", args.conv, flush, False,
+                          ref_for("c3") if wl == "c3" else None, 0, False, precision=int(name[-1]))
         else:
             short = name == "c5"      # 1.4 s per step: keep the sub-record to a few seconds
             rec = measure(D, name, WORKLOADS[name][6], 3 if short else args.steps, 3 if short else args.warmup, "weak",

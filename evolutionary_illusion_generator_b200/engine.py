@@ -210,6 +210,21 @@ class Engine:
         chunk = max(-(-chunk // 8) * 8, -(-n // 8))
         return min(max(chunk, 1), max(n, 1))
 
+    def _staging(self, k, blob_bytes, n_offsets):
+        """Pinned host + device buffers of chunk index k, grown geometrically."""
+        if not hasattr(self, "_stage"):
+            self._stage = []
+        while len(self._stage) <= k:
+            self._stage.append(None)
+        st = self._stage[k]
+        if st is None or st[0].numel() < blob_bytes or st[1].numel() < n_offsets:
+            cb = max(2 * blob_bytes, 1 << 16)
+            co = max(2 * n_offsets, 1 << 10)
+            st = (torch.empty((cb,), dtype=torch.uint8).pin_memory(), torch.empty((co,), dtype=torch.int64).pin_memory(),
+                  torch.empty((cb,), dtype=torch.uint8, device=self.tdev), torch.empty((co,), dtype=torch.int64, device=self.tdev))
+            self._stage[k] = st
+        return st
+
     def evaluate_streamed(self, items, flatten, structure, render_mode=RENDER_GRADIENT,
                           pair_mode=_lib.PAIR_POPULATION, chunk=None):
         """[(genome_id, genome)] -> device fp64 fitness tensor (a view of an engine-owned buffer), with the host-side
@@ -236,11 +251,16 @@ class Engine:
             blob, offsets, max_slots = G.pack_population(progs)
             max_blob = int(np.diff(offsets).max())
             if cuda:
-                hb, ho = torch.from_numpy(blob).pin_memory(), torch.from_numpy(offsets).pin_memory()
+                # pinned staging and device copies are kept per chunk index and re-used by later calls (the previous call
+                # ended with a synchronisation): cudaHostAlloc per generation cost more than the flattening itself
+                hb, ho, db, do = self._staging(len(keep), blob.nbytes, offsets.size)
+                hb[:blob.nbytes].copy_(torch.from_numpy(blob))
+                ho[:offsets.size].copy_(torch.from_numpy(offsets))
                 with torch.cuda.stream(self._up_stream):
-                    db, do = hb.to(self.tdev, non_blocking=True), ho.to(self.tdev, non_blocking=True)
+                    db[:blob.nbytes].copy_(hb[:blob.nbytes], non_blocking=True)
+                    do[:offsets.size].copy_(ho[:offsets.size], non_blocking=True)
                 ev.wait_stream(self._up_stream)
-                keep.append((hb, ho, db, do))               # alive until the final synchronisation
+                keep.append((hb, ho, db, do))
                 stream = C.c_void_p(ev.cuda_stream)
             else:
                 db, do = torch.from_numpy(blob), torch.from_numpy(offsets)

@@ -1,0 +1,9 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out/j14
+O=gpurun_out/j14
+timeout 900 python bench.py --steps 20 --warmup 5 > $O/bench_c3.json 2> $O/bench_c3.err
+tail -3 $O/bench_c3.err
+timeout 600 python bench.py --workload c2 --steps 100 --warmup 5 --also '' --no-cpu-baseline > $O/bench_c2_main.json 2> $O/bench_c2_main.err
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3 > $O/pytest_gpu.txt
+ls -la $O
