@@ -23,6 +23,7 @@ SYMBOLS = [
     ("eig_version", _I, []),
     ("eig_launch_count", C.c_int64, []),
     ("eig_create", _I, [C.POINTER(_P), _I, _I, _I, _I, C.POINTER(_I), _I]),
+    ("eig_create_render", _I, [C.POINTER(_P), _I, _I, _I, _I, _I]),
     ("eig_destroy", None, [_P]),
     ("eig_set_conv_mode", _I, [_P, _I]),
     ("eig_load_weights", _I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(C.c_int64)]),

@@ -106,6 +106,7 @@ struct eig_ctx : CtxCommon {
     int H[4], W[4], ctot[4];
     int conv_mode = EIG_CONV_SIMT;
     bool have_w = false, have_grid = false;
+    bool render_only = false;        // eig_create_render: only the CPPN stage (grid planes, image, input frame) exists
     double *xmat = nullptr, *ymat = nullptr;
     LayerW lw[4];
     // activations
@@ -226,6 +227,32 @@ extern "C" int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, co
     c->device = device;
     const int rc = create_buffers(c, w, h, c_dim, channels, max_genomes);
     if (rc != EIG_OK) { g_cur = sc.prev; eig_destroy(c); return rc; }   // nothing of a half-built context survives (e.g. out of memory)
+    *out = c;
+    return EIG_OK;
+}
+
+// A context for the CPPN stage alone (`get_image_from_cppn` / the 800x800 `enhanced.png` mosaic, generate_illusion.py:
+// 372-460, 664-671): no PredNet, no flow, hence none of their size rules (any w, h > 0).
+extern "C" int eig_create_render(eig_ctx** out, int device, int w, int h, int c_dim, int max_genomes) {
+    if (!out || max_genomes <= 0 || w <= 0 || h <= 0) return fail(EIG_E_INVALID, "eig_create_render: null/invalid argument");
+    if (c_dim != 1 && c_dim != 3) return fail(EIG_E_INVALID, "eig_create_render: c_dim must be 1 or 3");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(EIG_E_NODEVICE, "eig_create_render: no CUDA device visible; this engine has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(EIG_E_INVALID, "eig_create_render: bad device index");
+    CK(cudaSetDevice(device));
+    eig_ctx* c = new eig_ctx();
+    Scope sc(c);
+    c->device = device; c->render_only = true;
+    c->w = w; c->h = h; c->c_dim = c_dim; c->cap = max_genomes; c->ch[0] = c_dim;
+    const size_t npx = (size_t)max_genomes * w * h;
+    cudaError_t e = dalloc(c, &c->x_in, npx * c_dim);
+    if (e == cudaSuccess) e = dalloc(c, &c->img, npx * c_dim);
+    if (e == cudaSuccess) e = dalloc(c, &c->xmat, (size_t)w * h);
+    if (e == cudaSuccess) e = dalloc(c, &c->ymat, (size_t)w * h);
+    if (e == cudaSuccess) e = dalloc(c, &c->d_off, (size_t)max_genomes + 1);
+    if (e != cudaSuccess) { g_cur = sc.prev; eig_destroy(c); return fail(EIG_E_CUDA, std::string("eig_create_render: ") + cudaGetErrorString(e)); }
+    c->use_graphs = false; c->overlap = false;
     *out = c;
     return EIG_OK;
 }
@@ -444,6 +471,7 @@ void build_z_weights(std::vector<float>& dst, int npad, int C1, const std::vecto
 extern "C" int eig_load_weights(eig_ctx* c, int nt, const char* const* names, const float* const* ptrs, const int64_t* shapes) {
     Scope sc(c);
     if (!c || !names || !ptrs || !shapes || nt <= 0) return fail(EIG_E_INVALID, "eig_load_weights: null argument");
+    if (c->render_only) return fail(EIG_E_STATE, "eig_load_weights: render-only context");
     CK(cudaSetDevice(c->device));
     CK(cudaDeviceSynchronize());   // no evaluation may still be reading the old weights
     drop_graphs(c);
@@ -828,8 +856,9 @@ static int prednet_sequence(eig_ctx* c, const float* d_x, int B, int n_in, int n
     return join_side(c, s);
 }
 
-static int check_ready(eig_ctx* c, int n, bool need_w, bool need_grid) {
+static int check_ready(eig_ctx* c, int n, bool need_w, bool need_grid, bool render_call = false) {
     if (!c) return fail(EIG_E_INVALID, "null ctx");
+    if (c->render_only && !render_call) return fail(EIG_E_STATE, "this context was made by eig_create_render: it only renders");
     if (n <= 0) return fail(EIG_E_INVALID, "n must be positive");
     if (n > c->cap) return fail(EIG_E_CAPACITY, "population larger than max_genomes given to eig_create");
     if (need_w && !c->have_w) return fail(EIG_E_STATE, "PredNet weights not loaded (eig_load_weights)");
@@ -841,7 +870,7 @@ extern "C" int eig_cppn_render(eig_ctx* c, const void* d_blob, const int64_t* d_
                                int max_blob_bytes, int mode, double bg, uint8_t* d_img, float* d_x, void* stream) {
     Scope sc(c);
     int rc;
-    if ((rc = check_ready(c, n, false, true))) return rc;
+    if ((rc = check_ready(c, n, false, true, true))) return rc;
     if (!d_blob || !d_offsets || !d_img) return fail(EIG_E_INVALID, "eig_cppn_render: null pointer");
     if (mode < 0 || mode > 2) return fail(EIG_E_INVALID, "eig_cppn_render: mode must be 0, 1 or 2");
     CK(cudaSetDevice(c->device));

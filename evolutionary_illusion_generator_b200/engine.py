@@ -24,11 +24,14 @@ def render_mode_for(c_dim, gradient):
 
 
 class Engine:
-    def __init__(self, w, h, channels, max_genomes, device=None, lib=None, tensor_device=None):
+    def __init__(self, w, h, channels, max_genomes, device=None, lib=None, tensor_device=None, render_only=False):
+        """render_only: a context for the CPPN stage alone (`eig_create_render`): `channels` only supplies c_dim, any
+        image size works, and only set_grid / render are available."""
         self.w, self.h = int(w), int(h)
         self.channels = [int(c) for c in channels]
         self.c_dim = self.channels[0]
         self.max_genomes = int(max_genomes)
+        self.render_only = bool(render_only)
         if lib is None:
             lib = _lib.get_library()
             if not torch.cuda.is_available():
@@ -43,7 +46,10 @@ class Engine:
         self.dev_index = dev_index
         ctx = C.c_void_p()
         ch = (C.c_int * 4)(*self.channels)
-        lib.check(lib.eig_create(C.byref(ctx), dev_index, self.w, self.h, self.c_dim, ch, self.max_genomes))
+        if self.render_only:
+            lib.check(lib.eig_create_render(C.byref(ctx), dev_index, self.w, self.h, self.c_dim, self.max_genomes))
+        else:
+            lib.check(lib.eig_create(C.byref(ctx), dev_index, self.w, self.h, self.c_dim, ch, self.max_genomes))
         self.ctx = ctx
         self._grid_key = None
         self.structure = None

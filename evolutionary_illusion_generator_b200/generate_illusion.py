@@ -39,7 +39,7 @@ def get_image_from_cppn(inputs, genome, c_dim, w, h, config, bg=1, gradient=1, e
     if eng is None:    # a cached render-only context (tiny PredNet channels: only the CPPN kernel runs), one per image size
         key = (w, h, c_dim, "planes")
         if key not in _render_engines:
-            _render_engines[key] = runtime.engine_factory(w, h, (c_dim, 4, 4, 4), 1)
+            _render_engines[key] = runtime.render_engine_factory(w, h, c_dim, 1)
         eng = _render_engines[key]
     eng.set_grid(grid=inputs)
     prog = G.flatten_genome_fast(genome, config, n_outputs=_used_outputs(c_dim))
@@ -94,7 +94,7 @@ def _render_engine(w, h, c_dim, structure):
     grid planes are uploaded once per structure."""
     key = (w, h, c_dim, int(structure))
     if key not in _render_engines:
-        eng = runtime.engine_factory(w, h, (c_dim, 4, 4, 4), 1)
+        eng = runtime.render_engine_factory(w, h, c_dim, 1)
         eng.set_grid(grid=enhanced_image_grid(w, h, structure))
         _render_engines[key] = eng
     return _render_engines[key]

@@ -20,6 +20,14 @@ _engines = {}
 engine_factory = engine_mod.Engine   # (w, h, channels, max_genomes) -> Engine; the CPU tests bind the host-compiled library here
 
 
+def render_engine_factory(w, h, c_dim, max_genomes):
+    """A render-only engine (eig_create_render: CPPN stage alone, any image size) from the same factory."""
+    try:
+        return engine_factory(w, h, (c_dim, 4, 4, 4), max_genomes, render_only=True)
+    except TypeError:          # a test double without the keyword
+        return engine_factory(w, h, (c_dim, 4, 4, 4), max_genomes)
+
+
 def conv_policy():
     """EIG_CONV = auto | tc | simt (default auto): which convolution engine the drop-in entry points use.
     auto: the tcgen05 path; the exact-fp32 SIMT path when the library / device has no tensor-core path, and for the rest of

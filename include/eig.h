@@ -48,6 +48,9 @@ int64_t eig_launch_count(void);
 /* Replaces `net.PredNet(w, h, channels)` + per-call buffer setup (call_prednet.py:209-231).
  * channels[4] = PredNet channels per layer, c_dim = channels[0] (1 or 3); w, h divisible by 8. */
 int eig_create(eig_ctx** out, int device, int w, int h, int c_dim, const int channels[4], int max_genomes);
+/* A context for `get_image_from_cppn` alone (generate_illusion.py:372-460; the 800x800 `enhanced.png` mosaic, 664-671):
+ * only eig_set_grid and eig_cppn_render work on it (everything else returns EIG_E_STATE); any w, h > 0. */
+int eig_create_render(eig_ctx** out, int device, int w, int h, int c_dim, int max_genomes);
 void eig_destroy(eig_ctx* ctx);
 
 /* conv_mode: EIG_CONV_SIMT / EIG_CONV_TC.  Returns EIG_E_INVALID if the mode is not compiled in. */

@@ -44,7 +44,7 @@ def _worker(rank, world, port, n, out_dir):
     # the whole drop-in call under torch.distributed: every rank ends with the same genome.fitness, rank 0 alone writes files
     from evolutionary_illusion_generator_b200 import generate_illusion as GI
     emu = _lib.EigLibrary(EMU_SO)
-    runtime.engine_factory = lambda w_, h_, ch_, n_: E.Engine(w_, h_, ch_, n_, lib=emu)
+    runtime.engine_factory = lambda w_, h_, ch_, n_, **kw: E.Engine(w_, h_, ch_, n_, lib=emu, **kw)
     GI.ENHANCED_SIZE = 64
     model = os.path.join(out_dir, "model_%d.npz" % rank)
     W.save_npz(model, W.synthetic_weights(w, h, ch, seed=2))

@@ -215,7 +215,7 @@ def test_get_fitnesses_neat_on_the_host_compiled_library_vs_the_reference(emu_li
     from PIL import Image
     from conftest import GOLDEN
     from evolutionary_illusion_generator_b200 import generate_illusion as GI, runtime
-    monkeypatch.setattr(runtime, "engine_factory", lambda w, h, ch, n: E.Engine(w, h, ch, n, lib=emu_lib))
+    monkeypatch.setattr(runtime, "engine_factory", lambda w, h, ch, n, **kw: E.Engine(w, h, ch, n, lib=emu_lib, **kw))
     monkeypatch.setattr(runtime, "_engines", {})
     monkeypatch.setattr(GI, "_render_engines", {})
     monkeypatch.setattr(GI, "ENHANCED_SIZE", 64)            # the 800x800 mosaic is slow in the emulator
@@ -254,7 +254,7 @@ def test_single_image_rating_on_the_host_compiled_library_vs_the_reference(emu_l
     from PIL import Image
     from conftest import GOLDEN
     from evolutionary_illusion_generator_b200 import fitness_calculator as FC, generate_illusion as GI, runtime
-    monkeypatch.setattr(runtime, "engine_factory", lambda w, h, ch, n: E.Engine(w, h, ch, n, lib=emu_lib))
+    monkeypatch.setattr(runtime, "engine_factory", lambda w, h, ch, n, **kw: E.Engine(w, h, ch, n, lib=emu_lib, **kw))
     monkeypatch.setattr(runtime, "_engines", {})
     z = np.load(os.path.join(GOLDEN, "reference_single_image.npz"))
     m = json.loads(str(z["meta"]))[0]
@@ -287,3 +287,21 @@ def test_error_text_and_options_belong_to_the_context(emu_lib):
     for key, v in ((b"passes.all", 7), (b"passes.L", 6), (b"passes.A2", 5), (b"early_until", 3), (b"early_mask", 4), (b"graphs", 0)):
         assert emu_lib.eig_set_option(a.ctx, key, v) == 0, key
     a.close(); b.close()
+
+
+def test_render_only_context(emu_lib):
+    """eig_create_render: the CPPN stage alone, for `get_image_from_cppn` and the enhanced mosaic - any image
+    size (here 30 x 22, not a multiple of 8 and below the LK window), bytes equal to the oracle, everything else refused."""
+    w, h = 30, 22
+    eng = E.Engine(w, h, (3, 4, 4, 4), 2, lib=emu_lib, render_only=True)
+    grid = OG.create_grid(2, w, h, 10)
+    eng.set_grid(grid=grid)
+    cfg = G.make_config(2, 3)
+    pop = [G.synthetic_genome("circles", i, evolved=True) for i in (3, 4)]
+    img, x = eng.render([G.flatten_genome(g, cfg, n_outputs=3) for g in pop])
+    gc = cfg.genome_config
+    for k, g in enumerate(pop):
+        assert np.array_equal(img[k].numpy(), OC.render(grid, g, 3, w, h, gc.input_keys, gc.output_keys))
+    assert emu_lib.eig_prednet_reset(eng.ctx, 1, None) == _lib_mod.EIG_E_STATE
+    assert b"only renders" in emu_lib.eig_error(eng.ctx)
+    eng.close()
