@@ -136,6 +136,10 @@ def evaluate_genomes(eng, population, flatten, structure, render_mode=engine_mod
     if n == 0:
         return np.zeros((0,), dtype=np.float64)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if (chunk is None and eng.stream_chunk(n) >= n) or (chunk is not None and chunk >= n):
+            # one chunk: nothing to overlap - flatten, then the host entry point (one H2D, kernels, one D2H, one synchronisation)
+            progs = [flatten(gid, g) for gid, g in population]
+            return with_range_fallback(eng, lambda: eng.evaluate(progs, structure, render_mode, pair_mode))
         return with_range_fallback(
             eng, lambda: eng.evaluate_streamed(population, flatten, structure, render_mode, pair_mode, chunk)).cpu().numpy()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
