@@ -124,6 +124,7 @@ struct eig_ctx : CtxCommon {
     // copy of R_{n+1}.  -22 % of the MMAs of ConvLSTM1/2.
     float* Zf[3] = {nullptr, nullptr, nullptr};
     int fold = -1;                   // eig_set_option "fold": 0 off, 1 on wherever the shapes allow, -1 auto (by population size)
+    bool skip_zero_state = true;     // eig_set_option "skip_zero_state": step 0 skips the K blocks that only hold the zero state
     int npz = 0;                     // columns of the layer-1 ConvP+Z convolution: C1 + 16*C0
     float* x_in = nullptr;           // [B][h][w][c]
     unsigned char* img = nullptr;    // rendered [B][h][w][c]
@@ -369,6 +370,7 @@ extern "C" int eig_set_option(eig_ctx* c, const char* key, int value) {
         if (value < 0 || value > 2) return fail(EIG_E_INVALID, "eig_set_option: precision must be 0 (exact), 1 (balanced) or 2 (fast)");
         apply_precision(c, value); ok = true;
     }
+    else if (k == "skip_zero_state") { c->skip_zero_state = value != 0; ok = true; }
     else if (k == "fold") { c->fold = value < 0 ? -1 : (value != 0); ok = true; }
     else if (k == "simt_reverse_taps") { c->simt_reverse_taps = value != 0; ok = true; }
     else if (k == "graphs") { c->use_graphs = value != 0; ok = true; }
@@ -630,6 +632,7 @@ static L0Args l0_args(eig_ctx* c, const float* x, int B, int cur, int nxt) {
 // `last`: no step follows, so the predictions P_2 / P_3 (only read by the next step's error units) are not computed
 static int prednet_step(eig_ctx* c, const float* x, int B, int t, bool last, cudaStream_t s) {
     const int cur = t & 1, nxt = cur ^ 1;
+    const bool first_step = t == 0 && c->skip_zero_state;   // every caller resets the state right before step 0
     const bool tc = c->conv_mode == EIG_CONV_TC;
     const bool side_ok = c->overlap && !prof_on();   // the per-class profiler times launches on one stream
     int rc;
@@ -697,7 +700,15 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, bool last, cud
         a.epi = EPI_CONVA; a.P = c->P[n];
         a.dstE = mkview(c->X[n][cur], lo_plane(c, n, c->X[n][cur]), c->ctot[n], 0, 2 * c->ch[n]);
 #ifndef EIG_EMU
-        if (tc && c->lw[n].tcA.ok && tc_view_ok(a)) { prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcA, a, s, passes_for(c, KIND_A, n, t), &c->amaps); prof_post(s); EIG_COUNT_LAUNCH(); if (rc) return fail(EIG_E_CUDA, "tc_conv ConvA: " + tc_last_error()); continue; }
+        if (tc && c->lw[n].tcA.ok && tc_view_ok(a)) {
+            // step 0 of a sequence: P_{n-1} is still the zero state, so E-_{n-1} = relu(P - A) is exactly zero (A >= 0):
+            // the K blocks that only hold E- contribute exact zeros and are skipped (bit-identical result)
+            int skip_lo = 0, skip_hi = 0;
+            if (first_step) { skip_lo = (c->ch[n - 1] + TC_KB - 1) / TC_KB; skip_hi = c->lw[n].tcA.KBn; }
+            prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcA, a, s, passes_for(c, KIND_A, n, t), &c->amaps, skip_lo, skip_hi); prof_post(s); EIG_COUNT_LAUNCH();
+            if (rc) return fail(EIG_E_CUDA, "tc_conv ConvA: " + tc_last_error());
+            continue;
+        }
 #endif
         if ((rc = launch_conv(c, a, s))) return rc;
     }
@@ -748,6 +759,13 @@ static int prednet_step(eig_ctx* c, const float* x, int B, int t, bool last, cud
         if (tc && c->lw[n].tcL.ok && tc_view_ok(a)) {
             int skip_lo = 0, skip_hi = 0;
             if (fold_here) { a.Zin = c->Zf[n]; skip_lo = 2 * c->ch[n] / TC_KB; skip_hi = (2 * c->ch[n] + c->ch[n + 1]) / TC_KB; }
+            if (first_step) {
+                // step 0: E-_n (P_n is the zero state) and h_n (the zero state) are exactly zero.  With the up-sampled slice
+                // folded away (or absent: layer 3) everything behind E+_n goes; otherwise only the h tail can (one range).
+                const int kbn = c->lw[n].tcL.KBn;
+                if (fold_here || n == 3) { skip_lo = (c->ch[n] + TC_KB - 1) / TC_KB; skip_hi = kbn; }
+                else if ((2 * c->ch[n] + c->ch[n + 1]) % TC_KB == 0) { skip_lo = (2 * c->ch[n] + c->ch[n + 1]) / TC_KB; skip_hi = kbn; }
+            }
             prof_pre(CLS_CONV_TC, s); rc = tc_conv(c->lw[n].tcL, a, s, passes_for(c, KIND_L, n, t), &c->amaps, skip_lo, skip_hi); prof_post(s); EIG_COUNT_LAUNCH();
             if (rc) return fail(EIG_E_CUDA, "tc_conv ConvLSTM: " + tc_last_error());
             if (fold_below) {   // Z_{n-1}: the tap-masked half-resolution convolution of the h_n just written, raw fp32 partial sums

@@ -60,7 +60,11 @@ int eig_set_conv_mode(eig_ctx* ctx, int conv_mode);
  *   "passes.all" | "passes.A" | "passes.P" | "passes.L" | "passes.<A|P|L><1..3>" : which of the three split-fp16 MMA products
  *        a convolution issues per k-step (bit 0 a_lo*w_hi, bit 1 a_hi*w_lo, bit 2 a_hi*w_hi; default 7 = all, the setting
  *        the parity tests pin; profiles/r2/pass_ablation.md has the measured cost of every cheaper mix);
+ *   "precision" 0/1/2 : preset of those masks (0 exact, the default; 1 single product in layers 2+3; 2 single product everywhere);
  *   "early_until" = T, "early_mask" = m : PredNet steps t < T use (mask & m);
+ *   "fold" -1/0/1 : folded form of the ConvLSTM taps over up-sampled states (auto by problem size / off / on);
+ *   "skip_zero_state" 0/1 : step 0 skips the K blocks that only hold the zero state (bit-identical, default on);
+ *   "simt_reverse_taps" 0/1 : exact-fp32 kernel sums the taps in reverse order (the ablation's yardstick);
  *   "graphs" 0/1 : CUDA-graph replay of everything after the render; "overlap" 0/1 : ConvP2/3 on the side stream.
  * Synchronises the device and drops captured graphs. */
 int eig_set_option(eig_ctx* ctx, const char* key, int value);

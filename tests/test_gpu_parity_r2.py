@@ -122,6 +122,31 @@ def test_folded_upsampled_taps_match_unfolded(gpu_engine_factory, workload):
     assert mx <= 1 and frac < 1e-4
 
 
+@pytest.mark.parametrize("workload", ["c2", "c3"])
+def test_zero_state_skip_is_bit_identical(gpu_engine_factory, workload):
+    """Step 0 of a sequence skips the K blocks that only hold the zero state (E- with P = 0, h = 0): exact zeros, so frames
+    and fitness must not change by a single bit, folded or not."""
+    preset, c, ch = ("circles_bw", 1, (1, 16, 32, 64)) if workload == "c2" else ("circles", 3, (3, 48, 96, 192))
+    w, h, n = 160, 120, 8
+    eng = gpu_engine_factory(w, h, ch, n)
+    eng.set_conv_mode(_lib.CONV_TC)
+    eng.set_option("precision", 0)
+    eng.set_grid(1)
+    eng.load_weights(W.synthetic_predictor_weights(w, h, ch, seed=0))
+    progs = _progs(preset, c, range(70, 70 + n))
+    for fold in (0, 1):
+        eng.set_option("fold", fold)
+        out = {}
+        for skip in (0, 1):
+            eng.set_option("skip_zero_state", skip)
+            f = eng.evaluate(progs, 1)
+            out[skip] = (f, eng.debug_buffers(n)["frames"].copy())
+        assert np.array_equal(out[0][0], out[1][0], equal_nan=True), (workload, fold)
+        assert np.array_equal(out[0][1], out[1][1]), (workload, fold)
+    eng.set_option("fold", -1)
+    eng.set_option("skip_zero_state", 1)
+
+
 def test_precision_profiles_stay_within_one_lsb(gpu_engine_factory):
     """eig_set_option("precision"): 0 exact (3 products everywhere), 1 balanced (single product in layers 2 and 3),
     2 fast (single product everywhere).  Against the exact-fp32 path on 32 C3 genomes: frames never differ by more than
