@@ -328,3 +328,30 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "NEAT genome fitness evals/sec" in d["metric"]
+
+
+def test_fold_algebra_of_the_upsampled_taps():
+    """The identity behind `eig_ctx::Zf` / `build_fold_weights` (csrc/eig_api.cu): a 3x3 cross-correlation (pad 1) over a
+    nearest-neighbour x2 up-sampled tensor equals, per output-pixel parity (py, px), a 2x2 cross-correlation of the
+    half-resolution tensor whose taps are sums of the original ones - low-resolution offsets {-1, 0, 0} for parity 0 and
+    {0, 0, +1} for parity 1 along each axis - so each parity uses 4 of the 9 low-resolution taps (`fold_tap_mask`)."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.RandomState(0)
+    C, N, H, W = 5, 7, 6, 8
+    r = torch.from_numpy(rng.randn(1, C, H, W))
+    wgt = torch.from_numpy(rng.randn(N, C, 3, 3))
+    up = r.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+    want = F.conv2d(up, wgt, padding=1)                                   # [1, N, 2H, 2W]
+    low_off = {0: (-1, 0, 0), 1: (0, 0, 1)}
+    got = torch.zeros_like(want)
+    for py in (0, 1):
+        for px in (0, 1):
+            folded = torch.zeros(N, C, 3, 3, dtype=torch.float64)
+            for ky in range(3):
+                for kx in range(3):
+                    folded[:, :, low_off[py][ky] + 1, low_off[px][kx] + 1] += wgt[:, :, ky, kx]
+            used = {(low_off[py][ky] + 1) * 3 + (low_off[px][kx] + 1) for ky in range(3) for kx in range(3)}
+            assert len(used) == 4 and all(folded.reshape(N, C, 9)[:, :, t].abs().sum() == 0 for t in range(9) if t not in used)
+            got[:, :, py::2, px::2] = F.conv2d(r, folded, padding=1)      # the tap-masked half-resolution convolution
+    assert torch.allclose(got, want, rtol=1e-12, atol=1e-12)
