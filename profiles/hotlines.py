@@ -1,3 +1,12 @@
+#!/usr/bin/env python
+"""Hottest SASS lines of a kernel from `ncu -i X.ncu-rep --page source --csv` (needs --import-source on / -lineinfo).
+
+  ncu -i rep.ncu-rep --page source --csv > src.csv
+  python profiles/hotlines.py src.csv 12,14 25      # blocks 12 and 14 (every launch appears twice in the csv), top 25 lines
+
+Per block: total warp-stall samples, the stall-reason totals, and per line its samples, the two dominant stall reasons and
+the theoretical / ideal L2 sectors (uncoalesced accesses show a ratio > 1).  Samples cover ALL warps of the CTA, so spinning
+waiters (idle role warps, the final barrier) show up next to the real hot spots."""
 import csv, sys
 rows=list(csv.reader(open(sys.argv[1])))
 blocks=[]; cur=None
